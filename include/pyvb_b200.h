@@ -1,0 +1,152 @@
+/*
+ * pyvb_b200 -- C-ABI of the B200-native VB-PCA (missing data) hot path.
+ *
+ * Plain C symbols, raw DEVICE pointers (unless marked host), explicit CUDA stream
+ * (passed as void* = cudaStream_t), no hidden allocation: every workspace is
+ * passed in and sized by a *_len / *_bytes query.  Every entry point returns 0 on
+ * success or a negative PYVB_E* code; pyvb_last_error() gives the text.  No
+ * exceptions, no torch types.
+ *
+ * Each entry point replaces a piece of the reference's message-passing update
+ * (paths relative to /root/reference/src/pyvb):
+ *
+ *   pyvb_pack_gw_f64     nodes/node.py:214-224      <w_i w_j^T> + Cov(w_i) per data dimension, packed
+ *   pyvb_zstep_f64       nodes/node.py:203-227      m1 = tr(<w_i w_j^T> Lambda_n), m2 = <W>^T sum_m2   (K1)
+ *                        nodes/gaussian.py:112-123  qprec, cho_factor, cho_solve, qmu, q_ln_det         (K2)
+ *   pyvb_stats_f64       nodes/nodes_todo.py:50-61  hstack sufficient statistics over all rows         (K3)
+ *                        nodes/nodes_todo.py:136-138, nodes/gaussian.py:141-151  residual / ELBO sums  (K4)
+ *   pyvb_wupdate_f64     nodes/nodes_todo.py:53-62 + nodes/gaussian.py:117-123  one W column at a time
+ *   pyvb_global_f64      nodes/node.py:105-109 (Mu), nodes/nodes_todo.py:130-157 (Gamma update, bounds),
+ *                        nodes/gaussian.py:136-151 (Gaussian bounds), network.py:49 (ELBO sum)
+ *   pyvb_impute_f64      nodes/gaussian.py:125-134  partially observed X_n (mode A imputation)
+ *
+ * Layouts (all float64, row-major):
+ *   X      [N][ldx]   data; NaN = entry not observed (marginalised)
+ *   Zbar   [N][q]     <z_n>
+ *   M2     [N][P]     <z_n z_n^T>, packed lower triangle p(i,j) = i(i+1)/2 + j (i >= j), P = q(q+1)/2
+ *   Sig    [N][P]     Cov(z_n) packed (optional output)
+ *   logdet [N]        ln prod diag chol(qprec_n)  (= 0.5 ln det)
+ *   Gw     [D][ldg]   cols [0,P) = G_d packed, [P,P+q) = <w_d>, [P+q] = <mu_d>, rest zero padding;
+ *                     ldg = pyvb_gw_pitch(q)
+ *   Wbar, Wvar [D][q] column means / diagonal of the column covariances
+ *   stats  [pyvb_stats_len(D,q)] one contiguous buffer, ready for a single all-reduce(SUM):
+ *            T1 [D][P] = O^T vec<zz^T> | Bst [D][q] = O^T Zbar | Ast [D][q] = (O.X)^T Zbar |
+ *            cnt [D] | colsumX [D] | S [P] = sum_n <zz^T>_n | zsum [q] | scal [PYVB_NSCAL]
+ *   gl     [PYVB_GL_LEN]  device-resident globals (tau lives here so that no host sync is needed)
+ */
+#ifndef PYVB_B200_H
+#define PYVB_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYVB_OK 0
+#define PYVB_EINVAL (-1)   /* bad argument (shape, pitch, null pointer) */
+#define PYVB_ECUDA (-2)    /* CUDA runtime error; see pyvb_last_error() */
+#define PYVB_ENOSUP (-3)   /* shape not supported by the requested algorithm */
+
+#define PYVB_QMAX 64
+
+/* scalar slots at the tail of the stats buffer */
+#define PYVB_NSCAL 16
+#define PYVB_SC_SXX 0        /* sum over observed entries of <x>^2              */
+#define PYVB_SC_SUMV 1       /* sum of imputation variances (mode A)            */
+#define PYVB_SC_NE 2         /* number of observed (effective) entries          */
+#define PYVB_SC_QLDZ 3       /* sum_n 0.5/logdet_n  (gaussian.py:120 quirk)     */
+#define PYVB_SC_LOGDETZ 4    /* sum_n logdet_n                                  */
+#define PYVB_SC_LATQLD 5     /* mode A: sum over all-NaN rows of q_ln_det(X_n)  */
+#define PYVB_SC_NLAT 6       /* mode A: number of all-NaN rows                  */
+#define PYVB_SC_PNMISS 7     /* mode A: missing entries in partially observed rows */
+#define PYVB_SC_PLNV 8       /* mode A: sum ln v over those entries             */
+#define PYVB_SC_NROWS 9
+
+/* device globals */
+#define PYVB_GL_QA 0
+#define PYVB_GL_QB 1
+#define PYVB_GL_TAU 2
+#define PYVB_GL_ELBO 3
+#define PYVB_GL_ELBO_W 4
+#define PYVB_GL_ELBO_MU 5
+#define PYVB_GL_ELBO_Z 6
+#define PYVB_GL_ELBO_X 7
+#define PYVB_GL_ELBO_BETA 8
+#define PYVB_GL_ELBO_ALPHA 9
+#define PYVB_GL_RESID2 10
+#define PYVB_GL_NONPD 11     /* rows whose posterior precision was not positive definite (as a double) */
+#define PYVB_GL_ALPHA 16     /* [64] <alpha_i>  (constant prior precision when ARD is off) */
+#define PYVB_GL_ALQB 80      /* [64] ARD Gamma qb_i */
+#define PYVB_GL_LEN 144
+
+/* pyvb_global_f64 op mask */
+#define PYVB_OP_MU 1
+#define PYVB_OP_BETA 2
+#define PYVB_OP_ALPHA 4
+#define PYVB_OP_ELBO 8
+
+/* algorithm selector for zstep / stats */
+#define PYVB_ALGO_AUTO 0
+#define PYVB_ALGO_GENERIC 1  /* any D, q <= 64; FP64 FMA */
+#define PYVB_ALGO_DMMA 2     /* FP64 tensor-core (DMMA) + TMA bulk staging; q in {8,16,32}, D % 16 == 0 */
+
+typedef struct pyvb_consts {
+    double alpha_mu;      /* prior precision of Mu (Constant alpha*I)                    */
+    double a0, b0;        /* noise Gamma prior                                           */
+    double psi_qa;        /* digamma(qa), lgamma(qa), lgamma(a0): qa is fixed, host-computed */
+    double lgam_qa;
+    double lgam_a0;
+    double ard_a0, ard_b0;
+    double al_qa;         /* ARD: a0 + D/2 */
+    double psi_alqa, lgam_alqa, lgam_ard_a0;
+    double lndet_P0;      /* Z prior N(m0, P0^-1): ln det P0 and m0^T P0 m0              */
+    double m0P0m0;
+    int ard;              /* 1: W columns have Gamma (ARD) precisions                    */
+    int mode_a;           /* 1: reference-exact imputation mode (adds the X entropy terms) */
+} pyvb_consts;
+
+int pyvb_version(void);
+const char *pyvb_last_error(void);
+
+/* sizes */
+int pyvb_gw_pitch(int q);                              /* doubles per Gw row */
+size_t pyvb_stats_len(int D, int q);                   /* doubles */
+size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo);
+int pyvb_algo_supported(int algo, int D, int q);       /* 1/0 */
+
+int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu,
+                     double *Gw, int ldg, void *stream);
+
+/* K1+K2 for rows [0,N): reads X, Gw, tau = gl[PYVB_GL_TAU]; P0 [q][q] and h0 = P0 m0 [q] are the
+ * (constant) prior of z.  Sig may be NULL.  Non-PD rows are counted into gl[PYVB_GL_NONPD]. */
+int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
+                   const double *P0, const double *h0, double *gl,
+                   double *Zbar, double *M2, double *Sig, double *logdet, int algo, void *stream);
+
+/* K3+K4 over rows [0,N) into `stats` (fully overwritten).  V, Xorig, qldX are mode-A only (NULL in
+ * mode B).  ws: pyvb_stats_workspace_bytes(). */
+int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
+                   const double *Xorig, const double *qldX, const double *Zbar, const double *M2,
+                   const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo, void *stream);
+
+/* Gauss-Seidel update of W columns [col_lo, col_hi) from the (all-reduced) stats. */
+int pyvb_wupdate_f64(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
+                     const double *gl, double *Wbar, double *Wvar, void *stream);
+
+/* Replicated small updates + ELBO; ops = OR of PYVB_OP_*.  PYVB_OP_ALPHA updates the ARD Gammas of
+ * columns [col_lo, col_hi).  P0/h0 as in zstep.  elbo_out may be NULL. */
+int pyvb_global_f64(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,
+                    double *mu, double *muvar, double *gl, const double *P0, const double *h0,
+                    const pyvb_consts *consts /* host */, double *elbo_out, void *stream);
+
+/* Mode A: x_hat = observed ? x : W zbar + mu, v = observed ? 0 : 1/tau for rows [0,N) that are not
+ * fully observed (pointers already offset to the first row). */
+int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
+                    const double *mu, const double *Zbar, const double *gl,
+                    double *Xhat, double *V, double *qldX, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

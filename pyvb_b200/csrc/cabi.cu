@@ -1,0 +1,164 @@
+// extern "C" boundary of libpyvb_b200.so -- see include/pyvb_b200.h for the contract.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace pyvb;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, const char *detail) {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return PYVB_ECUDA;
+}
+#define ARG(cond, what)                                             \
+    do {                                                            \
+        if (!(cond)) return fail(PYVB_EINVAL, "bad argument: %s", what); \
+    } while (0)
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int pick_algo(int algo, int D, int q) {
+    if (algo == PYVB_ALGO_AUTO) return dmma_supported(D, q) ? PYVB_ALGO_DMMA : PYVB_ALGO_GENERIC;
+    return algo;
+}
+
+extern "C" {
+
+int pyvb_version(void) { return 100; }
+const char *pyvb_last_error(void) { return g_err; }
+
+int pyvb_gw_pitch(int q) {
+    // P + q + 1 used columns; pitch*8 bytes must be = 32 or 96 (mod 128) so that the four k-rows of a
+    // DMMA B fragment fall into distinct shared-memory bank groups, and a multiple of 16 bytes for
+    // bulk (TMA) copies.  => pitch = 4 (mod 8) ... choose the smallest such pitch >= P+q+1.
+    const int used = q * (q + 1) / 2 + q + 1;
+    int p = used;
+    while ((p % 8) != 4) ++p;
+    return p;
+}
+
+size_t pyvb_stats_len(int D, int q) { return StatLayout(D, q).len; }
+
+int pyvb_algo_supported(int algo, int D, int q) {
+    if (q < 1 || q > PYVB_QMAX || D < 1) return 0;
+    if (algo == PYVB_ALGO_GENERIC || algo == PYVB_ALGO_AUTO) return 1;
+    if (algo == PYVB_ALGO_DMMA) return dmma_supported(D, q) ? 1 : 0;
+    return 0;
+}
+
+size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo) {
+    const StatLayout L(D, q);
+    int nch = stats_generic_nchunks(N);
+    if (pick_algo(algo, D, q) == PYVB_ALGO_DMMA) {
+        const int n2 = stats_dmma_nchunks(N, D, q);
+        if (n2 > nch) nch = n2;
+    }
+    return align256((size_t)nch * L.len * sizeof(double)) +
+           align256((size_t)rowscalars_nblk(N) * PYVB_NSCAL * sizeof(double));
+}
+
+int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu, double *Gw, int ldg,
+                     void *stream) {
+    ARG(D >= 1 && q >= 1 && q <= PYVB_QMAX, "D, q");
+    ARG(Wbar && Wvar && mu && Gw, "null pointer");
+    ARG(ldg >= q * (q + 1) / 2 + q + 1, "ldg");
+    cudaError_t e = launch_pack_gw(D, q, Wbar, Wvar, mu, Gw, ldg, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "pack_gw");
+}
+
+int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
+                   const double *P0, const double *h0, double *gl, double *Zbar, double *M2, double *Sig,
+                   double *logdet, int algo, void *stream) {
+    ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    ARG(X && Gw && P0 && h0 && gl && Zbar && M2 && logdet, "null pointer");
+    ARG(ldx >= D, "ldx");
+    ARG(ldg >= q * (q + 1) / 2 + q + 1, "ldg");
+    if (N == 0) return PYVB_OK;
+    const int a = pick_algo(algo, D, q);
+    cudaError_t e;
+    if (a == PYVB_ALGO_DMMA) {
+        if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32}, D % 16 == 0");
+        ARG(ldg == pyvb_gw_pitch(q), "ldg must equal pyvb_gw_pitch(q) for the DMMA path");
+        ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
+        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, M2, Sig, logdet, (cudaStream_t)stream);
+    } else if (a == PYVB_ALGO_GENERIC) {
+        e = launch_zstep_generic(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, M2, Sig, logdet,
+                                 (cudaStream_t)stream);
+    } else {
+        return fail(PYVB_EINVAL, "%s", "unknown algo");
+    }
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep");
+}
+
+int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
+                   const double *Xorig, const double *qldX, const double *Zbar, const double *M2,
+                   const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo, void *stream) {
+    ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    ARG(X && Zbar && M2 && logdet && stats && ws, "null pointer");
+    ARG(ldx >= D, "ldx");
+    ARG((Xorig == NULL) || (V != NULL && qldX != NULL), "mode A needs V and qldX with Xorig");
+    ARG(ws_bytes >= pyvb_stats_workspace_bytes(N, D, q, algo), "workspace too small");
+    const StatLayout L(D, q);
+    const int a = pick_algo(algo, D, q);
+    cudaStream_t st = (cudaStream_t)stream;
+    int nch;
+    cudaError_t e;
+    double *ws_main = (double *)ws;
+    if (a == PYVB_ALGO_DMMA) {
+        if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32}, D % 16 == 0");
+        ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
+        nch = stats_dmma_nchunks(N, D, q);
+        e = launch_stats_dmma(N, D, q, X, ldx, Zbar, M2, ws_main, nch, st);
+    } else if (a == PYVB_ALGO_GENERIC) {
+        nch = stats_generic_nchunks(N);
+        e = launch_stats_generic(N, D, q, X, ldx, Zbar, M2, ws_main, nch, st);
+    } else {
+        return fail(PYVB_EINVAL, "%s", "unknown algo");
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "stats");
+    double *ws_sc = (double *)((char *)ws + align256((size_t)nch * L.len * sizeof(double)));
+    const int nblk = rowscalars_nblk(N);
+    e = launch_rowscalars(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc, nblk, st);
+    if (e != cudaSuccess) return cuda_fail(e, "rowscalars");
+    e = launch_stats_reduce(D, q, ws_main, nch, ws_sc, nblk, stats, st);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
+}
+
+int pyvb_wupdate_f64(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu, const double *gl,
+                     double *Wbar, double *Wvar, void *stream) {
+    ARG(D >= 1 && q >= 1 && q <= PYVB_QMAX, "D, q");
+    ARG(0 <= col_lo && col_lo <= col_hi && col_hi <= q, "column range");
+    ARG(stats && mu && gl && Wbar && Wvar, "null pointer");
+    cudaError_t e = launch_wupdate(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "wupdate");
+}
+
+int pyvb_global_f64(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar, double *mu,
+                    double *muvar, double *gl, const double *P0, const double *h0, const pyvb_consts *consts,
+                    double *elbo_out, void *stream) {
+    ARG(D >= 1 && q >= 1 && q <= PYVB_QMAX, "D, q");
+    ARG(stats && Wbar && Wvar && mu && muvar && gl && P0 && h0 && consts, "null pointer");
+    ARG(0 <= col_lo && col_lo <= col_hi && col_hi <= q, "column range");
+    cudaError_t e =
+        launch_global(D, q, ops, col_lo, col_hi, stats, Wbar, Wvar, mu, muvar, gl, P0, h0, *consts, elbo_out, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "global");
+}
+
+int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
+                    const double *mu, const double *Zbar, const double *gl, double *Xhat, double *V, double *qldX,
+                    void *stream) {
+    ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    ARG(Xorig && Wbar && mu && Zbar && gl && Xhat && V && qldX, "null pointer");
+    ARG(ldx >= D, "ldx");
+    cudaError_t e = launch_impute(N, D, q, Xorig, ldx, Wbar, mu, Zbar, gl, Xhat, V, qldX, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "impute");
+}
+
+}  // extern "C"

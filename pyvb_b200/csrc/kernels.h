@@ -1,0 +1,45 @@
+// Internal launch interface between the C-ABI (cabi.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "../../include/pyvb_b200.h"
+
+namespace pyvb {
+
+// ---- generic (any D, q <= 64) ------------------------------------------------
+cudaError_t launch_pack_gw(int D, int q, const double *Wbar, const double *Wvar, const double *mu,
+                           double *Gw, int ldg, cudaStream_t st);
+cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
+                                 int ldg, const double *P0, const double *h0, double *gl, double *Zbar,
+                                 double *M2, double *Sig, double *logdet, cudaStream_t st);
+// main statistics: partial sums for `nchunks` row chunks into ws_main[nchunks][statlen]
+int stats_generic_nchunks(long long N);
+cudaError_t launch_stats_generic(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
+                                 const double *M2, double *ws_main, int nchunks, cudaStream_t st);
+// per-row scalars: partial sums into ws_sc[nblk][PYVB_NSCAL]
+int rowscalars_nblk(long long N);
+cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx, const double *V,
+                              const double *Xorig, const double *qldX, const double *logdet, double *ws_sc,
+                              int nblk, cudaStream_t st);
+cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
+                                double *stats, cudaStream_t st);
+cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
+                           const double *gl, double *Wbar, double *Wvar, cudaStream_t st);
+cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,
+                          double *mu, double *muvar, double *gl, const double *P0, const double *h0,
+                          const pyvb_consts &c, double *elbo_out, cudaStream_t st);
+cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
+                          const double *mu, const double *Zbar, const double *gl, double *Xhat, double *V,
+                          double *qldX, cudaStream_t st);
+
+// ---- FP64 tensor-core (DMMA) + TMA-bulk kernels -------------------------------
+bool dmma_supported(int D, int q);
+cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
+                              int ldg, const double *P0, const double *h0, double *gl, double *Zbar,
+                              double *M2, double *Sig, double *logdet, cudaStream_t st);
+int stats_dmma_nchunks(long long N, int D, int q);
+cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
+                              const double *M2, double *ws_main, int nchunks, cudaStream_t st);
+
+}  // namespace pyvb

@@ -1,0 +1,615 @@
+// Generic FP64 kernels of the VB-PCA hot path: any D, any q <= 64.
+//
+// They are the correctness path for odd shapes (the shipped workload is D=5, q=2)
+// and host the small replicated updates (W columns, Mu, Gamma, ELBO).  The
+// throughput path for q in {8,16,32}, D % 16 == 0 is kernels_dmma.cu.
+//
+// Reference arithmetic restated here (paths under /root/reference/src/pyvb):
+//   zstep   : nodes/node.py:203-227 (m1, m2 for requester z) + nodes/gaussian.py:117-123
+//   stats   : nodes/nodes_todo.py:50-61 (hstack sums), nodes/nodes_todo.py:136-138 (Gamma traces)
+//   wupdate : nodes/nodes_todo.py:53-62 + nodes/gaussian.py:117-123 (diagonal precision)
+//   global  : nodes/node.py:105-109 (Mu), nodes/nodes_todo.py:130-157, nodes/gaussian.py:136-151
+//   impute  : nodes/gaussian.py:125-134
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pyvb {
+
+// =============================================================== pack Gw
+__global__ void pack_gw_kernel(int D, int q, const double *__restrict__ Wbar, const double *__restrict__ Wvar,
+                               const double *__restrict__ mu, double *__restrict__ Gw, int ldg) {
+    const int d = blockIdx.x;
+    if (d >= D) return;
+    const int P = tri(q);
+    const double *w = Wbar + (size_t)d * q;
+    const double *v = Wvar + (size_t)d * q;
+    double *g = Gw + (size_t)d * ldg;
+    for (int idx = threadIdx.x; idx < q * q; idx += blockDim.x) {
+        const int i = idx / q, j = idx % q;
+        if (j <= i) {
+            double val = w[i] * w[j];
+            if (i == j) val += v[i];
+            g[tri(i) + j] = val;
+        }
+    }
+    for (int c = P + threadIdx.x; c < ldg; c += blockDim.x) {
+        double val = 0.0;
+        if (c < P + q) val = w[c - P];
+        else if (c == P + q) val = mu[d];
+        g[c] = val;
+    }
+}
+
+cudaError_t launch_pack_gw(int D, int q, const double *Wbar, const double *Wvar, const double *mu, double *Gw,
+                           int ldg, cudaStream_t st) {
+    pack_gw_kernel<<<D, 128, 0, st>>>(D, q, Wbar, Wvar, mu, Gw, ldg);
+    return cudaGetLastError();
+}
+
+// =============================================================== Z step (K1+K2), one warp per row
+// In-place "bordering" inverse: row r of the matrix is owned by lane r (and r+32).  At step k the
+// leading k x k block holds the inverse of A[0:k,0:k]; columns > k still hold A (upper triangle only,
+// the strictly lower triangle starts at zero so that not-yet-active rows contribute nothing):
+//     a = A[0:k,k], u = B a, s = A[k,k] - a.u, B' = [[B,0],[0,0]] + [u;-1][u;-1]^T / s
+// The pivots s are those of the Cholesky factorisation, so ln prod diag chol = 0.5 sum ln s.
+template <int NT>
+__global__ void __launch_bounds__(128)
+zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, long long ldx,
+                     const double *__restrict__ Gw, int ldg, const double *__restrict__ P0,
+                     const double *__restrict__ h0, double *gl, double *__restrict__ Zbar,
+                     double *__restrict__ M2, double *__restrict__ Sig, double *__restrict__ logdet) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int P = tri(q), C = P + q;
+    const int pitch = q + 1;
+    const int per_warp = q * pitch + 4 * q;
+    double *a = smem + (size_t)warp * per_warp;
+    double *eta = a + q * pitch;
+    double *av = eta + q;
+    double *uv = av + q;
+    double *zb = uv + q;
+    const double tau = gl[PYVB_GL_TAU];
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (long long n = (long long)blockIdx.x * 4 + warp; n < N; n += (long long)gridDim.x * 4) {
+        double acc[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+        const double *xr = X + n * ldx;
+        for (int d0 = 0; d0 < D; d0 += 32) {
+            const int d = d0 + lane;
+            const double xv = (d < D) ? xr[d] : qnan;
+            const int dmax = min(32, D - d0);
+            for (int dd = 0; dd < dmax; ++dd) {
+                const double x = __shfl_sync(0xffffffffu, xv, dd);
+                if (x != x) continue;  // not observed: warp-uniform
+                const double *g = Gw + (size_t)(d0 + dd) * ldg;
+                const double xm = x - g[P + q];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const int c = lane + 32 * t;
+                    if (c < C) {
+                        const double gv = g[c];
+                        acc[t] += (c < P) ? gv : xm * gv;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const int c = lane + 32 * t;
+            if (c < P) {
+                int i, j;
+                unpack_p(c, i, j);
+                const double val = P0[i * q + j] + tau * acc[t];
+                a[j * pitch + i] = val;               // upper triangle (row j <= col i)
+                if (i != j) a[i * pitch + j] = 0.0;   // strictly lower triangle starts at zero
+            } else if (c < C) {
+                eta[c - P] = h0[c - P] + tau * acc[t];
+            }
+        }
+        double ld = 0.0;
+        bool ok = true;
+        for (int k = 0; k < q; ++k) {
+            __syncwarp();
+            for (int r = lane; r < q; r += 32) av[r] = a[r * pitch + k];
+            __syncwarp();
+            double u_r[2] = {0.0, 0.0};
+            double part = 0.0;
+            {
+                int idx = 0;
+                for (int r = lane; r < q; r += 32, ++idx) {
+                    double u = 0.0;
+                    for (int j = 0; j < k; ++j) u = fma(a[r * pitch + j], av[j], u);
+                    u_r[idx] = u;
+                    if (r != k) part = fma(av[r], u, part);
+                }
+            }
+            const double s = av[k] - warp_sum(part);
+            if (!(s > 0.0)) ok = false;
+            ld += log(s);
+            const double sinv = 1.0 / s;
+            {
+                int idx = 0;
+                for (int r = lane; r < q; r += 32, ++idx) uv[r] = (r == k) ? -1.0 : u_r[idx];
+            }
+            __syncwarp();
+            for (int r = lane; r < q; r += 32) {
+                const double c = uv[r] * sinv;
+                for (int j = 0; j < k; ++j) a[r * pitch + j] = fma(c, uv[j], a[r * pitch + j]);
+                a[r * pitch + k] = -c;
+            }
+        }
+        __syncwarp();
+        for (int r = lane; r < q; r += 32) {
+            double z = 0.0;
+            for (int j = 0; j < q; ++j) z = fma(a[r * pitch + j], eta[j], z);
+            zb[r] = z;
+            Zbar[n * q + r] = z;
+        }
+        __syncwarp();
+        for (int p = lane; p < P; p += 32) {
+            int i, j;
+            unpack_p(p, i, j);
+            const double sg = a[i * pitch + j];
+            M2[n * P + p] = fma(zb[i], zb[j], sg);
+            if (Sig) Sig[n * P + p] = sg;
+        }
+        if (lane == 0) {
+            logdet[n] = 0.5 * ld;
+            if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
+                                 int ldg, const double *P0, const double *h0, double *gl, double *Zbar,
+                                 double *M2, double *Sig, double *logdet, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const int C = tri(q) + q;
+    const int nt = (C + 31) / 32;
+    const size_t smem = (size_t)4 * (q * (q + 1) + 4 * q) * sizeof(double);
+    long long blocks = (N + 3) / 4;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+#define PYVB_LAUNCH_Z(NT)                                                                                      \
+    do {                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(zstep_generic_kernel<NT>,                                         \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (e != cudaSuccess) return e;                                                                        \
+        zstep_generic_kernel<NT><<<(unsigned)blocks, 128, smem, st>>>(N, D, q, X, ldx, Gw, ldg, P0, h0, gl,    \
+                                                                      Zbar, M2, Sig, logdet);                  \
+    } while (0)
+    if (nt <= 1) PYVB_LAUNCH_Z(1);
+    else if (nt <= 2) PYVB_LAUNCH_Z(2);
+    else if (nt <= 5) PYVB_LAUNCH_Z(5);
+    else if (nt <= 18) PYVB_LAUNCH_Z(18);
+    else PYVB_LAUNCH_Z(67);
+#undef PYVB_LAUNCH_Z
+    return cudaGetLastError();
+}
+
+// =============================================================== statistics (K3), generic
+// One thread per output element, rows of a chunk in the inner loop.  Outputs are per-chunk partial
+// sums (deterministic two-stage reduction).
+__global__ void __launch_bounds__(256)
+stats_generic_kernel(long long N, int D, int q, const double *__restrict__ X, long long ldx,
+                     const double *__restrict__ Zbar, const double *__restrict__ M2, double *__restrict__ ws,
+                     long long rows_per_chunk) {
+    const StatLayout L(D, q);
+    const int P = L.P;
+    const int CT = P + 2 * q + 2;
+    const long long nout = (long long)D * CT + P + q;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long r1 = min(N, r0 + rows_per_chunk);
+    double *out = ws + (size_t)blockIdx.y * L.len;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < nout;
+         o += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        size_t dest;
+        if (o < (long long)D * CT) {
+            const int d = (int)(o / CT), c = (int)(o % CT);
+            if (c < P) {
+                for (long long n = r0; n < r1; ++n) {
+                    const double x = X[n * ldx + d];
+                    if (x == x) acc += M2[n * P + c];
+                }
+                dest = L.t1 + (size_t)d * P + c;
+            } else if (c < P + q) {
+                const int i = c - P;
+                for (long long n = r0; n < r1; ++n) {
+                    const double x = X[n * ldx + d];
+                    if (x == x) acc += Zbar[n * q + i];
+                }
+                dest = L.bst + (size_t)d * q + i;
+            } else if (c < P + 2 * q) {
+                const int i = c - P - q;
+                for (long long n = r0; n < r1; ++n) {
+                    const double x = X[n * ldx + d];
+                    if (x == x) acc = fma(x, Zbar[n * q + i], acc);
+                }
+                dest = L.ast + (size_t)d * q + i;
+            } else if (c == P + 2 * q) {
+                for (long long n = r0; n < r1; ++n) {
+                    const double x = X[n * ldx + d];
+                    if (x == x) acc += 1.0;
+                }
+                dest = L.cnt + d;
+            } else {
+                for (long long n = r0; n < r1; ++n) {
+                    const double x = X[n * ldx + d];
+                    if (x == x) acc += x;
+                }
+                dest = L.colx + d;
+            }
+        } else {
+            const int c = (int)(o - (long long)D * CT);
+            if (c < P) {
+                for (long long n = r0; n < r1; ++n) acc += M2[n * P + c];
+                dest = L.S + c;
+            } else {
+                for (long long n = r0; n < r1; ++n) acc += Zbar[n * q + (c - P)];
+                dest = L.zsum + (c - P);
+            }
+        }
+        out[dest] = acc;
+    }
+}
+
+int stats_generic_nchunks(long long N) {
+    long long c = (N + 255) / 256;
+    if (c < 1) c = 1;
+    if (c > 64) c = 64;
+    return (int)c;
+}
+
+cudaError_t launch_stats_generic(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
+                                 const double *M2, double *ws_main, int nchunks, cudaStream_t st) {
+    const int P = tri(q);
+    const long long nout = (long long)D * (P + 2 * q + 2) + P + q;
+    long long bx = (nout + 255) / 256;
+    if (bx > 4096) bx = 4096;
+    const long long rpc = (N + nchunks - 1) / nchunks;
+    dim3 grid((unsigned)bx, (unsigned)nchunks);
+    stats_generic_kernel<<<grid, 256, 0, st>>>(N, D, q, X, ldx, Zbar, M2, ws_main, rpc > 0 ? rpc : 1);
+    return cudaGetLastError();
+}
+
+// =============================================================== per-row scalars (K4)
+__global__ void __launch_bounds__(256)
+rowscalars_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ V,
+                  const double *__restrict__ Xorig, const double *__restrict__ qldX,
+                  const double *__restrict__ logdet, double *__restrict__ ws_sc) {
+    __shared__ double sh[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    double sxx = 0, sumv = 0, ne = 0, qz = 0, ldz = 0, latq = 0, nlat = 0, pnm = 0, plnv = 0, nrows = 0;
+    for (long long n = (long long)blockIdx.x * nwarp + warp; n < N; n += (long long)gridDim.x * nwarp) {
+        const double *xr = X + n * ldx;
+        int nmiss = 0;
+        double lnv = 0.0;
+        for (int d = lane; d < D; d += 32) {
+            const double x = xr[d];
+            if (x == x) {
+                sxx = fma(x, x, sxx);
+                ne += 1.0;
+                if (V) sumv += V[n * (long long)D + d];
+            }
+            if (Xorig) {
+                const double xo = Xorig[n * ldx + d];
+                if (xo != xo) {
+                    ++nmiss;
+                    lnv += log(V[n * (long long)D + d]);
+                }
+            }
+        }
+        if (Xorig) {
+            nmiss = __reduce_add_sync(0xffffffffu, nmiss);
+            if (nmiss == D) {
+                if (lane == 0) {
+                    nlat += 1.0;
+                    latq += qldX[n];
+                }
+            } else if (nmiss > 0) {
+                plnv += lnv;
+                if (lane == 0) pnm += (double)nmiss;
+            }
+        }
+        if (lane == 0) {
+            const double l = logdet[n];
+            qz += 0.5 / l;
+            ldz += l;
+            nrows += 1.0;
+        }
+    }
+    double *out = ws_sc + (size_t)blockIdx.x * PYVB_NSCAL;
+    double r;
+    r = block_sum(sxx, sh);   if (threadIdx.x == 0) out[PYVB_SC_SXX] = r;
+    r = block_sum(sumv, sh);  if (threadIdx.x == 0) out[PYVB_SC_SUMV] = r;
+    r = block_sum(ne, sh);    if (threadIdx.x == 0) out[PYVB_SC_NE] = r;
+    r = block_sum(qz, sh);    if (threadIdx.x == 0) out[PYVB_SC_QLDZ] = r;
+    r = block_sum(ldz, sh);   if (threadIdx.x == 0) out[PYVB_SC_LOGDETZ] = r;
+    r = block_sum(latq, sh);  if (threadIdx.x == 0) out[PYVB_SC_LATQLD] = r;
+    r = block_sum(nlat, sh);  if (threadIdx.x == 0) out[PYVB_SC_NLAT] = r;
+    r = block_sum(pnm, sh);   if (threadIdx.x == 0) out[PYVB_SC_PNMISS] = r;
+    r = block_sum(plnv, sh);  if (threadIdx.x == 0) out[PYVB_SC_PLNV] = r;
+    r = block_sum(nrows, sh); if (threadIdx.x == 0) out[PYVB_SC_NROWS] = r;
+    if (threadIdx.x == 0)
+        for (int k = PYVB_SC_NROWS + 1; k < PYVB_NSCAL; ++k) out[k] = 0.0;
+}
+
+int rowscalars_nblk(long long N) {
+    long long b = (N + 7) / 8;
+    if (b < 1) b = 1;
+    if (b > 148 * 4) b = 148 * 4;
+    return (int)b;
+}
+
+cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx, const double *V,
+                              const double *Xorig, const double *qldX, const double *logdet, double *ws_sc,
+                              int nblk, cudaStream_t st) {
+    rowscalars_kernel<<<nblk, 256, 0, st>>>(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc);
+    return cudaGetLastError();
+}
+
+// =============================================================== deterministic second stage
+__global__ void __launch_bounds__(256)
+stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunks, const double *__restrict__ ws_sc,
+                    int nblk, double *__restrict__ stats) {
+    const StatLayout L(D, q);
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < L.len; o += (size_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        if (o < L.scal) {
+            for (int c = 0; c < nchunks; ++c) acc += ws_main[(size_t)c * L.len + o];
+        } else {
+            const size_t k = o - L.scal;
+            for (int b = 0; b < nblk; ++b) acc += ws_sc[(size_t)b * PYVB_NSCAL + k];
+        }
+        stats[o] = acc;
+    }
+}
+
+cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
+                                double *stats, cudaStream_t st) {
+    const StatLayout L(D, q);
+    size_t b = (L.len + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats);
+    return cudaGetLastError();
+}
+
+// =============================================================== W columns (Gauss-Seidel), thread per d
+__global__ void __launch_bounds__(128)
+wupdate_kernel(int D, int q, int col_lo, int col_hi, const double *__restrict__ stats,
+               const double *__restrict__ mu, const double *__restrict__ gl, double *__restrict__ Wbar,
+               double *__restrict__ Wvar) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const StatLayout L(D, q);
+    const int P = L.P;
+    const double tau = gl[PYVB_GL_TAU];
+    const double *T1 = stats + L.t1 + (size_t)d * P;
+    const double *Bst = stats + L.bst + (size_t)d * q;
+    const double *Ast = stats + L.ast + (size_t)d * q;
+    double w[PYVB_QMAX];
+    for (int i = 0; i < q; ++i) w[i] = Wbar[(size_t)d * q + i];
+    const double m = mu[d];
+    for (int i = col_lo; i < col_hi; ++i) {
+        const double prec = gl[PYVB_GL_ALPHA + i] + tau * T1[tri(i) + i];
+        double m2 = Ast[i] - m * Bst[i];
+        for (int j = 0; j < i; ++j) m2 = fma(-T1[tri(i) + j], w[j], m2);
+        for (int j = i + 1; j < q; ++j) m2 = fma(-T1[tri(j) + i], w[j], m2);
+        w[i] = tau * m2 / prec;
+        Wvar[(size_t)d * q + i] = 1.0 / prec;
+    }
+    for (int i = col_lo; i < col_hi; ++i) Wbar[(size_t)d * q + i] = w[i];
+}
+
+cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
+                           const double *gl, double *Wbar, double *Wvar, cudaStream_t st) {
+    wupdate_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar);
+    return cudaGetLastError();
+}
+
+// =============================================================== Mu, Gamma(s), ELBO: one CTA
+__global__ void __launch_bounds__(1024)
+global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__restrict__ stats, const double *__restrict__ Wbar,
+              const double *__restrict__ Wvar, double *mu, double *muvar, double *gl,
+              const double *__restrict__ P0, const double *__restrict__ h0, const pyvb_consts c,
+              double *elbo_out) {
+    __shared__ double sh[33];
+    const StatLayout L(D, q);
+    const int P = L.P;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double *T1 = stats + L.t1, *Bst = stats + L.bst, *Ast = stats + L.ast;
+    const double *cnt = stats + L.cnt, *colx = stats + L.colx, *S = stats + L.S, *zsum = stats + L.zsum;
+    const double *sc = stats + L.scal;
+    const double LN2PI = 1.8378770664093454835606594728112;
+    const double qa = gl[PYVB_GL_QA];
+    double qb = gl[PYVB_GL_QB];
+    double tau = gl[PYVB_GL_TAU];
+    __syncthreads();
+
+    if (ops & PYVB_OP_MU) {
+        for (int d = tid; d < D; d += nt) {
+            const double prec = c.alpha_mu + tau * cnt[d];
+            double s = colx[d];
+            for (int i = 0; i < q; ++i) s = fma(-Bst[(size_t)d * q + i], Wbar[(size_t)d * q + i], s);
+            mu[d] = tau * s / prec;
+            muvar[d] = 1.0 / prec;
+        }
+        __syncthreads();
+    }
+    if ((ops & PYVB_OP_ALPHA) && c.ard) {
+        for (int i = col_lo; i < col_hi; ++i) {
+            double part = 0.0;
+            for (int d = tid; d < D; d += nt) {
+                const double w = Wbar[(size_t)d * q + i];
+                part += fma(w, w, Wvar[(size_t)d * q + i]);
+            }
+            const double tot = block_sum(part, sh);
+            if (tid == 0) {
+                const double b = c.ard_b0 + 0.5 * tot;
+                gl[PYVB_GL_ALQB + i] = b;
+                gl[PYVB_GL_ALPHA + i] = c.al_qa / b;
+            }
+        }
+        __syncthreads();
+    }
+    double resid2 = 0.0;
+    if (ops & (PYVB_OP_BETA | PYVB_OP_ELBO)) {
+        double part = 0.0;
+        for (int d = tid; d < D; d += nt) {
+            double s1 = 0.0, s2 = 0.0;
+            for (int i = 0; i < q; ++i) {
+                const double w = Wbar[(size_t)d * q + i];
+                s1 = fma(w, Ast[(size_t)d * q + i], s1);
+                s2 = fma(w, Bst[(size_t)d * q + i], s2);
+            }
+            const double m = mu[d];
+            part += -2.0 * (s1 + m * colx[d]) + 2.0 * m * s2 + cnt[d] * (m * m + muvar[d]);
+        }
+        for (long long idx = tid; idx < (long long)D * P; idx += nt) {
+            const int d = (int)(idx / P), p = (int)(idx % P);
+            int i, j;
+            unpack_p(p, i, j);
+            double g = Wbar[(size_t)d * q + i] * Wbar[(size_t)d * q + j];
+            if (i == j) g += Wvar[(size_t)d * q + i];
+            else g *= 2.0;
+            part = fma(g, T1[idx], part);
+        }
+        resid2 = block_sum(part, sh) + sc[PYVB_SC_SXX] + sc[PYVB_SC_SUMV];
+        if (ops & PYVB_OP_BETA) {
+            qb = c.b0 + 0.5 * resid2;
+            tau = qa / qb;
+        }
+        if (tid == 0) {
+            gl[PYVB_GL_RESID2] = resid2;
+            if (ops & PYVB_OP_BETA) {
+                gl[PYVB_GL_QB] = qb;
+                gl[PYVB_GL_TAU] = tau;
+            }
+        }
+    }
+    if (ops & PYVB_OP_ELBO) {
+        __syncthreads();
+        // ---- W columns (gaussian.py:141-147; q_ln_det = .5/ln prod diag chol is a division)
+        double eW = 0.0;
+        for (int i = 0; i < q; ++i) {
+            double pw = 0.0, pl = 0.0;
+            for (int d = tid; d < D; d += nt) {
+                const double w = Wbar[(size_t)d * q + i], v = Wvar[(size_t)d * q + i];
+                pw += fma(w, w, v);
+                pl += log(v);
+            }
+            const double ww = block_sum(pw, sh);
+            const double lv = block_sum(pl, sh);
+            const double qld = 0.5 / (-0.5 * lv);
+            const double al = gl[PYVB_GL_ALPHA + i];
+            const double lndet = c.ard ? D * (log(c.al_qa) - log(gl[PYVB_GL_ALQB + i])) : D * log(al);
+            eW += -0.5 * D * LN2PI + 0.5 * lndet - 0.5 * al * ww - (-0.5 * D * LN2PI - 0.5 * qld - 0.5 * D);
+        }
+        // ---- Mu
+        double pm = 0.0, pl = 0.0;
+        for (int d = tid; d < D; d += nt) {
+            pm += fma(mu[d], mu[d], muvar[d]);
+            pl += log(muvar[d]);
+        }
+        const double mm = block_sum(pm, sh);
+        const double lvm = block_sum(pl, sh);
+        const double qldm = 0.5 / (-0.5 * lvm);
+        const double eMu = -0.5 * D * LN2PI + 0.5 * D * log(c.alpha_mu) - 0.5 * c.alpha_mu * mm -
+                           (-0.5 * D * LN2PI - 0.5 * qldm - 0.5 * D);
+        // ---- Z rows
+        double pt = 0.0, pz = 0.0;
+        for (int idx = tid; idx < q * q; idx += nt) {
+            const int i = idx / q, j = idx % q;
+            const int p = (i >= j) ? tri(i) + j : tri(j) + i;
+            pt = fma(P0[idx], S[p], pt);
+        }
+        for (int i = tid; i < q; i += nt) pz = fma(zsum[i], h0[i], pz);
+        const double trPS = block_sum(pt, sh);
+        const double zh = block_sum(pz, sh);
+        const double nrows = sc[PYVB_SC_NROWS];
+        const double eZ = nrows * (-0.5 * q * LN2PI + 0.5 * c.lndet_P0 - 0.5 * c.m0P0m0 + 0.5 * q * LN2PI + 0.5 * q) -
+                          0.5 * trPS + zh + 0.5 * sc[PYVB_SC_QLDZ];
+        // ---- X rows (nodes_todo.py:144-147 uses ln<tau>)
+        const double nE = sc[PYVB_SC_NE];
+        double eX = -0.5 * nE * LN2PI + 0.5 * nE * (log(qa) - log(qb)) - 0.5 * tau * resid2;
+        if (c.mode_a) {
+            eX -= sc[PYVB_SC_NLAT] * (-0.5 * D * LN2PI - 0.5 * D) - 0.5 * sc[PYVB_SC_LATQLD];
+            eX -= 0.5 * sc[PYVB_SC_PNMISS] * LN2PI - 0.5 * sc[PYVB_SC_PLNV] - 0.5 * sc[PYVB_SC_PNMISS];
+        }
+        // ---- Gammas (nodes_todo.py:149-157)
+        const double El = c.psi_qa - log(qb);
+        const double eB = (c.a0 - 1.0) * El - c.lgam_a0 + c.a0 * log(c.b0) - c.b0 * (qa / qb) -
+                          ((qa - 1.0) * El - c.lgam_qa + qa * log(qb) - qa);
+        double eA = 0.0;
+        if (c.ard) {
+            for (int i = 0; i < q; ++i) {
+                const double b = gl[PYVB_GL_ALQB + i];
+                const double E2 = c.psi_alqa - log(b);
+                eA += (c.ard_a0 - 1.0) * E2 - c.lgam_ard_a0 + c.ard_a0 * log(c.ard_b0) - c.ard_b0 * (c.al_qa / b) -
+                      ((c.al_qa - 1.0) * E2 - c.lgam_alqa + c.al_qa * log(b) - c.al_qa);
+            }
+        }
+        if (tid == 0) {
+            const double e = eW + eMu + eZ + eX + eB + eA;
+            gl[PYVB_GL_ELBO] = e;
+            gl[PYVB_GL_ELBO_W] = eW;
+            gl[PYVB_GL_ELBO_MU] = eMu;
+            gl[PYVB_GL_ELBO_Z] = eZ;
+            gl[PYVB_GL_ELBO_X] = eX;
+            gl[PYVB_GL_ELBO_BETA] = eB;
+            gl[PYVB_GL_ELBO_ALPHA] = eA;
+            if (elbo_out) *elbo_out = e;
+        }
+    }
+}
+
+cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,
+                          double *mu, double *muvar, double *gl, const double *P0, const double *h0,
+                          const pyvb_consts &c, double *elbo_out, cudaStream_t st) {
+    global_kernel<<<1, 1024, 0, st>>>(D, q, ops, col_lo, col_hi, stats, Wbar, Wvar, mu, muvar, gl, P0, h0, c, elbo_out);
+    return cudaGetLastError();
+}
+
+// =============================================================== mode A imputation, warp per row
+__global__ void __launch_bounds__(256)
+impute_kernel(long long N, int D, int q, const double *__restrict__ Xorig, long long ldx,
+              const double *__restrict__ Wbar, const double *__restrict__ mu, const double *__restrict__ Zbar,
+              const double *__restrict__ gl, double *__restrict__ Xhat, double *__restrict__ V,
+              double *__restrict__ qldX) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double tau = gl[PYVB_GL_TAU];
+    const double vmiss = 1.0 / tau;
+    for (long long n = (long long)blockIdx.x * nwarp + warp; n < N; n += (long long)gridDim.x * nwarp) {
+        const double *xo = Xorig + n * ldx;
+        int nmiss = 0;
+        for (int d = lane; d < D; d += 32) nmiss += (xo[d] != xo[d]) ? 1 : 0;
+        nmiss = __reduce_add_sync(0xffffffffu, nmiss);
+        if (nmiss == 0) continue;  // fully observed rows are never updated (gaussian.py:109-110)
+        const double *z = Zbar + n * q;
+        for (int d = lane; d < D; d += 32) {
+            const double x = xo[d];
+            const bool miss = (x != x);
+            double m = mu[d];
+            for (int i = 0; i < q; ++i) m = fma(Wbar[(size_t)d * q + i], z[i], m);
+            Xhat[n * (long long)D + d] = miss ? m : x;
+            V[n * (long long)D + d] = miss ? vmiss : 0.0;
+        }
+        if (lane == 0) qldX[n] = 0.5 / (0.5 * D * log(tau));
+    }
+}
+
+cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
+                          const double *mu, const double *Zbar, const double *gl, double *Xhat, double *V,
+                          double *qldX, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    long long b = (N + 7) / 8;
+    if (b > 148 * 8) b = 148 * 8;
+    impute_kernel<<<(unsigned)b, 256, 0, st>>>(N, D, q, Xorig, ldx, Wbar, mu, Zbar, gl, Xhat, V, qldX);
+    return cudaGetLastError();
+}
+
+}  // namespace pyvb

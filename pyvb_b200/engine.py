@@ -1,0 +1,373 @@
+"""Plate engine: device-resident state of the VB-PCA (missing data) model and the update
+operators, each one a call into the CUDA C-ABI (include/pyvb_b200.h).
+
+This is the host side of the hot path.  It mirrors, as batched "plate" operators, the
+per-node methods of the reference (paths under /root/reference/src/pyvb):
+
+    update_W(i0,i1)  <-  Gaussian.update on W_i          nodes/gaussian.py:102-123 + nodes/nodes_todo.py:43-62
+    update_Z(lo,hi)  <-  Gaussian.update on Z_n          nodes/gaussian.py:102-123 + nodes/node.py:182-232
+    update_X(lo,hi)  <-  Gaussian.update on partial X_n  nodes/gaussian.py:125-134           (mode A only)
+    update_Mu()      <-  Gaussian.update on Mu           nodes/node.py:95-110
+    update_Beta()    <-  Gamma.update                    nodes/nodes_todo.py:130-138
+    update_Alpha()   <-  Gamma.update on ARD precisions  nodes/nodes_todo.py:130-138
+    elbo()           <-  sum of log_lower_bound()        network.py:49
+    iterate()        <-  one sweep in Network.learn order network.py:46-48
+
+PyTorch is used for device memory, streams and torch.distributed only.  Rows shard across
+ranks; the only exchange is one all-reduce(SUM) of the packed statistics buffer per sweep.
+There is no CPU fallback: without the CUDA library or a GPU the constructor raises.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_LEN, GL_NONPD, GL_QA,
+                      GL_QB, GL_TAU, OP_ALPHA, OP_BETA, OP_ELBO, OP_MU, QMAX, StatLayout)
+
+_ALGOS = {"auto": ALGO_AUTO, "generic": ALGO_GENERIC, "dmma": ALGO_DMMA}
+
+
+def _digamma(x):
+    try:
+        from scipy import special
+        return float(special.digamma(x))
+    except Exception:  # pragma: no cover
+        return float(torch.special.digamma(torch.tensor(x, dtype=torch.float64)))
+
+
+def tril_pack_index(q):
+    ii, jj = np.tril_indices(q)
+    return ii, jj
+
+
+class PlateEngine(object):
+    """VB-PCA plate on one GPU (one process per GPU; rows sharded when torch.distributed is up).
+
+    Parameters
+    ----------
+    X : (N, D) array or tensor, NaN = missing.  The local row shard.
+    q : latent dimension (<= 64)
+    mode : "B" masked/marginalised (throughput path) or "A" reference-exact imputation
+    distributed : all-reduce the statistics over torch.distributed's default group
+    row_offset : global index of local row 0 (mode A treats global row 0 specially)
+    """
+
+    def __init__(self, X, q, mode="B", alpha0=1e-3, alpha_mu=1e-3, a0=1e-3, b0=1e-3, ard=False,
+                 ard_a0=1e-3, ard_b0=1e-3, P0=None, m0=None, device=None, algo="auto",
+                 keep_sigma=True, distributed=False, row_offset=0, trace_len=4096):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyvb_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _cabi.lib()
+        assert mode in ("A", "B")
+        assert 1 <= q <= QMAX, "latent dimension must be in [1, %d]" % QMAX
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.mode, self.q, self.ard = mode, int(q), bool(ard)
+        self.algo = _ALGOS[algo] if isinstance(algo, str) else int(algo)
+        self.distributed = bool(distributed)
+        self.row_offset = int(row_offset)
+        f64 = torch.float64
+        dev = self.device
+        Xt = torch.as_tensor(X)
+        assert Xt.dim() == 2
+        Xt = Xt.to(device=dev, dtype=f64).contiguous()
+        self.N, self.D = int(Xt.shape[0]), int(Xt.shape[1])
+        N, D = self.N, self.D
+        self.P = q * (q + 1) // 2
+        self.L = StatLayout(D, q)
+        self.alpha0, self.alpha_mu = float(alpha0), float(alpha_mu)
+        self.a0, self.b0 = float(a0), float(b0)
+        self.ard_a0, self.ard_b0 = float(ard_a0), float(ard_b0)
+
+        # ---- data
+        obs = ~torch.isnan(Xt)
+        n_obs_local = int(obs.sum().item())
+        if mode == "A":
+            self.Xorig = Xt
+            self.X = torch.where(obs, Xt, torch.zeros((), dtype=f64, device=dev)).contiguous()   # Xhat
+            self.V = torch.where(obs, torch.zeros((), dtype=f64, device=dev),
+                                 torch.ones((), dtype=f64, device=dev)).contiguous()
+            self.qldX = torch.zeros(N, dtype=f64, device=dev)
+            n_eff_local = N * D               # nodes_todo.py:125-128: every child counts dim/2
+        else:
+            self.Xorig = None
+            self.X = Xt
+            self.V = None
+            self.qldX = None
+            n_eff_local = n_obs_local
+        del obs
+        n_eff = self._allreduce_scalar(float(n_eff_local))
+        self.n_rows_total = int(self._allreduce_scalar(float(N)))
+
+        # ---- latent state
+        self.Zbar = torch.zeros(N, q, dtype=f64, device=dev)
+        self.M2 = torch.zeros(N, self.P, dtype=f64, device=dev)
+        self.Sig = torch.zeros(N, self.P, dtype=f64, device=dev) if keep_sigma else None
+        self.logdet = torch.ones(N, dtype=f64, device=dev)
+        self.Wbar = torch.zeros(D, q, dtype=f64, device=dev)
+        self.Wvar = torch.ones(D, q, dtype=f64, device=dev)
+        self.mu = torch.zeros(D, dtype=f64, device=dev)
+        self.muvar = torch.ones(D, dtype=f64, device=dev)
+        self.ldg = int(self.lib.pyvb_gw_pitch(q))
+        self.Gw = torch.zeros(D, self.ldg, dtype=f64, device=dev)
+        self.stats = torch.zeros(self.L.len, dtype=f64, device=dev)
+        assert self.L.len == int(self.lib.pyvb_stats_len(D, q))
+        self.ws_bytes = int(self.lib.pyvb_stats_workspace_bytes(N, D, q, self.algo))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.gl = torch.zeros(GL_LEN, dtype=f64, device=dev)
+        self.trace = torch.zeros(int(trace_len), dtype=f64, device=dev)
+        self.trace_pos = 0
+
+        # ---- priors
+        P0 = np.eye(q) if P0 is None else np.asarray(P0, dtype=np.float64).reshape(q, q)
+        m0 = np.zeros(q) if m0 is None else np.asarray(m0, dtype=np.float64).reshape(q)
+        self.P0 = torch.as_tensor(P0, dtype=f64).contiguous().to(dev)
+        self.h0 = torch.as_tensor(P0 @ m0, dtype=f64).contiguous().to(dev)
+        qa = self.a0 + 0.5 * n_eff
+        al_qa = self.ard_a0 + 0.5 * D
+        c = _cabi.Consts()
+        c.alpha_mu, c.a0, c.b0 = self.alpha_mu, self.a0, self.b0
+        c.psi_qa, c.lgam_qa, c.lgam_a0 = _digamma(qa), math.lgamma(qa), math.lgamma(self.a0)
+        c.ard_a0, c.ard_b0, c.al_qa = self.ard_a0, self.ard_b0, al_qa
+        c.psi_alqa, c.lgam_alqa, c.lgam_ard_a0 = _digamma(al_qa), math.lgamma(al_qa), math.lgamma(self.ard_a0)
+        c.lndet_P0 = float(np.linalg.slogdet(P0)[1])
+        c.m0P0m0 = float(m0 @ P0 @ m0)
+        c.ard, c.mode_a = int(self.ard), int(mode == "A")
+        self.consts = c
+        self.qa, self.al_qa = qa, al_qa
+
+        # deterministic stand-in initialisation; parity runs call set_state()
+        self.set_state({"qb": 0.5, "al_qb": np.ones(q)})
+        self._stats_fresh = False
+        self._gw_fresh = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _allreduce_scalar(self, v):
+        if self.distributed:
+            import torch.distributed as dist
+            t = torch.tensor([v], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t)
+            return float(t.item())
+        return v
+
+    @staticmethod
+    def _p(t):
+        return 0 if t is None else t.data_ptr()
+
+    # ------------------------------------------------------------------ state io
+    def set_state(self, st):
+        """Inject state (numpy arrays in the oracle's layout: Sig is (N,q,q), qb scalar ...)."""
+        f64, dev = torch.float64, self.device
+        q = self.q
+
+        def put(dst, src):
+            dst.copy_(torch.as_tensor(np.ascontiguousarray(src), dtype=f64).reshape(dst.shape).to(dev))
+
+        for k in ("Wbar", "Wvar", "mu", "muvar", "Zbar"):
+            if k in st:
+                put(getattr(self, k), st[k])
+        if "Xhat" in st and self.mode == "A":
+            put(self.X, st["Xhat"])
+        if "V" in st and self.mode == "A":
+            put(self.V, st["V"])
+        if "Sig" in st or "Zbar" in st:
+            ii, jj = tril_pack_index(q)
+            if "Sig" in st:
+                sig = np.asarray(st["Sig"], dtype=np.float64)[:, ii, jj]
+                sig_t = torch.as_tensor(np.ascontiguousarray(sig), dtype=f64).to(dev)
+            elif self.Sig is not None:
+                sig_t = self.Sig
+            else:
+                raise ValueError("Sig needed")
+            if self.Sig is not None:
+                self.Sig.copy_(sig_t)
+            it, jt = torch.as_tensor(ii, device=dev), torch.as_tensor(jj, device=dev)
+            self.M2.copy_(sig_t + self.Zbar[:, it] * self.Zbar[:, jt])
+        gl = self.gl.cpu()
+        gl[GL_QA] = self.qa
+        if "qb" in st:
+            gl[GL_QB] = float(st["qb"])
+        gl[GL_TAU] = gl[GL_QA] / gl[GL_QB]
+        if self.ard:
+            if "al_qb" in st:
+                gl[GL_ALQB:GL_ALQB + q] = torch.as_tensor(np.asarray(st["al_qb"], dtype=np.float64).reshape(q))
+            gl[GL_ALPHA:GL_ALPHA + q] = self.al_qa / gl[GL_ALQB:GL_ALQB + q]
+        else:
+            gl[GL_ALPHA:GL_ALPHA + q] = self.alpha0
+        self.gl.copy_(gl.to(dev))
+        self._stats_fresh = False
+        self._gw_fresh = False
+
+    def get_state(self):
+        """Host copy of the state in the oracle's layout."""
+        q = self.q
+        ii, jj = tril_pack_index(q)
+        out = {k: getattr(self, k).cpu().numpy() for k in ("Wbar", "Wvar", "mu", "muvar", "Zbar")}
+        N = self.N
+        if self.Sig is not None:
+            sp = self.Sig.cpu().numpy()
+        else:
+            z = out["Zbar"]
+            sp = self.M2.cpu().numpy() - z[:, ii] * z[:, jj]
+        Sig = np.zeros((N, q, q))
+        Sig[:, ii, jj] = sp
+        Sig[:, jj, ii] = sp
+        out["Sig"] = Sig
+        if self.mode == "A":
+            out["Xhat"] = self.X.cpu().numpy()
+            out["V"] = self.V.cpu().numpy()
+        gl = self.gl.cpu().numpy()
+        out["qa"], out["qb"], out["tau"] = float(gl[GL_QA]), float(gl[GL_QB]), float(gl[GL_TAU])
+        out["alpha"] = gl[GL_ALPHA:GL_ALPHA + q].copy()
+        out["al_qb"] = gl[GL_ALQB:GL_ALQB + q].copy()
+        return out
+
+    def check(self):
+        """Raise LinAlgError if any posterior precision was not positive definite (gaussian.py:118)."""
+        if float(self.gl[GL_NONPD].item()) > 0:
+            raise np.linalg.LinAlgError("posterior precision of %d row(s) is not positive definite"
+                                        % int(self.gl[GL_NONPD].item()))
+
+    # ------------------------------------------------------------------ operators
+    def _ensure_gw(self):
+        if not self._gw_fresh:
+            rc = self.lib.pyvb_pack_gw_f64(self.D, self.q, self.Wbar.data_ptr(), self.Wvar.data_ptr(),
+                                           self.mu.data_ptr(), self.Gw.data_ptr(), self.ldg, self._stream())
+            _cabi.check(rc, "pyvb_pack_gw_f64")
+            self._gw_fresh = True
+
+    def _ensure_stats(self):
+        if self._stats_fresh:
+            return
+        rc = self.lib.pyvb_stats_f64(self.N, self.D, self.q, self.X.data_ptr(), self.D, self._p(self.V),
+                                     self._p(self.Xorig), self._p(self.qldX), self.Zbar.data_ptr(),
+                                     self.M2.data_ptr(), self.logdet.data_ptr(), self.stats.data_ptr(),
+                                     self.ws.data_ptr(), self.ws_bytes, self.algo, self._stream())
+        _cabi.check(rc, "pyvb_stats_f64")
+        if self.distributed:
+            import torch.distributed as dist
+            dist.all_reduce(self.stats)          # the ONE collective of a sweep (NCCL over NVLink)
+        self._stats_fresh = True
+
+    def update_W(self, col_lo=0, col_hi=None):
+        col_hi = self.q if col_hi is None else col_hi
+        self._ensure_stats()
+        rc = self.lib.pyvb_wupdate_f64(self.D, self.q, col_lo, col_hi, self.stats.data_ptr(), self.mu.data_ptr(),
+                                       self.gl.data_ptr(), self.Wbar.data_ptr(), self.Wvar.data_ptr(),
+                                       self._stream())
+        _cabi.check(rc, "pyvb_wupdate_f64")
+        self._gw_fresh = False
+
+    def update_Z(self, lo=0, hi=None):
+        hi = self.N if hi is None else hi
+        self._stats_fresh = False
+        if hi <= lo:
+            return
+        self._ensure_gw()
+        q, P, D = self.q, self.P, self.D
+        sig = 0 if self.Sig is None else self.Sig.data_ptr() + lo * P * 8
+        rc = self.lib.pyvb_zstep_f64(hi - lo, D, q, self.X.data_ptr() + lo * D * 8, D, self.Gw.data_ptr(),
+                                     self.ldg, self.P0.data_ptr(), self.h0.data_ptr(), self.gl.data_ptr(),
+                                     self.Zbar.data_ptr() + lo * q * 8, self.M2.data_ptr() + lo * P * 8, sig,
+                                     self.logdet.data_ptr() + lo * 8, self.algo, self._stream())
+        _cabi.check(rc, "pyvb_zstep_f64")
+        self._stats_fresh = False
+
+    def update_X(self, lo=0, hi=None):
+        """Mode A imputation of rows [lo,hi) that are not fully observed; no-op in mode B."""
+        if self.mode != "A":
+            return
+        hi = self.N if hi is None else hi
+        self._stats_fresh = False          # before the early return: every rank must redo the all-reduce
+        if hi <= lo:
+            return
+        q, D = self.q, self.D
+        rc = self.lib.pyvb_impute_f64(hi - lo, D, q, self.Xorig.data_ptr() + lo * D * 8, D, self.Wbar.data_ptr(),
+                                      self.mu.data_ptr(), self.Zbar.data_ptr() + lo * q * 8, self.gl.data_ptr(),
+                                      self.X.data_ptr() + lo * D * 8, self.V.data_ptr() + lo * D * 8,
+                                      self.qldX.data_ptr() + lo * 8, self._stream())
+        _cabi.check(rc, "pyvb_impute_f64")
+        self._stats_fresh = False
+
+    def _global(self, ops, elbo_out=0, col_lo=0, col_hi=None):
+        self._ensure_stats()
+        col_hi = self.q if col_hi is None else col_hi
+        rc = self.lib.pyvb_global_f64(self.D, self.q, ops, col_lo, col_hi, self.stats.data_ptr(), self.Wbar.data_ptr(),
+                                      self.Wvar.data_ptr(), self.mu.data_ptr(), self.muvar.data_ptr(),
+                                      self.gl.data_ptr(), self.P0.data_ptr(), self.h0.data_ptr(),
+                                      _cabi.ctypes.byref(self.consts), elbo_out, self._stream())
+        _cabi.check(rc, "pyvb_global_f64")
+        if ops & OP_MU:
+            self._gw_fresh = False
+
+    def update_Mu(self):
+        self._global(OP_MU)
+
+    def update_Beta(self):
+        self._global(OP_BETA)
+
+    def update_Alpha(self, col_lo=0, col_hi=None):
+        if self.ard:
+            self._global(OP_ALPHA, 0, col_lo, col_hi)
+
+    def elbo_async(self):
+        """Evaluate the bound into the device trace; returns the trace slot (no host sync)."""
+        slot = self.trace_pos % self.trace.numel()
+        self._global(OP_ELBO, self.trace.data_ptr() + slot * 8)
+        self.trace_pos += 1
+        return slot
+
+    def elbo(self):
+        slot = self.elbo_async()
+        return float(self.trace[slot].item())
+
+    # ------------------------------------------------------------------ sweeps
+    def iterate_async(self):
+        """One sweep in the reference's order: W cols, Z rows, [Alpha], X_0, Mu, X_1.., Beta,
+        then the ELBO -- with no host synchronisation.  Returns the trace slot of the bound."""
+        self.update_W()
+        self.update_Z()
+        if self.mode == "A":
+            self.update_Alpha()
+            self.update_X(0, 1 if self.row_offset == 0 else 0)   # global row 0 lives on the first shard
+            self.update_Mu()
+            self.update_X(1 if self.row_offset == 0 else 0, self.N)
+            slot = self.trace_pos % self.trace.numel()
+            self._global(OP_BETA | OP_ELBO, self.trace.data_ptr() + slot * 8)
+            self.trace_pos += 1
+            return slot
+        # mode B: one statistics pass feeds Mu, Alpha, Beta and the bound (and the next W update)
+        slot = self.trace_pos % self.trace.numel()
+        self._global(OP_MU | OP_ALPHA | OP_BETA | OP_ELBO, self.trace.data_ptr() + slot * 8)
+        self.trace_pos += 1
+        return slot
+
+    def iterate(self):
+        slot = self.iterate_async()
+        return float(self.trace[slot].item())
+
+    def learn(self, niters, tol=1e-3, verbose=False):
+        """Network.learn semantics (network.py:40-56): stop as soon as the bound improves by < tol."""
+        old = -np.inf
+        out = []
+        for i in range(niters):
+            llb = self.iterate()
+            out.append(llb)
+            if verbose:
+                print(niters - i, llb)
+            if llb - old < tol:
+                if verbose:
+                    print("Convergence!")
+                break
+            old = llb
+        self.check()
+        return out
+
+    def run(self, niters):
+        """niters sweeps back to back without host syncs; returns the bound trace as a device tensor view."""
+        slots = [self.iterate_async() for _ in range(niters)]
+        return self.trace[slots]
