@@ -26,8 +26,8 @@
  *   M2     [N][P]     <z_n z_n^T>, packed lower triangle p(i,j) = i(i+1)/2 + j (i >= j), P = q(q+1)/2
  *   Sig    [N][P]     Cov(z_n) packed (optional output)
  *   logdet [N]        ln prod diag chol(qprec_n)  (= 0.5 ln det)
- *   Gw     [D][ldg]   cols [0,P) = G_d packed, [P,P+q) = <w_d>, [P+q] = <mu_d>, rest zero padding;
- *                     ldg = pyvb_gw_pitch(q)
+ *   Gw     [D][ldg]   cols [0,P) = G_d packed, [Pp,Pp+q) = <w_d>, [Pp+q] = <mu_d>, rest zero padding;
+ *                     Pp = pyvb_gw_woff(q) = P rounded up to a multiple of 8, ldg = pyvb_gw_pitch(q)
  *   Wbar, Wvar [D][q] column means / diagonal of the column covariances
  *   stats  [pyvb_stats_len(D,q)] one contiguous buffer, ready for a single all-reduce(SUM):
  *            T1 [D][P] = O^T vec<zz^T> | Bst [D][q] = O^T Zbar | Ast [D][q] = (O.X)^T Zbar |
@@ -111,6 +111,7 @@ const char *pyvb_last_error(void);
 
 /* sizes */
 int pyvb_gw_pitch(int q);                              /* doubles per Gw row */
+int pyvb_gw_woff(int q);                               /* first <w_d> column of a Gw row */
 size_t pyvb_stats_len(int D, int q);                   /* doubles */
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo);
 int pyvb_algo_supported(int algo, int D, int q);       /* 1/0 */

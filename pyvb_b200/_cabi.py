@@ -24,6 +24,7 @@ SIGNATURES = {
     "pyvb_version": (c_int, []),
     "pyvb_last_error": (ctypes.c_char_p, []),
     "pyvb_gw_pitch": (c_int, [c_int]),
+    "pyvb_gw_woff": (c_int, [c_int]),
     "pyvb_stats_len": (c_sz, [c_int, c_int]),
     "pyvb_stats_workspace_bytes": (c_sz, [c_ll, c_int, c_int, c_int]),
     "pyvb_algo_supported": (c_int, [c_int, c_int, c_int]),

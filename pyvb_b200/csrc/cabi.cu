@@ -38,11 +38,13 @@ int pyvb_gw_pitch(int q) {
     // P + q + 1 used columns; pitch*8 bytes must be = 32 or 96 (mod 128) so that the four k-rows of a
     // DMMA B fragment fall into distinct shared-memory bank groups, and a multiple of 16 bytes for
     // bulk (TMA) copies.  => pitch = 4 (mod 8) ... choose the smallest such pitch >= P+q+1.
-    const int used = q * (q + 1) / 2 + q + 1;
+    const int used = gw_woff(q) + q + 1;
     int p = used;
     while ((p % 8) != 4) ++p;
     return p;
 }
+
+int pyvb_gw_woff(int q) { return gw_woff(q); }
 
 size_t pyvb_stats_len(int D, int q) { return StatLayout(D, q).len; }
 
@@ -68,7 +70,7 @@ int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const
                      void *stream) {
     ARG(D >= 1 && q >= 1 && q <= PYVB_QMAX, "D, q");
     ARG(Wbar && Wvar && mu && Gw, "null pointer");
-    ARG(ldg >= q * (q + 1) / 2 + q + 1, "ldg");
+    ARG(ldg >= gw_woff(q) + q + 1, "ldg");
     cudaError_t e = launch_pack_gw(D, q, Wbar, Wvar, mu, Gw, ldg, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "pack_gw");
 }
@@ -79,7 +81,7 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Gw && P0 && h0 && gl && Zbar && M2 && logdet, "null pointer");
     ARG(ldx >= D, "ldx");
-    ARG(ldg >= q * (q + 1) / 2 + q + 1, "ldg");
+    ARG(ldg >= gw_woff(q) + q + 1, "ldg");
     if (N == 0) return PYVB_OK;
     const int a = pick_algo(algo, D, q);
     cudaError_t e;

@@ -27,6 +27,8 @@ struct StatLayout {
 };
 
 __host__ __device__ inline int tri(int i) { return i * (i + 1) / 2; }
+// first <w_d> column of a Gw row: P rounded up to a multiple of 8 (one DMMA column group)
+__host__ __device__ inline int gw_woff(int q) { return (tri(q) + 7) & ~7; }
 
 // packed index p -> (i, j), i >= j
 __device__ inline void unpack_p(int p, int &i, int &j) {

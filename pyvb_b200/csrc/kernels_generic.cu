@@ -20,7 +20,7 @@ __global__ void pack_gw_kernel(int D, int q, const double *__restrict__ Wbar, co
                                const double *__restrict__ mu, double *__restrict__ Gw, int ldg) {
     const int d = blockIdx.x;
     if (d >= D) return;
-    const int P = tri(q);
+    const int P = tri(q), Pp = gw_woff(q);
     const double *w = Wbar + (size_t)d * q;
     const double *v = Wvar + (size_t)d * q;
     double *g = Gw + (size_t)d * ldg;
@@ -34,8 +34,8 @@ __global__ void pack_gw_kernel(int D, int q, const double *__restrict__ Wbar, co
     }
     for (int c = P + threadIdx.x; c < ldg; c += blockDim.x) {
         double val = 0.0;
-        if (c < P + q) val = w[c - P];
-        else if (c == P + q) val = mu[d];
+        if (c >= Pp && c < Pp + q) val = w[c - Pp];
+        else if (c == Pp + q) val = mu[d];
         g[c] = val;
     }
 }
@@ -47,31 +47,28 @@ cudaError_t launch_pack_gw(int D, int q, const double *Wbar, const double *Wvar,
 }
 
 // =============================================================== Z step (K1+K2), one warp per row
-// In-place "bordering" inverse: row r of the matrix is owned by lane r (and r+32).  At step k the
-// leading k x k block holds the inverse of A[0:k,0:k]; columns > k still hold A (upper triangle only,
-// the strictly lower triangle starts at zero so that not-yet-active rows contribute nothing):
-//     a = A[0:k,k], u = B a, s = A[k,k] - a.u, B' = [[B,0],[0,0]] + [u;-1][u;-1]^T / s
-// The pivots s are those of the Cholesky factorisation, so ln prod diag chol = 0.5 sum ln s.
-template <int NT>
-__global__ void __launch_bounds__(128)
+// K2 follows the reference literally (nodes/gaussian.py:118-123): Cholesky factor of qprec, then
+// cho_solve against the identity (two triangular solves per column; lane j owns column j), then
+// qmu = qcov . (pprec.pmu + sum m2).  ln prod diag chol comes from the factor's diagonal.
+template <int NT, int WPB>
+__global__ void __launch_bounds__(32 * WPB)
 zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, long long ldx,
                      const double *__restrict__ Gw, int ldg, const double *__restrict__ P0,
                      const double *__restrict__ h0, double *gl, double *__restrict__ Zbar,
                      double *__restrict__ M2, double *__restrict__ Sig, double *__restrict__ logdet) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int P = tri(q), C = P + q;
+    const int P = tri(q), Pp = gw_woff(q), C = P + q;
     const int pitch = q + 1;
-    const int per_warp = q * pitch + 4 * q;
-    double *a = smem + (size_t)warp * per_warp;
-    double *eta = a + q * pitch;
-    double *av = eta + q;
-    double *uv = av + q;
-    double *zb = uv + q;
+    const int per_warp = 2 * q * pitch + 2 * q;
+    double *a = smem + (size_t)warp * per_warp;   // qprec, overwritten by its Cholesky factor (lower)
+    double *sv = a + q * pitch;                   // solution columns: sv[i*pitch + j], column j <- lane j
+    double *eta = sv + q * pitch;
+    double *zb = eta + q;
     const double tau = gl[PYVB_GL_TAU];
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-    for (long long n = (long long)blockIdx.x * 4 + warp; n < N; n += (long long)gridDim.x * 4) {
+    for (long long n = (long long)blockIdx.x * WPB + warp; n < N; n += (long long)gridDim.x * WPB) {
         double acc[NT];
 #pragma unroll
         for (int t = 0; t < NT; ++t) acc[t] = 0.0;
@@ -84,14 +81,12 @@ zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
                 const double x = __shfl_sync(0xffffffffu, xv, dd);
                 if (x != x) continue;  // not observed: warp-uniform
                 const double *g = Gw + (size_t)(d0 + dd) * ldg;
-                const double xm = x - g[P + q];
+                const double xm = x - g[Pp + q];
 #pragma unroll
                 for (int t = 0; t < NT; ++t) {
                     const int c = lane + 32 * t;
-                    if (c < C) {
-                        const double gv = g[c];
-                        acc[t] += (c < P) ? gv : xm * gv;
-                    }
+                    if (c < P) acc[t] += g[c];
+                    else if (c < C) acc[t] = fma(xm, g[c - P + Pp], acc[t]);
                 }
             }
         }
@@ -102,49 +97,47 @@ zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
             if (c < P) {
                 int i, j;
                 unpack_p(c, i, j);
-                const double val = P0[i * q + j] + tau * acc[t];
-                a[j * pitch + i] = val;               // upper triangle (row j <= col i)
-                if (i != j) a[i * pitch + j] = 0.0;   // strictly lower triangle starts at zero
+                a[i * pitch + j] = P0[i * q + j] + tau * acc[t];   // lower triangle
             } else if (c < C) {
                 eta[c - P] = h0[c - P] + tau * acc[t];
             }
         }
+        __syncwarp();
+        // ---- left-looking Cholesky, lanes over rows
         double ld = 0.0;
         bool ok = true;
         for (int k = 0; k < q; ++k) {
-            __syncwarp();
-            for (int r = lane; r < q; r += 32) av[r] = a[r * pitch + k];
-            __syncwarp();
-            double u_r[2] = {0.0, 0.0};
-            double part = 0.0;
-            {
-                int idx = 0;
-                for (int r = lane; r < q; r += 32, ++idx) {
-                    double u = 0.0;
-                    for (int j = 0; j < k; ++j) u = fma(a[r * pitch + j], av[j], u);
-                    u_r[idx] = u;
-                    if (r != k) part = fma(av[r], u, part);
-                }
-            }
-            const double s = av[k] - warp_sum(part);
-            if (!(s > 0.0)) ok = false;
-            ld += log(s);
-            const double sinv = 1.0 / s;
-            {
-                int idx = 0;
-                for (int r = lane; r < q; r += 32, ++idx) uv[r] = (r == k) ? -1.0 : u_r[idx];
+            for (int r = k + lane; r < q; r += 32) {
+                double v = a[r * pitch + k];
+                for (int m = 0; m < k; ++m) v = fma(-a[r * pitch + m], a[k * pitch + m], v);
+                a[r * pitch + k] = v;
             }
             __syncwarp();
-            for (int r = lane; r < q; r += 32) {
-                const double c = uv[r] * sinv;
-                for (int j = 0; j < k; ++j) a[r * pitch + j] = fma(c, uv[j], a[r * pitch + j]);
-                a[r * pitch + k] = -c;
+            const double dkk = a[k * pitch + k];
+            if (!(dkk > 0.0)) ok = false;
+            const double lkk = sqrt(dkk);
+            ld += log(lkk);
+            __syncwarp();
+            for (int r = k + lane; r < q; r += 32) a[r * pitch + k] = (r == k) ? lkk : a[r * pitch + k] / lkk;
+            __syncwarp();
+        }
+        // ---- cho_solve(L, I): column j by lane j
+        for (int j = lane; j < q; j += 32) {
+            for (int i = 0; i < q; ++i) {           // forward: L y = e_j
+                double t = (i == j) ? 1.0 : 0.0;
+                for (int m = 0; m < i; ++m) t = fma(-a[i * pitch + m], sv[m * pitch + j], t);
+                sv[i * pitch + j] = t / a[i * pitch + i];
+            }
+            for (int i = q - 1; i >= 0; --i) {      // backward: L^T s = y
+                double t = sv[i * pitch + j];
+                for (int m = i + 1; m < q; ++m) t = fma(-a[m * pitch + i], sv[m * pitch + j], t);
+                sv[i * pitch + j] = t / a[i * pitch + i];
             }
         }
         __syncwarp();
         for (int r = lane; r < q; r += 32) {
             double z = 0.0;
-            for (int j = 0; j < q; ++j) z = fma(a[r * pitch + j], eta[j], z);
+            for (int j = 0; j < q; ++j) z = fma(sv[r * pitch + j], eta[j], z);
             zb[r] = z;
             Zbar[n * q + r] = z;
         }
@@ -152,12 +145,12 @@ zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
         for (int p = lane; p < P; p += 32) {
             int i, j;
             unpack_p(p, i, j);
-            const double sg = a[i * pitch + j];
+            const double sg = 0.5 * (sv[i * pitch + j] + sv[j * pitch + i]);
             M2[n * P + p] = fma(zb[i], zb[j], sg);
             if (Sig) Sig[n * P + p] = sg;
         }
         if (lane == 0) {
-            logdet[n] = 0.5 * ld;
+            logdet[n] = ld;
             if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
         }
         __syncwarp();
@@ -170,22 +163,23 @@ cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, lon
     if (N <= 0) return cudaSuccess;
     const int C = tri(q) + q;
     const int nt = (C + 31) / 32;
-    const size_t smem = (size_t)4 * (q * (q + 1) + 4 * q) * sizeof(double);
-    long long blocks = (N + 3) / 4;
+    const int wpb = (q > 32) ? 2 : 4;
+    const size_t smem = (size_t)wpb * (2 * q * (q + 1) + 2 * q) * sizeof(double);
+    long long blocks = (N + wpb - 1) / wpb;
     if (blocks > 148 * 16) blocks = 148 * 16;
-#define PYVB_LAUNCH_Z(NT)                                                                                      \
+#define PYVB_LAUNCH_Z(NT, WPB)                                                                                 \
     do {                                                                                                       \
-        cudaError_t e = cudaFuncSetAttribute(zstep_generic_kernel<NT>,                                         \
+        cudaError_t e = cudaFuncSetAttribute(zstep_generic_kernel<NT, WPB>,                                    \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
         if (e != cudaSuccess) return e;                                                                        \
-        zstep_generic_kernel<NT><<<(unsigned)blocks, 128, smem, st>>>(N, D, q, X, ldx, Gw, ldg, P0, h0, gl,    \
-                                                                      Zbar, M2, Sig, logdet);                  \
+        zstep_generic_kernel<NT, WPB><<<(unsigned)blocks, 32 * WPB, smem, st>>>(                               \
+            N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, M2, Sig, logdet);                                      \
     } while (0)
-    if (nt <= 1) PYVB_LAUNCH_Z(1);
-    else if (nt <= 2) PYVB_LAUNCH_Z(2);
-    else if (nt <= 5) PYVB_LAUNCH_Z(5);
-    else if (nt <= 18) PYVB_LAUNCH_Z(18);
-    else PYVB_LAUNCH_Z(67);
+    if (nt <= 1) PYVB_LAUNCH_Z(1, 4);
+    else if (nt <= 2) PYVB_LAUNCH_Z(2, 4);
+    else if (nt <= 5) PYVB_LAUNCH_Z(5, 4);
+    else if (nt <= 18) PYVB_LAUNCH_Z(18, 4);
+    else PYVB_LAUNCH_Z(67, 2);
 #undef PYVB_LAUNCH_Z
     return cudaGetLastError();
 }
