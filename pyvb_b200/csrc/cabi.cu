@@ -118,6 +118,7 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
         nch = stats_dmma_nchunks(N, D, q);
         e = launch_stats_dmma(N, D, q, X, ldx, Zbar, M2, ws_main, nch, st);
+        if (e == cudaSuccess) e = launch_colsums(N, D, q, X, ldx, ws_main, nch, st);
     } else if (a == PYVB_ALGO_GENERIC) {
         nch = stats_generic_nchunks(N);
         e = launch_stats_generic(N, D, q, X, ldx, Zbar, M2, ws_main, nch, st);

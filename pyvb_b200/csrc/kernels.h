@@ -17,6 +17,8 @@ cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, lon
 int stats_generic_nchunks(long long N);
 cudaError_t launch_stats_generic(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
                                  const double *M2, double *ws_main, int nchunks, cudaStream_t st);
+cudaError_t launch_colsums(long long N, int D, int q, const double *X, long long ldx, double *ws_main, int nchunks,
+                           cudaStream_t st);
 // per-row scalars: partial sums into ws_sc[nblk][PYVB_NSCAL]
 int rowscalars_nblk(long long N);
 cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx, const double *V,

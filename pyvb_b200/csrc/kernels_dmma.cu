@@ -1,15 +1,601 @@
-// placeholder until the DMMA kernels land
+// FP64 tensor-core (DMMA.8x8x4) kernels with TMA bulk-copy staging -- the throughput path.
+//
+//   zstep_dmma_kernel<Q>  K1: [O | O.(X-mu)] (rows x D)  @  Gw (D x (P+q))      -> per-row qprec (packed) and eta
+//                         K2: per-row Cholesky / inverse / solve with the matrix row held in registers
+//                             (lane i owns row i; q lanes per matrix), outputs leave through TMA bulk stores
+//   stats_dmma_kernel<Q>  K3: [O | O.X]^T (D x rows) @ [<zz^T> | zbar] (rows x (P+q)) -> T1, Bst, Ast (+ S, zsum)
+//
+// Reference arithmetic: nodes/node.py:203-227 (K1), nodes/gaussian.py:117-123 (K2), nodes/nodes_todo.py:50-61 (K3).
+//
+// Pipeline: one producer warp issues cp.async.bulk (SASS UBLKCP) copies that complete on mbarriers;
+// consumer warps issue mma.sync.m8n8k4.f64 (the only FP64 tensor shape the hardware has; measured 37.0 TF on
+// B200 = the roofline of this path).  Shared-memory pitches are chosen so that every fragment load is
+// bank-conflict free (pitch = 32 or 96 bytes mod 128).
 #include "common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
+
 namespace pyvb {
-bool dmma_supported(int, int) { return false; }
-cudaError_t launch_zstep_dmma(long long, int, int, const double *, long long, const double *, int, const double *,
-                              const double *, double *, double *, double *, double *, double *, cudaStream_t) {
+
+// ------------------------------------------------------------------ compile-time geometry
+__host__ __device__ constexpr int c_tri(int i) { return i * (i + 1) / 2; }
+__host__ __device__ constexpr int c_gw_pitch(int q) {
+    int p = ((c_tri(q) + 7) & ~7) + q + 1;
+    while ((p % 8) != 4) ++p;
+    return p;
+}
+// start of row k in the "even padded" packed lower-triangular layout (every row starts 16-byte aligned)
+__host__ __device__ constexpr int c_off(int k) {
+    return (k & 1) ? 2 * ((k - 1) / 2 + 1) * ((k - 1) / 2 + 1) : 2 * (k / 2) * (k / 2 + 1);
+}
+__host__ __device__ constexpr int c_srow(int need) {
+    int s = need + (need & 1);
+    while ((s % 16) != 2) s += 2;
+    return s;
+}
+__host__ __device__ constexpr int c_max(int a, int b) { return a > b ? a : b; }
+
+template <int Q> struct ZC;
+template <> struct ZC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, MI = 2, OCC = 2; };
+template <> struct ZC<16> { static constexpr int WM = 4, WN = 1, RGW = 2, KC = 16, ST = 3, MI = 2, OCC = 2; };
+template <> struct ZC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, MI = 1, OCC = 1; };
+
+template <int Q> struct ZT {
+    using C = ZC<Q>;
+    static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, NGO = PP / 8, NGE = Q / 8, NG = NGO + NGE;
+    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST, MI = C::MI;
+    static constexpr int NGW = (NG + WN - 1) / WN;
+    static constexpr int R = WM * RGW * 8;
+    static constexpr int NCW = WM * WN;
+    static constexpr int NTHR = NCW * 32;       // no dedicated producer warp: warp 0 also issues the bulk copies
+    static constexpr int LDG = c_gw_pitch(Q);
+    static constexpr int MUCOL = PP + Q;
+    static constexpr int XP = KC + 4;
+    static constexpr int XS_D = R * XP, GS_D = KC * LDG, STAGE_D = XS_D + GS_D;
+    static constexpr int SPL = Q * (Q + 2) / 2;
+    static constexpr int SROW = c_srow(SPL + Q);
+    static constexpr int MAIN_D = c_max(ST * STAGE_D, R * SROW);
+    static constexpr int G = 32 / Q;            // matrices side by side in a warp
+    static constexpr int RPP = G * MI;          // rows per warp pass
+    static constexpr int XR_D = NCW * 2 * MI * 32;
+    static constexpr size_t SMEM = (size_t)(MAIN_D + P + Q + XR_D) * 8 + 2 * ST * 8 + ((P * 2 + 15) & ~15);
+    static_assert(R % (NCW * RPP) == 0, "rows must split evenly over the K2 passes");
+};
+
+// ------------------------------------------------------------------ K2: per-row Cholesky inverse in registers
+// Lane li of a Q-lane group owns row li.  The matrix (lower triangle, even-padded packed rows) lives in
+// the staging row `A`; the factor overwrites it in place (diagonal holds 1/L_kk) so that "row k of L" is a
+// contiguous broadcast read.  Pass 1: left-looking Cholesky.  Pass 2: X = L^-1 by forward substitution
+// (lane j owns column j) fused with Sigma = X^T X accumulated row by row.  Everything is statically
+// unrolled so the rows stay in registers.
+template <int Q, int MI>
+__device__ __forceinline__ void k2_solve(double *const (&A)[MI], double *xbuf, const int li, const int offli,
+                                         double (&Sg)[MI][Q], double (&z)[MI], double (&ldet)[MI], bool &ok) {
+    using T = ZT<Q>;
+    double Lr[MI][Q];
+    double mant[MI];
+    int esum[MI];
+#pragma unroll
+    for (int m = 0; m < MI; ++m) {
+        mant[m] = 1.0;
+        esum[m] = 0;
+    }
+    // ---- pass 1
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const double *Lk = A[m] + c_off(k);
+            double v0 = (li >= k) ? A[m][offli + k] : 0.0;
+            double v1 = 0.0;
+#pragma unroll
+            for (int mm = 0; mm + 1 < k; mm += 2) {
+                const double2 l2 = *reinterpret_cast<const double2 *>(Lk + mm);
+                v0 = fma(-Lr[m][mm], l2.x, v0);
+                v1 = fma(-Lr[m][mm + 1], l2.y, v1);
+            }
+            if (k & 1) v0 = fma(-Lr[m][k - 1], Lk[k - 1], v0);
+            const double v = v0 + v1;
+            const double d = __shfl_sync(0xffffffffu, v, k, Q);
+            ok = ok && (d > 0.0);
+            const long long bits = __double_as_longlong(d);
+            esum[m] += (int)((bits >> 52) & 0x7ff) - 1023;
+            mant[m] *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
+            const double rinv = rsqrt(d);
+            const double l = v * rinv;
+            Lr[m][k] = l;
+            if (li > k) A[m][offli + k] = l;
+            else if (li == k) A[m][offli + k] = rinv;
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int m = 0; m < MI; ++m) ldet[m] = 0.5 * (log(mant[m]) + (double)esum[m] * 0.69314718055994530942);
+    // ---- pass 2
+#pragma unroll
+    for (int m = 0; m < MI; ++m)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) Sg[m][j] = 0.0;
+    {
+        double xv[MI][Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            double xi[MI];
+            double *xb = xbuf + (i & 1) * (MI * 32);
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const double *Li = A[m] + c_off(i);
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int mm = 0; mm + 1 < i; mm += 2) {
+                    const double2 l2 = *reinterpret_cast<const double2 *>(Li + mm);
+                    t0 = fma(l2.x, xv[m][mm], t0);
+                    t1 = fma(l2.y, xv[m][mm + 1], t1);
+                }
+                if (i & 1) t0 = fma(Li[i - 1], xv[m][i - 1], t0);
+                xi[m] = (((li == i) ? 1.0 : 0.0) - (t0 + t1)) * Li[i];
+                xv[m][i] = xi[m];
+                xb[m * 32 + (threadIdx.x & 31)] = xi[m];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const double *xrow = xb + m * 32 + ((threadIdx.x & 31) - li);
+#pragma unroll
+                for (int j = 0; j + 1 <= i; j += 2) {
+                    const double2 x2 = *reinterpret_cast<const double2 *>(xrow + j);
+                    Sg[m][j] = fma(xi[m], x2.x, Sg[m][j]);
+                    Sg[m][j + 1] = fma(xi[m], x2.y, Sg[m][j + 1]);
+                }
+                if (!(i & 1)) Sg[m][i] = fma(xi[m], xrow[i], Sg[m][i]);
+            }
+        }
+    }
+    // ---- posterior mean: z = Sigma . eta
+#pragma unroll
+    for (int m = 0; m < MI; ++m) {
+        const double *eta = A[m] + T::SPL;
+        double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < Q; j += 2) {
+            const double2 e2 = *reinterpret_cast<const double2 *>(eta + j);
+            z0 = fma(Sg[m][j], e2.x, z0);
+            z1 = fma(Sg[m][j + 1], e2.y, z1);
+        }
+        z[m] = z0 + z1;
+    }
+}
+
+// ------------------------------------------------------------------ Z step kernel
+template <int Q>
+__global__ void __launch_bounds__(ZT<Q>::NTHR, ZC<Q>::OCC)
+zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ Gw,
+                  const double *__restrict__ P0, const double *__restrict__ h0, double *gl,
+                  double *__restrict__ Zbar, double *__restrict__ M2, double *__restrict__ Sig,
+                  double *__restrict__ logdet) {
+    using T = ZT<Q>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    double *p0v = smem + T::MAIN_D;
+    double *h0s = p0v + T::P;
+    double *xr = h0s + Q;
+    uint64_t *full = reinterpret_cast<uint64_t *>(xr + T::XR_D);
+    uint64_t *empty = full + T::ST;
+    uint16_t *soff = reinterpret_cast<uint16_t *>(empty + T::ST);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long row0 = (long long)blockIdx.x * T::R;
+    const int nk = D / T::KC;
+
+    for (int p = tid; p < T::P; p += T::NTHR) {
+        int i, j;
+        unpack_p(p, i, j);
+        soff[p] = (uint16_t)(c_off(i) + j);
+        p0v[p] = P0[i * Q + j];
+    }
+    if (tid < Q) h0s[tid] = h0[tid];
+    if (tid == 0) {
+        for (int s = 0; s < T::ST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], T::NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ===================== producer role (warp 0): TMA bulk copies, ST-1 chunks ahead =====================
+    auto produce = [&](int kc) {
+        const int s = kc % T::ST;
+        const uint32_t ph = (uint32_t)((kc / T::ST) & 1);
+        mbar_wait(&empty[s], ph ^ 1);
+        double *xs = smem + s * T::STAGE_D;
+        double *gs = xs + T::XS_D;
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)((T::GS_D + T::R * T::KC) * 8));
+        __syncwarp();
+        if (lane == 0) bulk_g2s(gs, Gw + (size_t)kc * T::KC * T::LDG, T::GS_D * 8, &full[s]);
+        for (int r = lane; r < T::R; r += 32) {
+            long long row = row0 + r;
+            if (row >= N) row = N - 1;   // tail tile: duplicate a valid row, results are discarded
+            bulk_g2s(xs + r * T::XP, X + row * ldx + (long long)kc * T::KC, T::KC * 8, &full[s]);
+        }
+    };
+    if (warp == 0)
+        for (int kc = 0; kc < T::ST - 1 && kc < nk; ++kc) produce(kc);
+
+    // ===================== DMMA main loop =====================
+    const int wm = warp / T::WN, wn = warp % T::WN;
+    const int gid = lane >> 2, qd = lane & 3;
+    const int cg0 = wn * T::NGW;
+    const int ncg = (T::NG - cg0 < T::NGW) ? (T::NG - cg0) : T::NGW;
+    double acc[T::RGW][T::NGW][2];
+#pragma unroll
+    for (int rg = 0; rg < T::RGW; ++rg)
+#pragma unroll
+        for (int j = 0; j < T::NGW; ++j) acc[rg][j][0] = acc[rg][j][1] = 0.0;
+    {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kc = 0; kc < nk; ++kc) {
+            if (warp == 0 && kc + T::ST - 1 < nk) produce(kc + T::ST - 1);
+            mbar_wait(&full[s], ph);
+            const double *xs = smem + s * T::STAGE_D + (wm * T::RGW * 8 + gid) * T::XP + qd;
+            const double *gs = smem + s * T::STAGE_D + T::XS_D + qd * T::LDG;
+#pragma unroll
+            for (int kk = 0; kk < T::KC / 4; ++kk) {
+                const double *grow = gs + kk * 4 * T::LDG;
+                const double muv = grow[T::MUCOL];
+                double ao[T::RGW], ax[T::RGW];
+#pragma unroll
+                for (int rg = 0; rg < T::RGW; ++rg) {
+                    const double x = xs[rg * 8 * T::XP + kk * 4];
+                    const bool ob = (x == x);          // NaN = not observed
+                    ao[rg] = ob ? 1.0 : 0.0;
+                    ax[rg] = ob ? (x - muv) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < T::NGW; ++j) {
+                    if (T::WN > 1 && j >= ncg) continue;
+                    const int cg = cg0 + j;
+                    const double b = grow[cg * 8 + gid];
+                    const bool otype = cg < T::NGO;
+#pragma unroll
+                    for (int rg = 0; rg < T::RGW; ++rg)
+                        dmma884(acc[rg][j][0], acc[rg][j][1], otype ? ao[rg] : ax[rg], b);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == T::ST) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+
+    // ===================== epilogue: accumulators -> staging (aliases the pipeline buffers) =====================
+    named_bar_sync(1, T::NCW * 32);
+    const double tau = gl[PYVB_GL_TAU];
+    double *stg = smem;
+#pragma unroll
+    for (int rg = 0; rg < T::RGW; ++rg) {
+        double *srow = stg + (size_t)(wm * T::RGW * 8 + rg * 8 + gid) * T::SROW;
+#pragma unroll
+        for (int j = 0; j < T::NGW; ++j) {
+            if (T::WN > 1 && j >= ncg) continue;
+            const int cg = cg0 + j;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cg * 8 + 2 * qd + e;
+                if (cg < T::NGO) {
+                    if (c < T::P) srow[soff[c]] = fma(tau, acc[rg][j][e], p0v[c]);
+                } else {
+                    const int i = c - T::PP;
+                    srow[T::SPL + i] = fma(tau, acc[rg][j][e], h0s[i]);
+                }
+            }
+        }
+    }
+    named_bar_sync(1, T::NCW * 32);
+
+    // ===================== K2 =====================
+    const int li = lane % Q, lg = lane / Q;
+    const int offli = c_off(li);
+    double *xbuf = xr + warp * (2 * T::MI * 32);
+    for (int rb = warp * T::RPP; rb < T::R; rb += T::NCW * T::RPP) {
+        double *A[T::MI];
+        long long nrow[T::MI];
+#pragma unroll
+        for (int m = 0; m < T::MI; ++m) {
+            const int r = rb + lg * T::MI + m;
+            A[m] = stg + (size_t)r * T::SROW;
+            nrow[m] = row0 + r;
+        }
+        double Sg[T::MI][Q], z[T::MI], ldet[T::MI];
+        bool ok = true;
+        k2_solve<Q, T::MI>(A, xbuf, li, offli, Sg, z, ldet, ok);
+        // publish z (buffer 0), then second moments; staging row is reused as the output row
+#pragma unroll
+        for (int m = 0; m < T::MI; ++m) xbuf[m * 32 + lane] = z[m];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < T::MI; ++m) {
+            const bool valid = nrow[m] < N;
+            const double *zrow = xbuf + m * 32 + (lane - li);
+            double *orow = A[m] + c_tri(li);
+            double *sgl = (Sig != nullptr && valid) ? (Sig + nrow[m] * T::P + c_tri(li)) : nullptr;
+#pragma unroll
+            for (int j = 0; j < Q; ++j) {
+                if (j <= li) {
+                    orow[j] = fma(z[m], zrow[j], Sg[m][j]);
+                    if (sgl) sgl[j] = Sg[m][j];
+                }
+            }
+            A[m][T::SPL + li] = z[m];
+            if (li == 0 && valid) {
+                logdet[nrow[m]] = ldet[m];
+                if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
+            }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (li == 0) {
+#pragma unroll
+            for (int m = 0; m < T::MI; ++m) {
+                if (nrow[m] < N) {
+                    bulk_s2g(M2 + nrow[m] * T::P, A[m], T::P * 8);
+                    bulk_s2g(Zbar + nrow[m] * Q, A[m] + T::SPL, Q * 8);
+                }
+            }
+            bulk_commit();
+        }
+    }
+    if (li == 0) bulk_wait_read_all();
+}
+
+bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32) && D >= 16 && (D % 16) == 0; }
+
+template <int Q>
+static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long ldx, const double *Gw,
+                                  const double *P0, const double *h0, double *gl, double *Zbar, double *M2,
+                                  double *Sig, double *logdet, cudaStream_t st) {
+    using T = ZT<Q>;
+    cudaError_t e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)T::SMEM);
+    if (e != cudaSuccess) return e;
+    const long long blocks = (N + T::R - 1) / T::R;
+    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig,
+                                                                     logdet);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
+                              const double *P0, const double *h0, double *gl, double *Zbar, double *M2,
+                              double *Sig, double *logdet, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    if (ldg != c_gw_pitch(q)) return cudaErrorInvalidValue;
+    switch (q) {
+        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig, logdet, st);
+        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig, logdet, st);
+        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig, logdet, st);
+    }
     return cudaErrorNotSupported;
 }
-int stats_dmma_nchunks(long long, int, int) { return 1; }
-cudaError_t launch_stats_dmma(long long, int, int, const double *, long long, const double *, const double *,
-                              double *, int, cudaStream_t) {
+
+// ------------------------------------------------------------------ statistics kernel (K3)
+template <int Q> struct SC;
+template <> struct SC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, OCC = 1; };
+template <> struct SC<16> { static constexpr int WM = 8, WN = 1, RGW = 2, KC = 16, ST = 3, OCC = 1; };
+template <> struct SC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1; };
+
+template <int Q> struct STT {
+    using C = SC<Q>;
+    static constexpr int P = c_tri(Q), PP = (P + 7) & ~7;
+    static constexpr int NGO = (PP + Q) / 8, NGX = Q / 8, NG = NGO + NGX;   // O-type: [<zz^T> | pad | zbar]; X-type: zbar
+    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST;
+    static constexpr int NGW = (NG + WN - 1) / WN;
+    static constexpr int DT = WM * RGW * 8;     // data dimensions per CTA
+    static constexpr int NCW = WM * WN;
+    static constexpr int NTHR = NCW * 32;       // warp 0 doubles as the producer
+    static constexpr int VP = c_gw_pitch(Q);    // pitch of the [<zz^T> | zbar] tile rows
+    static constexpr int AP = DT + 4;           // pitch of the X tile rows (= 4 mod 16 doubles)
+    static constexpr int AS_D = KC * AP, VS_D = KC * VP, STAGE_D = AS_D + VS_D;
+    static constexpr size_t SMEM = (size_t)(ST * STAGE_D) * 8 + 2 * ST * 8;
+    static_assert(AP % 16 == 4 || AP % 16 == 12, "X tile pitch must avoid bank conflicts");
+};
+
+// grid.x = number of d tiles + 1 (the last one is the "virtual" all-ones row that yields S and zsum),
+// grid.y = row chunks.  Partial sums go to ws[chunk][stat layout]; a second kernel adds the chunks.
+template <int Q>
+__global__ void __launch_bounds__(STT<Q>::NTHR, SC<Q>::OCC)
+stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ Zbar,
+                  const double *__restrict__ M2, double *__restrict__ ws, long long rows_per_chunk) {
+    using T = STT<Q>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *smem = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + T::ST * T::STAGE_D);
+    uint64_t *empty = full + T::ST;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ndt = (D + T::DT - 1) / T::DT;
+    const bool virt = ((int)blockIdx.x == ndt);
+    const int d0 = blockIdx.x * T::DT;
+    const int dvalid = virt ? 0 : ((D - d0 < T::DT) ? (D - d0) : T::DT);
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    long long r1 = r0 + rows_per_chunk;
+    if (r1 > N) r1 = N;
+    const int nsteps = (r1 > r0) ? (int)((r1 - r0 + T::KC - 1) / T::KC) : 0;
+
+    // zero the pad columns of the V tiles once (bulk copies never touch them)
+    for (int idx = tid; idx < T::ST * T::KC * (T::VP - T::P); idx += T::NTHR) {
+        const int s = idx / (T::KC * (T::VP - T::P));
+        const int rem = idx % (T::KC * (T::VP - T::P));
+        const int r = rem / (T::VP - T::P), c = T::P + rem % (T::VP - T::P);
+        if (c < T::PP || c >= T::PP + Q) smem[s * T::STAGE_D + T::AS_D + r * T::VP + c] = 0.0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < T::ST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], T::NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ===================== producer role (warp 0) =====================
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    auto produce = [&](int it) {
+        const int s = it % T::ST;
+        const uint32_t ph = (uint32_t)((it / T::ST) & 1);
+        mbar_wait(&empty[s], ph ^ 1);
+        double *as = smem + s * T::STAGE_D;
+        double *vs = as + T::AS_D;
+        const long long nb = r0 + (long long)it * T::KC;
+        const int nval = (r1 - nb < T::KC) ? (int)(r1 - nb) : T::KC;
+        // rows past the end of the chunk: X -> NaN (mask 0), V -> 0
+        for (int r = nval; r < T::KC; ++r) {
+            for (int c = lane; c < T::AP; c += 32) as[r * T::AP + c] = qnan;
+            for (int c = lane; c < T::VP; c += 32) vs[r * T::VP + c] = 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(nval * ((virt ? 0 : dvalid) + T::P + Q) * 8));
+        __syncwarp();
+        if (lane < nval) {
+            const long long n = nb + lane;
+            if (!virt) bulk_g2s(as + lane * T::AP, X + n * ldx + d0, dvalid * 8, &full[s]);
+            bulk_g2s(vs + lane * T::VP, M2 + n * T::P, T::P * 8, &full[s]);
+            bulk_g2s(vs + lane * T::VP + T::PP, Zbar + n * Q, Q * 8, &full[s]);
+        }
+    };
+    if (warp == 0)
+        for (int it = 0; it < T::ST - 1 && it < nsteps; ++it) produce(it);
+
+    // ===================== DMMA main loop =====================
+    const int wm = warp / T::WN, wn = warp % T::WN;
+    const int gid = lane >> 2, qd = lane & 3;
+    const int cg0 = wn * T::NGW;
+    const int ncg = (T::NG - cg0 < T::NGW) ? (T::NG - cg0) : T::NGW;
+    const int dw = wm * T::RGW * 8;                       // first d of this warp inside the tile
+    const bool active = virt ? (wm == 0) : (dw < dvalid); // warp-uniform
+    double acc[T::RGW][T::NGW][2];
+#pragma unroll
+    for (int rg = 0; rg < T::RGW; ++rg)
+#pragma unroll
+        for (int j = 0; j < T::NGW; ++j) acc[rg][j][0] = acc[rg][j][1] = 0.0;
+    {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < nsteps; ++it) {
+            if (warp == 0 && it + T::ST - 1 < nsteps) produce(it + T::ST - 1);
+            mbar_wait(&full[s], ph);
+            if (active) {
+                const double *as = smem + s * T::STAGE_D + qd * T::AP + dw + gid;
+                const double *vs = smem + s * T::STAGE_D + T::AS_D + qd * T::VP + gid;
+#pragma unroll
+                for (int kk = 0; kk < T::KC / 4; ++kk) {
+                    double ao[T::RGW], ax[T::RGW];
+#pragma unroll
+                    for (int rg = 0; rg < T::RGW; ++rg) {
+                        if (virt) {
+                            ao[rg] = (rg == 0 && gid == 0) ? 1.0 : 0.0;
+                            ax[rg] = 0.0;
+                        } else {
+                            const double x = (dw + rg * 8 < dvalid) ? as[kk * 4 * T::AP + rg * 8] : qnan;
+                            const bool ob = (x == x);
+                            ao[rg] = ob ? 1.0 : 0.0;
+                            ax[rg] = ob ? x : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < T::NGW; ++j) {
+                        if (T::WN > 1 && j >= ncg) continue;
+                        const int cg = cg0 + j;
+                        const bool otype = cg < T::NGO;
+                        // X-type groups re-use the zbar columns of the tile
+                        const int col = otype ? cg * 8 : (T::PP + (cg - T::NGO) * 8);
+                        const double b = vs[kk * 4 * T::VP + col];
+#pragma unroll
+                        for (int rg = 0; rg < T::RGW; ++rg)
+                            dmma884(acc[rg][j][0], acc[rg][j][1], otype ? ao[rg] : ax[rg], b);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == T::ST) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+    }
+    if (!active) return;
+    // ===================== store partial sums =====================
+    const StatLayout L(D, Q);
+    double *out = ws + (size_t)blockIdx.y * L.len;
+#pragma unroll
+    for (int rg = 0; rg < T::RGW; ++rg) {
+        const int d = d0 + dw + rg * 8 + gid;
+#pragma unroll
+        for (int j = 0; j < T::NGW; ++j) {
+            if (T::WN > 1 && j >= ncg) continue;
+            const int cg = cg0 + j;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = cg * 8 + 2 * qd + e;
+                const double v = acc[rg][j][e];
+                if (virt) {
+                    if (rg == 0 && gid == 0 && cg < T::NGO) {
+                        if (c < T::P) out[L.S + c] = v;
+                        else if (c >= T::PP) out[L.zsum + (c - T::PP)] = v;
+                    }
+                } else if (d < D) {
+                    if (cg < T::NGO) {
+                        if (c < T::P) out[L.t1 + (size_t)d * T::P + c] = v;
+                        else if (c >= T::PP) out[L.bst + (size_t)d * Q + (c - T::PP)] = v;
+                    } else {
+                        out[L.ast + (size_t)d * Q + (c - T::NGO * 8)] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+int stats_dmma_nchunks(long long N, int D, int q) {
+    int kc = 16, dt = 128;
+    if (q == 32) { kc = 8; dt = 32; }
+    const int ndt = (D + dt - 1) / dt + 1;
+    long long target = (148LL * 4 + ndt - 1) / ndt;            // ~4 CTAs per SM overall
+    long long by_rows = (N + 64LL * kc - 1) / (64LL * kc);     // at least 64 pipeline steps per chunk
+    long long c = target < by_rows ? target : by_rows;
+    if (c < 1) c = 1;
+    if (c > 512) c = 512;
+    return (int)c;
+}
+
+template <int Q>
+static cudaError_t launch_stats_q(long long N, int D, const double *X, long long ldx, const double *Zbar,
+                                  const double *M2, double *ws, int nchunks, cudaStream_t st) {
+    using T = STT<Q>;
+    cudaError_t e = cudaFuncSetAttribute(stats_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)T::SMEM);
+    if (e != cudaSuccess) return e;
+    long long rpc = (N + nchunks - 1) / nchunks;
+    rpc = ((rpc + T::KC - 1) / T::KC) * T::KC;                 // chunk boundaries on pipeline-step boundaries
+    if (rpc < T::KC) rpc = T::KC;
+    const int ndt = (D + T::DT - 1) / T::DT;
+    dim3 grid((unsigned)(ndt + 1), (unsigned)nchunks);
+    stats_dmma_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(N, D, X, ldx, Zbar, M2, ws, rpc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
+                              const double *M2, double *ws_main, int nchunks, cudaStream_t st) {
+    switch (q) {
+        case 8: return launch_stats_q<8>(N, D, X, ldx, Zbar, M2, ws_main, nchunks, st);
+        case 16: return launch_stats_q<16>(N, D, X, ldx, Zbar, M2, ws_main, nchunks, st);
+        case 32: return launch_stats_q<32>(N, D, X, ldx, Zbar, M2, ws_main, nchunks, st);
+    }
     return cudaErrorNotSupported;
 }
+
 }  // namespace pyvb

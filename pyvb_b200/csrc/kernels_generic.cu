@@ -270,6 +270,59 @@ cudaError_t launch_stats_generic(long long N, int D, int q, const double *X, lon
     return cudaGetLastError();
 }
 
+// =============================================================== column sums of the mask and of O.X
+// (the DMMA statistics kernel leaves cnt / colsumX to this HBM-bound pass)
+template <int ROWS>
+__global__ void __launch_bounds__(128)
+colsums2_kernel(long long N, int D, int q, const double *__restrict__ X, long long ldx, double *__restrict__ ws,
+                long long rows_per_chunk) {
+    const StatLayout L(D, q);
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    long long r1 = r0 + rows_per_chunk;
+    if (r1 > N) r1 = N;
+    if (d >= D) return;
+    double c[ROWS], s[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) c[u] = s[u] = 0.0;
+    long long n = r0;
+    for (; n + ROWS <= r1; n += ROWS) {
+#pragma unroll
+        for (int u = 0; u < ROWS; ++u) {
+            const double x = X[(n + u) * ldx + d];
+            if (x == x) {
+                c[u] += 1.0;
+                s[u] += x;
+            }
+        }
+    }
+    for (; n < r1; ++n) {
+        const double x = X[n * ldx + d];
+        if (x == x) {
+            c[0] += 1.0;
+            s[0] += x;
+        }
+    }
+    double ct = 0.0, stot = 0.0;
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        ct += c[u];
+        stot += s[u];
+    }
+    double *out = ws + (size_t)blockIdx.y * L.len;
+    out[L.cnt + d] = ct;
+    out[L.colx + d] = stot;
+}
+
+cudaError_t launch_colsums(long long N, int D, int q, const double *X, long long ldx, double *ws_main, int nchunks,
+                           cudaStream_t st) {
+    long long rpc = (N + nchunks - 1) / nchunks;
+    if (rpc < 1) rpc = 1;
+    dim3 grid((unsigned)((D + 127) / 128), (unsigned)nchunks);
+    colsums2_kernel<8><<<grid, 128, 0, st>>>(N, D, q, X, ldx, ws_main, rpc);
+    return cudaGetLastError();
+}
+
 // =============================================================== per-row scalars (K4)
 __global__ void __launch_bounds__(256)
 rowscalars_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ V,

@@ -151,3 +151,63 @@ def test_stats_are_additive_over_row_shards(eng):
         p = eng(X[lo:hi], q, mode="B", algo="generic"); p.set_state(sub); p._ensure_stats()
         acc = p.stats.clone() if acc is None else acc + p.stats
     assert tensor_rel(acc.cpu().numpy(), full.stats.cpu().numpy()) < 1e-12
+
+
+# ---------------------------------------------------------------- DMMA (FP64 tensor core) path
+DMMA_SHAPES = [(5000, 256, 16), (64, 16, 16), (1, 32, 16), (777, 64, 32), (2100, 128, 32), (1000, 48, 8), (4099, 80, 8)]
+
+
+@pytest.mark.parametrize("shape", DMMA_SHAPES)
+def test_dmma_zstep_and_stats_match_generic(eng, shape):
+    """kernel-level: same inputs through the DMMA kernels and the generic kernels."""
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.3, seed=N + q)
+    if N > 10:
+        X[2, :] = np.nan            # an all-missing row
+        X[5, :] = 1.0               # a fully observed row
+    init = rand_init(N, D, q, seed=7)
+    eg, ed = eng(X, q, mode="B", algo="generic"), eng(X, q, mode="B", algo="dmma")
+    for e in (eg, ed):
+        e.set_state(init)
+        e.update_Z()
+        e._ensure_stats()
+    sg, sd = eg.get_state(), ed.get_state()
+    for k in ("Zbar", "Sig"):
+        assert tensor_rel(sd[k], sg[k]) < 1e-11, (shape, k)
+    assert tensor_rel(ed.M2.cpu().numpy(), eg.M2.cpu().numpy()) < 1e-11
+    lg, ld = eg.logdet.cpu().numpy(), ed.logdet.cpu().numpy()
+    assert np.max(np.abs(lg - ld)) < 1e-11 * max(1.0, np.max(np.abs(lg)))
+    vg, vd = eg.L.views(eg.stats.cpu().numpy()), ed.L.views(ed.stats.cpu().numpy())
+    for k in ("T1", "Bst", "Ast", "cnt", "colx", "S", "zsum"):
+        assert tensor_rel(vd[k], vg[k]) < 1e-11, (shape, k)
+    fin = np.isfinite(vg["scal"])
+    assert np.array_equal(fin, np.isfinite(vd["scal"]))
+    assert tensor_rel(vd["scal"][fin], vg["scal"][fin]) < 1e-11
+    ed.check()
+
+
+@pytest.mark.parametrize("shape", [(3000, 256, 16), (1200, 64, 32), (900, 32, 8)])
+def test_dmma_iterations_match_oracle(eng, shape):
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.25, seed=N)
+    init = rand_init(N, D, q, seed=11)
+    o = PlateOracle(X, q, mode="B")
+    o.load_state(init)
+    e = eng(X, q, mode="B", algo="dmma")
+    e.set_state(init)
+    for it in range(5):
+        ref, got = o.iterate(), e.iterate()
+        st = e.get_state()
+        _cmp_state(st, o.state(), ("Wbar", "Wvar", "mu", "muvar", "Zbar", "Sig"), (shape, it))
+        assert abs(st["qb"] - o.qb) <= TOL * abs(o.qb)
+        assert abs(got - ref) <= TOL * abs(ref), (shape, it, got, ref)
+    e.check()
+
+
+def test_dmma_rejects_unsupported_shape(eng):
+    from pyvb_b200._cabi import PyvbError
+    X = synth_pca(40, 10, 3, 0.1, seed=1)
+    e = eng(X, 3, mode="B", algo="dmma")
+    e.set_state(rand_init(40, 10, 3))
+    with pytest.raises(PyvbError):
+        e.update_Z()
