@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the VB-PCA (missing data) hot path -- BASELINE.json's metric: rows*iterations/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA arm (one process per GPU)
+    python bench.py --impl reference [--steps K] [--warmup W]      the reference's own CPU implementation
+
+Workload (config.workload): BASELINE.json configs[1] -- N=1M rows, D=256, q=16, 20% entries missing,
+FP64, masked ("mode B") VB-PCA, synthetic data generated on the device.  With --gpus N every rank owns
+its own 1M-row shard (weak scaling); the only exchange per sweep is one NCCL all-reduce of the packed
+statistics buffer.  A "step" is one full VB sweep (W columns, Z rows, Mu, Beta, ELBO) over the shard.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "VB-PCA missing-data rows*iters/sec"
+UNIT = "rows*iters/s"
+
+
+def workload_name(a):
+    return "VB-PCA missing data N=%d (per GPU) D=%d q=%d %d%% missing FP64 mode=%s" % (
+        a.N, a.D, a.q, int(round(a.missing * 100)), a.mode)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
+        sm, smax, reasons, pw = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax = float(r[1]); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU baselines
+def _synth_host(N, D, q, missing, seed):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    W = rng.randn(D, q); Z = rng.randn(N, q); mu = rng.randn(D)
+    X = Z @ W.T + mu[None, :] + rng.randn(N, D) * np.sqrt(1.0 / 20.0)
+    X[rng.rand(N, D) < missing] = np.nan
+    return X
+
+
+def time_literal_reference(D, q, missing, rows, steps, warmup):
+    """The UNMODIFIED reference (py3-translated copy in oracle/_ref), built exactly like
+    examples/PCA_missing_data.py:31-42, one Network.learn(1) sweep per step."""
+    import numpy as np
+    from oracle.make_ref import import_ref
+    pyvb = import_ref()
+    if pyvb is None:
+        return None
+    X = _synth_host(rows, D, q, missing, seed=99)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        np.random.seed(0)
+        nodes = pyvb.nodes
+        Ws = [nodes.Gaussian(D, np.zeros((D, 1)), np.eye(D) * 1e-3) for i in range(q)]
+        W = nodes.hstack(Ws)
+        Mu = nodes.Gaussian(D, np.zeros((D, 1)), np.eye(D) * 1e-3)
+        Beta = nodes.Gamma(D, 1e-3, 1e-3)
+        Zs = [nodes.Gaussian(q, np.zeros((q, 1)), np.eye(q)) for i in range(rows)]
+        Xs = [nodes.Gaussian(D, W * z + Mu, Beta) for z in Zs]
+        [xn.observe(xv.reshape(D, 1)) for xn, xv in zip(Xs, X)]
+        net = pyvb.Network(); net.addnode(W); net.fetch_network()
+        for _ in range(warmup):
+            net.learn(1, tol=-np.inf)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            net.learn(1, tol=-np.inf)
+        dt = time.perf_counter() - t0
+    return {"value": rows * steps / dt, "seconds": dt, "rows": rows, "steps": steps}
+
+
+def time_port(D, q, missing, rows, steps, warmup):
+    """The numpy restatement (oracle/plate_oracle.py, mode B), all host cores through BLAS."""
+    import numpy as np
+    from oracle.plate_oracle import PlateOracle
+    X = _synth_host(rows, D, q, missing, seed=98)
+    o = PlateOracle(X, q, mode="B")
+    rng = np.random.RandomState(0)
+    o.Wbar = rng.randn(D, q); o.Zbar = rng.randn(rows, q)
+    for _ in range(warmup):
+        o.iterate()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.iterate()
+    dt = time.perf_counter() - t0
+    return {"value": rows * steps / dt, "seconds": dt, "rows": rows, "steps": steps}
+
+
+def cpu_baseline(a, budget_s=25.0):
+    cores = os.cpu_count() or 1
+    lit = None
+    try:
+        lit = time_literal_reference(a.D, a.q, a.missing, rows=max(1, int(budget_s / 2 / 7.0)), steps=1, warmup=0)
+    except Exception as e:  # pragma: no cover
+        lit = None
+        sys.stderr.write("literal reference failed: %r\n" % (e,))
+    port = time_port(a.D, a.q, a.missing, rows=16384, steps=1, warmup=1)
+    if lit is not None:
+        out = {"value": lit["value"], "unit": UNIT, "cores": 1, "kind": "reference",
+               "sample": "literal pyvb (py3-translated, single-threaded Python+numpy): %d rows x %d sweep of the same "
+                         "D=%d q=%d %d%%-missing workload in %.1f s (its Z step allocates 8*q^2*D^2 bytes per row)"
+                         % (lit["rows"], lit["steps"], a.D, a.q, int(a.missing * 100), lit["seconds"])}
+    else:
+        out = {"value": port["value"], "unit": UNIT, "cores": cores, "kind": "port", "sample": ""}
+    out["port"] = {"value": port["value"], "cores": cores,
+                   "sample": "numpy plate oracle (mode B, OpenBLAS on all cores): %d rows x %d sweep in %.1f s"
+                             % (port["rows"], port["steps"], port["seconds"])}
+    return out
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = max(1, a.steps + a.warmup)
+    rows = max(1, min(8, int(200.0 / (total * 7.0))))
+    res, kind, cores = None, "reference", 1
+    try:
+        res = time_literal_reference(a.D, a.q, a.missing, rows=rows, steps=a.steps, warmup=a.warmup)
+    except Exception as e:  # pragma: no cover
+        sys.stderr.write("literal reference failed: %r\n" % (e,))
+    if res is None:
+        kind, cores = "port", os.cpu_count() or 1
+        res = time_port(a.D, a.q, a.missing, rows=16384, steps=a.steps, warmup=a.warmup)
+    sample = "%d rows per step, %d steps (+%d warm-up) of the D=%d q=%d %d%%-missing workload, %.1f s" % (
+        res["rows"], res["steps"], a.warmup, a.D, a.q, int(a.missing * 100), res["seconds"])
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * res["seconds"] / max(1, a.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": sample},
+            "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def make_data(torch, N, D, q, missing, seed, dev):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    f64 = torch.float64
+    Wt = torch.randn(D, q, generator=g, device=dev, dtype=f64)
+    mu = torch.randn(D, generator=g, device=dev, dtype=f64)
+    X = torch.empty(N, D, device=dev, dtype=f64)
+    step = 1 << 16
+    for lo in range(0, N, step):
+        n = min(step, N - lo)
+        Z = torch.randn(n, q, generator=g, device=dev, dtype=f64)
+        x = Z @ Wt.t() + mu + torch.randn(n, D, generator=g, device=dev, dtype=f64) * (1.0 / 20.0) ** 0.5
+        m = torch.rand(n, D, generator=g, device=dev) < missing
+        x[m] = float("nan")
+        X[lo:lo + n] = x
+    return X
+
+
+def run_ours(a):
+    import torch
+    from pyvb_b200 import PlateEngine, _cabi
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    X = make_data(torch, a.N, a.D, a.q, a.missing, 1234 + rank, dev)
+    eng = PlateEngine(X, a.q, mode=a.mode, algo=a.algo, keep_sigma=False, distributed=(world > 1),
+                      row_offset=rank * a.N, device=dev)
+    del X
+    eng.init_random(seed=4321, rank=rank)
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(a.warmup, 3)):
+        eng.iterate_async()
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    slots = [eng.iterate_async() for _ in range(a.steps)]
+    e1.record()
+    sync()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    eng.check()
+    elbo = [float(v) for v in eng.trace[slots].cpu().tolist()]
+    value = world * a.N * a.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers: every step uploads the shard from pinned
+    # host memory, runs one sweep and reads the bound back
+    Xh = torch.empty(a.N, a.D, dtype=torch.float64, pin_memory=True)
+    Xh.copy_(eng.X)
+    res_h = torch.empty(1, dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(1, min(a.steps, 8))
+    sync()
+    e0.record()
+    for _ in range(e2e_steps):
+        eng.X.copy_(Xh, non_blocking=True)
+        slot = eng.iterate_async()
+        res_h.copy_(eng.trace[slot:slot + 1], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+    e1.record()
+    sync()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_val = world * a.N * e2e_steps / (float(ms2.item()) * 1e-3)
+    del Xh
+
+    # ---- per-kernel timing (CUDA events on the launching stream) + the FP64 tensor roofline of this box
+    def time_calls(fn, n):
+        fn(); torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n):
+            fn()
+        a1.record(); torch.cuda.synchronize(dev)
+        return a0.elapsed_time(a1) / n
+
+    eng._ensure_gw()
+    ms_z = time_calls(lambda: eng.update_Z(), 5)
+
+    def stats_call():
+        eng._stats_fresh = False
+        dflag, eng.distributed = eng.distributed, False
+        eng._ensure_stats()
+        eng.distributed = dflag
+    ms_s = time_calls(stats_call, 5)
+    scratch = torch.empty(148 * 2 * 256, dtype=torch.float64, device=dev)
+    iters = 20000
+    ms_p = min(time_calls(lambda: _cabi.check(lib.pyvb_bench_dmma_f64(148 * 2, iters, scratch.data_ptr(),
+               torch.cuda.current_stream(dev).cuda_stream), "bench_dmma"), 2) for _ in range(3))
+    peak_tf = 148 * 2 * 8 * iters * 8 * 512.0 / (ms_p * 1e-3) * 1e-12
+    D, q = a.D, a.q
+    P = q * (q + 1) // 2
+    fl_z = a.N * (2.0 * D * P + 2.0 * D * q + q ** 3 + 2.0 * q * q)      # K1 + K2 (SURVEY 8d terms)
+    fl_s = a.N * (2.0 * D * P + 4.0 * D * q)                              # K3
+    ach = fl_z / (ms_z * 1e-3) * 1e-12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("zstep_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "zstep_dmma_kernel (K1 contraction + K2 per-row solve)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+                "peak_source": "FP64 DMMA.8x8x4 loop measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
+                               "BASELINE.md section 4 asks for it to be measured on the box)",
+                "flops_per_launch": fl_z, "ms_per_launch": ms_z}
+    kernels = {"zstep_ms": ms_z, "stats_ms": ms_s, "stats_tflops": fl_s / (ms_s * 1e-3) * 1e-12,
+               "sweep_algorithmic_tflops": world * a.N * (4.0 * D * P + 6.0 * D * q + q ** 3 + 2.0 * q * q)
+               * a.steps / (ms * 1e-3) * 1e-12 / world}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "algo": a.algo, "rows_total": world * a.N,
+                           "l2": "inputs larger than L2 (X shard %.2f GB per GPU)" % (a.N * a.D * 8 / 1e9),
+                           "parallelism": "rows sharded over %d GPU(s), one all-reduce of %d doubles per sweep"
+                                          % (world, eng.L.len)},
+                "clocks": clocks, "gpu_launches": 8 * a.steps,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": a.N * a.D * 8, "d2h_bytes_per_step": 8,
+                        "steps": e2e_steps},
+                "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}
+        if world == 1 and not a.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(a)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--N", type=int, default=1000000)
+    ap.add_argument("--D", type=int, default=256)
+    ap.add_argument("--q", type=int, default=16)
+    ap.add_argument("--missing", type=float, default=0.2)
+    ap.add_argument("--mode", default="B", choices=["A", "B"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "dmma"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

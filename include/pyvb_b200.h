@@ -147,6 +147,11 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
                     const double *mu, const double *Zbar, const double *gl,
                     double *Xhat, double *V, double *qldX, void *stream);
 
+/* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
+ * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.
+ * bench.py times it with CUDA events to obtain the FP64 tensor roofline of the box it runs on. */
+int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch /* blocks*256 doubles */, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

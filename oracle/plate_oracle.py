@@ -167,8 +167,22 @@ class PlateOracle(object):
         self.qldW[i] = 0.5 / (0.5 * np.sum(np.log(prec)))
 
     def update_W(self):
-        for i in range(self.q):
-            self.update_W_col(i)
+        """All columns in sequence; the row sums are shared (one GEMM) but every column still sees the
+        already-updated columns j < i, exactly as calling update_W_col(i) for i = 0..q-1."""
+        tau, E, q = self.tau, self.E(), self.q
+        T1 = (E.T @ self.M2().reshape(self.N, q * q)).reshape(self.D, q, q)
+        R = E * (self.Xe() - self.mu[None, :])
+        T2 = R.T @ self.Zbar
+        al = self.alpha()
+        for i in range(q):
+            prec = al[i] + tau * T1[:, i, i]
+            m2 = tau * T2[:, i]
+            for j in range(q):
+                if j != i:
+                    m2 -= tau * T1[:, i, j] * self.Wbar[:, j]
+            self.Wbar[:, i] = m2 / prec
+            self.Wvar[:, i] = 1.0 / prec
+            self.qldW[i] = 0.5 / (0.5 * np.sum(np.log(prec)))
 
     def update_Z(self, lo=0, hi=None):
         """Multiplication.pass_up_m1_m2 requester=z (node.py:203-227) + Gaussian.update."""

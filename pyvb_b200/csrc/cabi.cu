@@ -164,4 +164,10 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "impute");
 }
 
+int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch, void *stream) {
+    ARG(blocks >= 1 && iters >= 1 && scratch, "blocks, iters, scratch");
+    cudaError_t e = launch_bench_dmma(blocks, iters, scratch, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "bench_dmma");
+}
+
 }  // extern "C"

@@ -44,4 +44,6 @@ int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
                               const double *M2, double *ws_main, int nchunks, cudaStream_t st);
 
+cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
+
 }  // namespace pyvb

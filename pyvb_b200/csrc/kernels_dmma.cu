@@ -352,6 +352,26 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     if (li == 0) bulk_wait_read_all();
 }
 
+// pure-DMMA loop: the FP64 tensor roofline of the box (see pyvb_bench_dmma_f64)
+__global__ void __launch_bounds__(256) bench_dmma_kernel(double *out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st) {
+    bench_dmma_kernel<<<blocks, 256, 0, st>>>(scratch, iters, 1.0000001, 0.9999999);
+    return cudaGetLastError();
+}
+
 bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32) && D >= 16 && (D % 16) == 0; }
 
 template <int Q>

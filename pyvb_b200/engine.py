@@ -202,6 +202,30 @@ class PlateEngine(object):
         self._stats_fresh = False
         self._gw_fresh = False
 
+    def init_random(self, seed=1234, rank=0):
+        """Scale-run initialisation on the device: Wbar ~ N(0,1) (same on every rank),
+        Zbar ~ N(0,1) (per-rank stream), Wvar = 1, Sigma = I, mu = 0, qb = 0.5."""
+        dev, q, P = self.device, self.q, self.P
+        g = torch.Generator(device=dev)
+        g.manual_seed(int(seed))
+        self.Wbar.normal_(generator=g)
+        self.Wvar.fill_(1.0)
+        self.mu.zero_()
+        self.muvar.fill_(1.0)
+        g.manual_seed(int(seed) + 1 + int(rank))
+        self.Zbar.normal_(generator=g)
+        ii, jj = tril_pack_index(q)
+        it, jt = torch.as_tensor(ii, device=dev), torch.as_tensor(jj, device=dev)
+        eye = (it == jt).to(torch.float64)
+        step = 1 << 16
+        for lo in range(0, self.N, step):
+            z = self.Zbar[lo:lo + step]
+            self.M2[lo:lo + step] = z[:, it] * z[:, jt] + eye
+            if self.Sig is not None:
+                self.Sig[lo:lo + step] = eye
+        self.logdet.fill_(1.0)
+        self.set_state({"qb": 0.5, "al_qb": np.ones(q)})
+
     def get_state(self):
         """Host copy of the state in the oracle's layout."""
         q = self.q
