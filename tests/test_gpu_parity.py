@@ -132,7 +132,7 @@ def test_modeB_equals_modeA_when_nothing_missing(eng):
 
 def test_nonpd_raises_linalgerror(eng):
     X = synth_pca(50, 6, 2, 0.1, seed=1)
-    e = eng(X, 2, mode="B", P0=-50.0 * np.eye(2), algo="generic")
+    e = eng(X, 2, mode="B", P0=-1e9 * np.eye(2), algo="generic")
     e.set_state(rand_init(50, 6, 2))
     e.update_Z()
     with pytest.raises(np.linalg.LinAlgError):
