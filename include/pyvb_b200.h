@@ -22,8 +22,11 @@
  *
  * Layouts (all float64, row-major):
  *   X      [N][ldx]   data; NaN = entry not observed (marginalised)
- *   Zbar   [N][q]     <z_n>
- *   M2     [N][P]     <z_n z_n^T>, packed lower triangle p(i,j) = i(i+1)/2 + j (i >= j), P = q(q+1)/2
+ *   Zbar   [N][ldz]   <z_n>
+ *   M2     [N][ldm]   <z_n z_n^T>, packed lower triangle p(i,j) = i(i+1)/2 + j (i >= j), P = q(q+1)/2
+ *                     The DMMA path wants the two interleaved in ONE array MZ [N][pyvb_mz_pitch(q)]:
+ *                     M2 = MZ, Zbar = MZ + pyvb_gw_woff(q), ldm = ldz = pyvb_mz_pitch(q), unused columns 0
+ *                     (one TMA tile then feeds the statistics GEMM, one bulk store per row leaves the Z step)
  *   Sig    [N][P]     Cov(z_n) packed (optional output)
  *   logdet [N]        ln prod diag chol(qprec_n)  (= 0.5 ln det)
  *   Gw     [D][ldg]   cols [0,P) = G_d packed, [Pp,Pp+q) = <w_d>, [Pp+q] = <mu_d>, rest zero padding;
@@ -111,7 +114,8 @@ const char *pyvb_last_error(void);
 
 /* sizes */
 int pyvb_gw_pitch(int q);                              /* doubles per Gw row */
-int pyvb_gw_woff(int q);                               /* first <w_d> column of a Gw row */
+int pyvb_gw_woff(int q);                               /* first <w_d> column of a Gw row (= zbar offset in MZ) */
+int pyvb_mz_pitch(int q);                              /* doubles per row of the interleaved [M2 | zbar] array */
 size_t pyvb_stats_len(int D, int q);                   /* doubles */
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo);
 int pyvb_algo_supported(int algo, int D, int q);       /* 1/0 */
@@ -123,13 +127,15 @@ int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const
  * (constant) prior of z.  Sig may be NULL.  Non-PD rows are counted into gl[PYVB_GL_NONPD]. */
 int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
                    const double *P0, const double *h0, double *gl,
-                   double *Zbar, double *M2, double *Sig, double *logdet, int algo, void *stream);
+                   double *Zbar, long long ldz, double *M2, long long ldm, double *Sig, double *logdet,
+                   int algo, void *stream);
 
 /* K3+K4 over rows [0,N) into `stats` (fully overwritten).  V, Xorig, qldX are mode-A only (NULL in
  * mode B).  ws: pyvb_stats_workspace_bytes(). */
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
-                   const double *Xorig, const double *qldX, const double *Zbar, const double *M2,
-                   const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo, void *stream);
+                   const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
+                   long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo,
+                   void *stream);
 
 /* Gauss-Seidel update of W columns [col_lo, col_hi) from the (all-reduced) stats. */
 int pyvb_wupdate_f64(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
@@ -144,7 +150,7 @@ int pyvb_global_f64(int D, int q, int ops, int col_lo, int col_hi, const double 
 /* Mode A: x_hat = observed ? x : W zbar + mu, v = observed ? 0 : 1/tau for rows [0,N) that are not
  * fully observed (pointers already offset to the first row). */
 int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
-                    const double *mu, const double *Zbar, const double *gl,
+                    const double *mu, const double *Zbar, long long ldz, const double *gl,
                     double *Xhat, double *V, double *qldX, void *stream);
 
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent

@@ -25,19 +25,20 @@ SIGNATURES = {
     "pyvb_last_error": (ctypes.c_char_p, []),
     "pyvb_gw_pitch": (c_int, [c_int]),
     "pyvb_gw_woff": (c_int, [c_int]),
+    "pyvb_mz_pitch": (c_int, [c_int]),
     "pyvb_stats_len": (c_sz, [c_int, c_int]),
     "pyvb_stats_workspace_bytes": (c_sz, [c_ll, c_int, c_int, c_int]),
     "pyvb_algo_supported": (c_int, [c_int, c_int, c_int]),
     "pyvb_pack_gw_f64": (c_int, [c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
     "pyvb_zstep_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_int, c_dp, c_dp, c_dp,
-                               c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
-    "pyvb_stats_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
+                               c_dp, c_ll, c_dp, c_ll, c_dp, c_dp, c_int, c_dp]),
+    "pyvb_stats_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_ll, c_dp, c_ll, c_dp,
                                c_dp, c_dp, c_sz, c_int, c_dp]),
     "pyvb_wupdate_f64": (c_int, [c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pyvb_global_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                 ctypes.POINTER(Consts), c_dp, c_dp]),
     "pyvb_bench_dmma_f64": (c_int, [c_int, c_int, c_dp, c_dp]),
-    "pyvb_impute_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "pyvb_impute_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),
 }
 
 _lib = None

@@ -45,6 +45,7 @@ int pyvb_gw_pitch(int q) {
 }
 
 int pyvb_gw_woff(int q) { return gw_woff(q); }
+int pyvb_mz_pitch(int q) { return pyvb_gw_pitch(q); }
 
 size_t pyvb_stats_len(int D, int q) { return StatLayout(D, q).len; }
 
@@ -76,11 +77,11 @@ int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const
 }
 
 int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
-                   const double *P0, const double *h0, double *gl, double *Zbar, double *M2, double *Sig,
-                   double *logdet, int algo, void *stream) {
+                   const double *P0, const double *h0, double *gl, double *Zbar, long long ldz, double *M2,
+                   long long ldm, double *Sig, double *logdet, int algo, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Gw && P0 && h0 && gl && Zbar && M2 && logdet, "null pointer");
-    ARG(ldx >= D, "ldx");
+    ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
     ARG(ldg >= gw_woff(q) + q + 1, "ldg");
     if (N == 0) return PYVB_OK;
     const int a = pick_algo(algo, D, q);
@@ -89,9 +90,11 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
         if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32}, D % 16 == 0");
         ARG(ldg == pyvb_gw_pitch(q), "ldg must equal pyvb_gw_pitch(q) for the DMMA path");
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
-        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, M2, Sig, logdet, (cudaStream_t)stream);
+        ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
+            "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");
+        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, M2, Sig, logdet, (cudaStream_t)stream);
     } else if (a == PYVB_ALGO_GENERIC) {
-        e = launch_zstep_generic(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, M2, Sig, logdet,
+        e = launch_zstep_generic(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, ldz, M2, ldm, Sig, logdet,
                                  (cudaStream_t)stream);
     } else {
         return fail(PYVB_EINVAL, "%s", "unknown algo");
@@ -100,11 +103,12 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
 }
 
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
-                   const double *Xorig, const double *qldX, const double *Zbar, const double *M2,
-                   const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo, void *stream) {
+                   const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
+                   long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo,
+                   void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Zbar && M2 && logdet && stats && ws, "null pointer");
-    ARG(ldx >= D, "ldx");
+    ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
     ARG((Xorig == NULL) || (V != NULL && qldX != NULL), "mode A needs V and qldX with Xorig");
     ARG(ws_bytes >= pyvb_stats_workspace_bytes(N, D, q, algo), "workspace too small");
     const StatLayout L(D, q);
@@ -116,12 +120,14 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
     if (a == PYVB_ALGO_DMMA) {
         if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32}, D % 16 == 0");
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
+        ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
+            "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");
         nch = stats_dmma_nchunks(N, D, q);
-        e = launch_stats_dmma(N, D, q, X, ldx, Zbar, M2, ws_main, nch, st);
+        e = launch_stats_dmma(N, D, q, X, ldx, M2, ws_main, nch, st);
         if (e == cudaSuccess) e = launch_colsums(N, D, q, X, ldx, ws_main, nch, st);
     } else if (a == PYVB_ALGO_GENERIC) {
         nch = stats_generic_nchunks(N);
-        e = launch_stats_generic(N, D, q, X, ldx, Zbar, M2, ws_main, nch, st);
+        e = launch_stats_generic(N, D, q, X, ldx, Zbar, ldz, M2, ldm, ws_main, nch, st);
     } else {
         return fail(PYVB_EINVAL, "%s", "unknown algo");
     }
@@ -155,12 +161,13 @@ int pyvb_global_f64(int D, int q, int ops, int col_lo, int col_hi, const double 
 }
 
 int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
-                    const double *mu, const double *Zbar, const double *gl, double *Xhat, double *V, double *qldX,
-                    void *stream) {
+                    const double *mu, const double *Zbar, long long ldz, const double *gl, double *Xhat, double *V,
+                    double *qldX, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(Xorig && Wbar && mu && Zbar && gl && Xhat && V && qldX, "null pointer");
-    ARG(ldx >= D, "ldx");
-    cudaError_t e = launch_impute(N, D, q, Xorig, ldx, Wbar, mu, Zbar, gl, Xhat, V, qldX, (cudaStream_t)stream);
+    ARG(ldx >= D && ldz >= q, "ldx, ldz");
+    cudaError_t e =
+        launch_impute(N, D, q, Xorig, ldx, Wbar, mu, Zbar, ldz, gl, Xhat, V, qldX, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "impute");
 }
 

@@ -12,11 +12,13 @@ cudaError_t launch_pack_gw(int D, int q, const double *Wbar, const double *Wvar,
                            double *Gw, int ldg, cudaStream_t st);
 cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                                  int ldg, const double *P0, const double *h0, double *gl, double *Zbar,
-                                 double *M2, double *Sig, double *logdet, cudaStream_t st);
+                                 long long ldz, double *M2, long long ldm, double *Sig, double *logdet,
+                                 cudaStream_t st);
 // main statistics: partial sums for `nchunks` row chunks into ws_main[nchunks][statlen]
 int stats_generic_nchunks(long long N);
 cudaError_t launch_stats_generic(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
-                                 const double *M2, double *ws_main, int nchunks, cudaStream_t st);
+                                 long long ldz, const double *M2, long long ldm, double *ws_main, int nchunks,
+                                 cudaStream_t st);
 cudaError_t launch_colsums(long long N, int D, int q, const double *X, long long ldx, double *ws_main, int nchunks,
                            cudaStream_t st);
 // per-row scalars: partial sums into ws_sc[nblk][PYVB_NSCAL]
@@ -32,17 +34,17 @@ cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const d
                           double *mu, double *muvar, double *gl, const double *P0, const double *h0,
                           const pyvb_consts &c, double *elbo_out, cudaStream_t st);
 cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
-                          const double *mu, const double *Zbar, const double *gl, double *Xhat, double *V,
-                          double *qldX, cudaStream_t st);
+                          const double *mu, const double *Zbar, long long ldz, const double *gl, double *Xhat,
+                          double *V, double *qldX, cudaStream_t st);
 
 // ---- FP64 tensor-core (DMMA) + TMA-bulk kernels -------------------------------
 bool dmma_supported(int D, int q);
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
-                              int ldg, const double *P0, const double *h0, double *gl, double *Zbar,
-                              double *M2, double *Sig, double *logdet, cudaStream_t st);
+                              int ldg, const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
+                              double *logdet, cudaStream_t st);
 int stats_dmma_nchunks(long long N, int D, int q);
-cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
-                              const double *M2, double *ws_main, int nchunks, cudaStream_t st);
+cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
+                              double *ws_main, int nchunks, cudaStream_t st);
 
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
 

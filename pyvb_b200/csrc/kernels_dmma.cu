@@ -1,16 +1,22 @@
-// FP64 tensor-core (DMMA.8x8x4) kernels with TMA bulk-copy staging -- the throughput path.
+// FP64 tensor-core (DMMA.8x8x4) kernels fed by TMA -- the throughput path.
 //
 //   zstep_dmma_kernel<Q>  K1: [O | O.(X-mu)] (rows x D)  @  Gw (D x (P+q))      -> per-row qprec (packed) and eta
 //                         K2: per-row Cholesky / inverse / solve with the matrix row held in registers
-//                             (lane i owns row i; q lanes per matrix), outputs leave through TMA bulk stores
+//                             (lane i owns row i; q lanes per matrix); each row leaves as ONE bulk store of
+//                             [<zz^T> packed | zbar]
 //   stats_dmma_kernel<Q>  K3: [O | O.X]^T (D x rows) @ [<zz^T> | zbar] (rows x (P+q)) -> T1, Bst, Ast (+ S, zsum)
 //
 // Reference arithmetic: nodes/node.py:203-227 (K1), nodes/gaussian.py:117-123 (K2), nodes/nodes_todo.py:50-61 (K3).
 //
-// Pipeline: one producer warp issues cp.async.bulk (SASS UBLKCP) copies that complete on mbarriers;
-// consumer warps issue mma.sync.m8n8k4.f64 (the only FP64 tensor shape the hardware has; measured 37.0 TF on
-// B200 = the roofline of this path).  Shared-memory pitches are chosen so that every fragment load is
-// bank-conflict free (pitch = 32 or 96 bytes mod 128).
+// Data movement: 2-D TMA tensor tiles (cp.async.bulk.tensor.2d, SASS UTMALDG) with 128-byte (64-byte)
+// swizzle for X, 1-D bulk copies (UBLKCP) for contiguous blocks, mbarrier full/empty pipeline; warp 0 of the
+// CTA issues the copies ST-1 stages ahead and is otherwise a normal MMA warp.  Math: mma.sync.m8n8k4.f64
+// (the only FP64 tensor shape the hardware has; measured 37.0 TF on B200 = the roofline of this path).
+// Every fragment load is bank-conflict free: the MMA row <-> tile row assignment is permuted so that the
+// four rows a half-warp touches differ in the swizzle bits, and row pitches of the non-swizzled tiles are
+// 32 or 96 bytes mod 128.
+#include <cuda.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -35,6 +41,51 @@ __host__ __device__ constexpr int c_srow(int need) {
 }
 __host__ __device__ constexpr int c_max(int a, int b) { return a > b ? a : b; }
 
+// Swizzled X tile with KC doubles per row (KC = 16: 128-byte rows, SWIZZLE_128B; KC = 8: 64-byte rows,
+// SWIZZLE_64B).  Byte offset of element (row, col) inside a tile whose base is 1024-byte aligned:
+template <int KC>
+__device__ __forceinline__ int xt_off(int row, int col) {
+    if (KC == 16) return row * 128 + ((((col >> 1) ^ (row & 7)) << 4) | ((col & 1) << 3));
+    return row * 64 + ((((col >> 1) ^ ((row >> 1) & 3)) << 4) | ((col & 1) << 3));
+}
+// MMA row g (0..7) -> tile row inside a group of 8 such that the rows g = 0..3 (one half-warp) differ in the
+// swizzle bits: KC = 16 -> {0,2,4,6 | 1,3,5,7}; KC = 8 -> {0,1,4,5 | 2,3,6,7}
+template <int KC>
+__device__ __forceinline__ int row_perm(int g) {
+    if (KC == 16) return ((g & 3) << 1) | (g >> 2);
+    return (g & 1) | (((g >> 1) & 1) << 2) | ((g >> 2) << 1);
+}
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+// row-major FP64 matrix [outer][inner] with row pitch `pitch` (doubles); box = box_outer x box_inner
+static cudaError_t make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint64_t pitch,
+                            uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return cudaErrorNotSupported;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch * sizeof(double)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int Q> struct ZC;
 template <> struct ZC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, MI = 2, OCC = 2; };
 template <> struct ZC<16> { static constexpr int WM = 4, WN = 1, RGW = 2, KC = 16, ST = 3, MI = 2, OCC = 2; };
@@ -47,19 +98,20 @@ template <int Q> struct ZT {
     static constexpr int NGW = (NG + WN - 1) / WN;
     static constexpr int R = WM * RGW * 8;
     static constexpr int NCW = WM * WN;
-    static constexpr int NTHR = NCW * 32;       // no dedicated producer warp: warp 0 also issues the bulk copies
-    static constexpr int LDG = c_gw_pitch(Q);
+    static constexpr int NTHR = NCW * 32;       // no dedicated producer warp: warp 0 also issues the copies
+    static constexpr int LDG = c_gw_pitch(Q);   // pitch of Gw rows and of the interleaved MZ rows
     static constexpr int MUCOL = PP + Q;
-    static constexpr int XP = KC + 4;
-    static constexpr int XS_D = R * XP, GS_D = KC * LDG, STAGE_D = XS_D + GS_D;
+    static constexpr int XT_B = R * KC * 8;     // swizzled X tile (bytes), multiple of 1024
+    static constexpr int GS_B = KC * LDG * 8;
     static constexpr int SPL = Q * (Q + 2) / 2;
     static constexpr int SROW = c_srow(SPL + Q);
-    static constexpr int MAIN_D = c_max(ST * STAGE_D, R * SROW);
+    static constexpr int MAIN_B = (c_max(ST * (XT_B + GS_B), R * SROW * 8) + 15) & ~15;
     static constexpr int G = 32 / Q;            // matrices side by side in a warp
     static constexpr int RPP = G * MI;          // rows per warp pass
     static constexpr int XR_D = NCW * 2 * MI * 32;
-    static constexpr size_t SMEM = (size_t)(MAIN_D + P + Q + XR_D) * 8 + 2 * ST * 8 + ((P * 2 + 15) & ~15);
+    static constexpr size_t SMEM = 1024 + (size_t)MAIN_B + (size_t)(P + Q + XR_D) * 8 + 2 * ST * 8 + ((P * 2 + 15) & ~15);
     static_assert(R % (NCW * RPP) == 0, "rows must split evenly over the K2 passes");
+    static_assert(XT_B % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
 };
 
 // ------------------------------------------------------------------ K2: per-row Cholesky inverse in registers
@@ -169,14 +221,16 @@ __device__ __forceinline__ void k2_solve(double *const (&A)[MI], double *xbuf, c
 // ------------------------------------------------------------------ Z step kernel
 template <int Q>
 __global__ void __launch_bounds__(ZT<Q>::NTHR, ZC<Q>::OCC)
-zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ Gw,
+zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, const double *__restrict__ Gw,
                   const double *__restrict__ P0, const double *__restrict__ h0, double *gl,
-                  double *__restrict__ Zbar, double *__restrict__ M2, double *__restrict__ Sig,
-                  double *__restrict__ logdet) {
+                  double *__restrict__ MZ, double *__restrict__ Sig, double *__restrict__ logdet) {
     using T = ZT<Q>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *smem = reinterpret_cast<double *>(smem_raw);
-    double *p0v = smem + T::MAIN_D;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *xs_base = smem;                              // ST swizzled X tiles
+    unsigned char *gs_base = smem + T::ST * T::XT_B;            // ST Gw chunks
+    double *stg = reinterpret_cast<double *>(smem);             // epilogue staging aliases the pipeline buffers
+    double *p0v = reinterpret_cast<double *>(smem + T::MAIN_B);
     double *h0s = p0v + T::P;
     double *xr = h0s + Q;
     uint64_t *full = reinterpret_cast<uint64_t *>(xr + T::XR_D);
@@ -195,6 +249,7 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     }
     if (tid < Q) h0s[tid] = h0[tid];
     if (tid == 0) {
+        tma_prefetch_desc(&tmX);
         for (int s = 0; s < T::ST; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], T::NCW);
@@ -203,21 +258,17 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     }
     __syncthreads();
 
-    // ===================== producer role (warp 0): TMA bulk copies, ST-1 chunks ahead =====================
+    // ===================== producer role (warp 0, one lane): two TMA copies per stage =====================
     auto produce = [&](int kc) {
         const int s = kc % T::ST;
         const uint32_t ph = (uint32_t)((kc / T::ST) & 1);
         mbar_wait(&empty[s], ph ^ 1);
-        double *xs = smem + s * T::STAGE_D;
-        double *gs = xs + T::XS_D;
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)((T::GS_D + T::R * T::KC) * 8));
-        __syncwarp();
-        if (lane == 0) bulk_g2s(gs, Gw + (size_t)kc * T::KC * T::LDG, T::GS_D * 8, &full[s]);
-        for (int r = lane; r < T::R; r += 32) {
-            long long row = row0 + r;
-            if (row >= N) row = N - 1;   // tail tile: duplicate a valid row, results are discarded
-            bulk_g2s(xs + r * T::XP, X + row * ldx + (long long)kc * T::KC, T::KC * 8, &full[s]);
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::GS_B));
+            tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);   // rows past N: zero fill
+            bulk_g2s(gs_base + s * T::GS_B, Gw + (size_t)kc * T::KC * T::LDG, T::GS_B, &full[s]);
         }
+        __syncwarp();
     };
     if (warp == 0)
         for (int kc = 0; kc < T::ST - 1 && kc < nk; ++kc) produce(kc);
@@ -225,6 +276,7 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     // ===================== DMMA main loop =====================
     const int wm = warp / T::WN, wn = warp % T::WN;
     const int gid = lane >> 2, qd = lane & 3;
+    const int prow = row_perm<T::KC>(gid);                 // tile row (within a group of 8) of MMA row gid
     const int cg0 = wn * T::NGW;
     const int ncg = (T::NG - cg0 < T::NGW) ? (T::NG - cg0) : T::NGW;
     double acc[T::RGW][T::NGW][2];
@@ -233,13 +285,16 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
 #pragma unroll
         for (int j = 0; j < T::NGW; ++j) acc[rg][j][0] = acc[rg][j][1] = 0.0;
     {
+        int xo[T::KC / 4];                                  // swizzled byte offsets of this lane's X element
+#pragma unroll
+        for (int kk = 0; kk < T::KC / 4; ++kk) xo[kk] = xt_off<T::KC>(wm * T::RGW * 8 + prow, kk * 4 + qd);
         int s = 0;
         uint32_t ph = 0;
         for (int kc = 0; kc < nk; ++kc) {
             if (warp == 0 && kc + T::ST - 1 < nk) produce(kc + T::ST - 1);
             mbar_wait(&full[s], ph);
-            const double *xs = smem + s * T::STAGE_D + (wm * T::RGW * 8 + gid) * T::XP + qd;
-            const double *gs = smem + s * T::STAGE_D + T::XS_D + qd * T::LDG;
+            const unsigned char *xs = xs_base + s * T::XT_B;
+            const double *gs = reinterpret_cast<const double *>(gs_base + s * T::GS_B) + qd * T::LDG;
 #pragma unroll
             for (int kk = 0; kk < T::KC / 4; ++kk) {
                 const double *grow = gs + kk * 4 * T::LDG;
@@ -247,7 +302,8 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
                 double ao[T::RGW], ax[T::RGW];
 #pragma unroll
                 for (int rg = 0; rg < T::RGW; ++rg) {
-                    const double x = xs[rg * 8 * T::XP + kk * 4];
+                    // rows of group rg sit 8 tile rows further: +8 rows keeps (row & 7) and ((row >> 1) & 3)
+                    const double x = *reinterpret_cast<const double *>(xs + xo[kk] + rg * 8 * T::KC * 8);
                     const bool ob = (x == x);          // NaN = not observed
                     ao[rg] = ob ? 1.0 : 0.0;
                     ax[rg] = ob ? (x - muv) : 0.0;
@@ -275,10 +331,9 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     // ===================== epilogue: accumulators -> staging (aliases the pipeline buffers) =====================
     named_bar_sync(1, T::NCW * 32);
     const double tau = gl[PYVB_GL_TAU];
-    double *stg = smem;
 #pragma unroll
     for (int rg = 0; rg < T::RGW; ++rg) {
-        double *srow = stg + (size_t)(wm * T::RGW * 8 + rg * 8 + gid) * T::SROW;
+        double *srow = stg + (size_t)(wm * T::RGW * 8 + rg * 8 + prow) * T::SROW;
 #pragma unroll
         for (int j = 0; j < T::NGW; ++j) {
             if (T::WN > 1 && j >= ncg) continue;
@@ -313,7 +368,7 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
         double Sg[T::MI][Q], z[T::MI], ldet[T::MI];
         bool ok = true;
         k2_solve<Q, T::MI>(A, xbuf, li, offli, Sg, z, ldet, ok);
-        // publish z (buffer 0), then second moments; staging row is reused as the output row
+        // publish z (buffer 0); the staging row becomes the output row [<zz^T> packed | 0 | zbar]
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) xbuf[m * 32 + lane] = z[m];
         __syncwarp();
@@ -330,7 +385,8 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
                     if (sgl) sgl[j] = Sg[m][j];
                 }
             }
-            A[m][T::SPL + li] = z[m];
+            if (li < T::PP - T::P) A[m][T::P + li] = 0.0;
+            A[m][T::PP + li] = z[m];
             if (li == 0 && valid) {
                 logdet[nrow[m]] = ldet[m];
                 if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
@@ -340,12 +396,8 @@ zstep_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
         __syncwarp();
         if (li == 0) {
 #pragma unroll
-            for (int m = 0; m < T::MI; ++m) {
-                if (nrow[m] < N) {
-                    bulk_s2g(M2 + nrow[m] * T::P, A[m], T::P * 8);
-                    bulk_s2g(Zbar + nrow[m] * Q, A[m] + T::SPL, Q * 8);
-                }
-            }
+            for (int m = 0; m < T::MI; ++m)
+                if (nrow[m] < N) bulk_s2g(MZ + nrow[m] * T::LDG, A[m], (T::PP + Q) * 8);
             bulk_commit();
         }
     }
@@ -376,27 +428,29 @@ bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32) && D >
 
 template <int Q>
 static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long ldx, const double *Gw,
-                                  const double *P0, const double *h0, double *gl, double *Zbar, double *M2,
-                                  double *Sig, double *logdet, cudaStream_t st) {
+                                  const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
+                                  double *logdet, cudaStream_t st) {
     using T = ZT<Q>;
-    cudaError_t e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)T::SMEM);
+    CUtensorMap tmX;
+    cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, T::KC, T::R,
+                             T::KC == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     const long long blocks = (N + T::R - 1) / T::R;
-    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig,
-                                                                     logdet);
+    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, Sig, logdet);
     return cudaGetLastError();
 }
 
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
-                              const double *P0, const double *h0, double *gl, double *Zbar, double *M2,
-                              double *Sig, double *logdet, cudaStream_t st) {
+                              const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
+                              double *logdet, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     if (ldg != c_gw_pitch(q)) return cudaErrorInvalidValue;
     switch (q) {
-        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig, logdet, st);
-        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig, logdet, st);
-        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, Zbar, M2, Sig, logdet, st);
+        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, st);
+        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, st);
+        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, st);
     }
     return cudaErrorNotSupported;
 }
@@ -413,26 +467,30 @@ template <int Q> struct STT {
     static constexpr int NGO = (PP + Q) / 8, NGX = Q / 8, NG = NGO + NGX;   // O-type: [<zz^T> | pad | zbar]; X-type: zbar
     static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST;
     static constexpr int NGW = (NG + WN - 1) / WN;
-    static constexpr int DT = WM * RGW * 8;     // data dimensions per CTA
+    static constexpr int DT = WM * RGW * 8;     // data dimensions per CTA (multiple of 16)
+    static constexpr int NSUB = DT / 16;        // swizzled X sub-tiles [KC rows][16 d] per stage
     static constexpr int NCW = WM * WN;
     static constexpr int NTHR = NCW * 32;       // warp 0 doubles as the producer
-    static constexpr int VP = c_gw_pitch(Q);    // pitch of the [<zz^T> | zbar] tile rows
-    static constexpr int AP = DT + 4;           // pitch of the X tile rows (= 4 mod 16 doubles)
-    static constexpr int AS_D = KC * AP, VS_D = KC * VP, STAGE_D = AS_D + VS_D;
-    static constexpr size_t SMEM = (size_t)(ST * STAGE_D) * 8 + 2 * ST * 8;
-    static_assert(AP % 16 == 4 || AP % 16 == 12, "X tile pitch must avoid bank conflicts");
+    static constexpr int VP = c_gw_pitch(Q);    // pitch of the MZ rows (global and in shared memory)
+    static constexpr bool BTILE = VP <= 256;    // MZ tile through one tensor copy (box dims are limited to 256)
+    static constexpr int SUB_B = KC * 128;
+    static constexpr int AS_B = NSUB * SUB_B, VS_B = KC * VP * 8;
+    static constexpr size_t SMEM = 1024 + (size_t)ST * (AS_B + VS_B) + 2 * ST * 8;
+    static_assert(DT % 16 == 0 && SUB_B % 1024 == 0, "sub-tiles must stay 1024-byte aligned");
 };
 
 // grid.x = number of d tiles + 1 (the last one is the "virtual" all-ones row that yields S and zsum),
 // grid.y = row chunks.  Partial sums go to ws[chunk][stat layout]; a second kernel adds the chunks.
 template <int Q>
 __global__ void __launch_bounds__(STT<Q>::NTHR, SC<Q>::OCC)
-stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ Zbar,
-                  const double *__restrict__ M2, double *__restrict__ ws, long long rows_per_chunk) {
+stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV, long long N, int D,
+                  const double *__restrict__ MZ, double *__restrict__ ws, long long rows_per_chunk) {
     using T = STT<Q>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *smem = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + T::ST * T::STAGE_D);
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char *as_base = smem;                          // ST x NSUB swizzled X sub-tiles
+    unsigned char *vs_base = smem + T::ST * T::AS_B;        // ST MZ tiles [KC][VP]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + T::ST * (T::AS_B + T::VS_B));
     uint64_t *empty = full + T::ST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -440,19 +498,15 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     const bool virt = ((int)blockIdx.x == ndt);
     const int d0 = blockIdx.x * T::DT;
     const int dvalid = virt ? 0 : ((D - d0 < T::DT) ? (D - d0) : T::DT);
+    const int nsub = dvalid / 16;
     const long long r0 = (long long)blockIdx.y * rows_per_chunk;
     long long r1 = r0 + rows_per_chunk;
     if (r1 > N) r1 = N;
     const int nsteps = (r1 > r0) ? (int)((r1 - r0 + T::KC - 1) / T::KC) : 0;
 
-    // zero the pad columns of the V tiles once (bulk copies never touch them)
-    for (int idx = tid; idx < T::ST * T::KC * (T::VP - T::P); idx += T::NTHR) {
-        const int s = idx / (T::KC * (T::VP - T::P));
-        const int rem = idx % (T::KC * (T::VP - T::P));
-        const int r = rem / (T::VP - T::P), c = T::P + rem % (T::VP - T::P);
-        if (c < T::PP || c >= T::PP + Q) smem[s * T::STAGE_D + T::AS_D + r * T::VP + c] = 0.0;
-    }
     if (tid == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmV);
         for (int s = 0; s < T::ST; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], T::NCW);
@@ -462,29 +516,33 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     __syncthreads();
 
     // ===================== producer role (warp 0) =====================
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     auto produce = [&](int it) {
         const int s = it % T::ST;
         const uint32_t ph = (uint32_t)((it / T::ST) & 1);
         mbar_wait(&empty[s], ph ^ 1);
-        double *as = smem + s * T::STAGE_D;
-        double *vs = as + T::AS_D;
-        const long long nb = r0 + (long long)it * T::KC;
-        const int nval = (r1 - nb < T::KC) ? (int)(r1 - nb) : T::KC;
-        // rows past the end of the chunk: X -> NaN (mask 0), V -> 0
-        for (int r = nval; r < T::KC; ++r) {
-            for (int c = lane; c < T::AP; c += 32) as[r * T::AP + c] = qnan;
-            for (int c = lane; c < T::VP; c += 32) vs[r * T::VP + c] = 0.0;
+        const long long nb = r0 + (long long)it * T::KC;     // chunk boundaries are multiples of KC; rows >= N are
+        double *vs = reinterpret_cast<double *>(vs_base + s * T::VS_B);   // zero filled by the tensor copies
+        if (T::BTILE) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(nsub * T::SUB_B + T::VS_B));
+                for (int t = 0; t < nsub; ++t)
+                    tma_load_2d(as_base + s * T::AS_B + t * T::SUB_B, &tmX, d0 + t * 16, (int)nb, &full[s]);
+                tma_load_2d(vs, &tmV, 0, (int)nb, &full[s]);
+            }
+        } else {
+            const int nval = (N - nb < T::KC) ? (int)(N - nb) : T::KC;
+            for (int r = nval; r < T::KC; ++r)
+                for (int c = lane; c < T::VP; c += 32) vs[r * T::VP + c] = 0.0;
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(nsub * T::SUB_B + nval * (T::PP + Q) * 8));
+                for (int t = 0; t < nsub; ++t)
+                    tma_load_2d(as_base + s * T::AS_B + t * T::SUB_B, &tmX, d0 + t * 16, (int)nb, &full[s]);
+            }
+            __syncwarp();
+            if (lane < nval) bulk_g2s(vs + lane * T::VP, MZ + (nb + lane) * T::VP, (T::PP + Q) * 8, &full[s]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(nval * ((virt ? 0 : dvalid) + T::P + Q) * 8));
-        __syncwarp();
-        if (lane < nval) {
-            const long long n = nb + lane;
-            if (!virt) bulk_g2s(as + lane * T::AP, X + n * ldx + d0, dvalid * 8, &full[s]);
-            bulk_g2s(vs + lane * T::VP, M2 + n * T::P, T::P * 8, &full[s]);
-            bulk_g2s(vs + lane * T::VP + T::PP, Zbar + n * Q, Q * 8, &full[s]);
-        }
     };
     if (warp == 0)
         for (int it = 0; it < T::ST - 1 && it < nsteps; ++it) produce(it);
@@ -494,13 +552,24 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     const int gid = lane >> 2, qd = lane & 3;
     const int cg0 = wn * T::NGW;
     const int ncg = (T::NG - cg0 < T::NGW) ? (T::NG - cg0) : T::NGW;
-    const int dw = wm * T::RGW * 8;                       // first d of this warp inside the tile
-    const bool active = virt ? (wm == 0) : (dw < dvalid); // warp-uniform
+    const int blk0 = wm * T::RGW;                           // first group of 8 d's of this warp inside the tile
+    // MMA row gid -> d inside a 16-wide sub-tile (first or second half chosen by the group parity): the four
+    // rows of a half-warp must sit in chunks that differ in bit 2 -> {0,1,8,9 | 2,3,10,11} (+4 for odd groups)
+    const int dperm = (gid & 1) + 8 * ((gid >> 1) & 1) + 2 * (gid >> 2);
+    const bool active = virt ? (wm == 0) : (blk0 * 8 < dvalid);   // warp-uniform
     double acc[T::RGW][T::NGW][2];
 #pragma unroll
     for (int rg = 0; rg < T::RGW; ++rg)
 #pragma unroll
         for (int j = 0; j < T::NGW; ++j) acc[rg][j][0] = acc[rg][j][1] = 0.0;
+    int aoff[T::RGW];                                       // sub-tile offset + swizzle-independent part
+    int dl[T::RGW];
+#pragma unroll
+    for (int rg = 0; rg < T::RGW; ++rg) {
+        const int blk = blk0 + rg;
+        dl[rg] = 4 * (blk & 1) + dperm;
+        aoff[rg] = (blk >> 1) * T::SUB_B + ((dl[rg] & 1) << 3);
+    }
     {
         int s = 0;
         uint32_t ph = 0;
@@ -508,10 +577,11 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
             if (warp == 0 && it + T::ST - 1 < nsteps) produce(it + T::ST - 1);
             mbar_wait(&full[s], ph);
             if (active) {
-                const double *as = smem + s * T::STAGE_D + qd * T::AP + dw + gid;
-                const double *vs = smem + s * T::STAGE_D + T::AS_D + qd * T::VP + gid;
+                const unsigned char *as = as_base + s * T::AS_B;
+                const double *vs = reinterpret_cast<const double *>(vs_base + s * T::VS_B) + qd * T::VP + gid;
 #pragma unroll
                 for (int kk = 0; kk < T::KC / 4; ++kk) {
+                    const int row = kk * 4 + qd;
                     double ao[T::RGW], ax[T::RGW];
 #pragma unroll
                     for (int rg = 0; rg < T::RGW; ++rg) {
@@ -519,8 +589,10 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
                             ao[rg] = (rg == 0 && gid == 0) ? 1.0 : 0.0;
                             ax[rg] = 0.0;
                         } else {
-                            const double x = (dw + rg * 8 < dvalid) ? as[kk * 4 * T::AP + rg * 8] : qnan;
-                            const bool ob = (x == x);
+                            const bool in = (blk0 + rg) * 8 < dvalid;
+                            const int off = aoff[rg] + row * 128 + ((((dl[rg] >> 1) ^ (row & 7))) << 4);
+                            const double x = in ? *reinterpret_cast<const double *>(as + off) : 0.0;
+                            const bool ob = in && (x == x);
                             ao[rg] = ob ? 1.0 : 0.0;
                             ax[rg] = ob ? x : 0.0;
                         }
@@ -553,7 +625,7 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
     double *out = ws + (size_t)blockIdx.y * L.len;
 #pragma unroll
     for (int rg = 0; rg < T::RGW; ++rg) {
-        const int d = d0 + dw + rg * 8 + gid;
+        const int d = d0 + ((blk0 + rg) >> 1) * 16 + dl[rg];
 #pragma unroll
         for (int j = 0; j < T::NGW; ++j) {
             if (T::WN > 1 && j >= ncg) continue;
@@ -567,7 +639,7 @@ stats_dmma_kernel(long long N, int D, const double *__restrict__ X, long long ld
                         if (c < T::P) out[L.S + c] = v;
                         else if (c >= T::PP) out[L.zsum + (c - T::PP)] = v;
                     }
-                } else if (d < D) {
+                } else if (d < D && (blk0 + rg) * 8 < dvalid) {
                     if (cg < T::NGO) {
                         if (c < T::P) out[L.t1 + (size_t)d * T::P + c] = v;
                         else if (c >= T::PP) out[L.bst + (size_t)d * Q + (c - T::PP)] = v;
@@ -593,27 +665,36 @@ int stats_dmma_nchunks(long long N, int D, int q) {
 }
 
 template <int Q>
-static cudaError_t launch_stats_q(long long N, int D, const double *X, long long ldx, const double *Zbar,
-                                  const double *M2, double *ws, int nchunks, cudaStream_t st) {
+static cudaError_t launch_stats_q(long long N, int D, const double *X, long long ldx, const double *MZ, double *ws,
+                                  int nchunks, cudaStream_t st) {
     using T = STT<Q>;
-    cudaError_t e = cudaFuncSetAttribute(stats_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)T::SMEM);
+    CUtensorMap tmX, tmV;
+    cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, 16, T::KC, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e != cudaSuccess) return e;
+    if (T::BTILE) {
+        e = make_map(&tmV, MZ, (uint64_t)T::VP, (uint64_t)N, (uint64_t)T::VP, T::VP, T::KC, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (e != cudaSuccess) return e;
+    } else {
+        tmV = tmX;   // unused
+    }
+    e = cudaFuncSetAttribute(stats_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     long long rpc = (N + nchunks - 1) / nchunks;
     rpc = ((rpc + T::KC - 1) / T::KC) * T::KC;                 // chunk boundaries on pipeline-step boundaries
     if (rpc < T::KC) rpc = T::KC;
     const int ndt = (D + T::DT - 1) / T::DT;
     dim3 grid((unsigned)(ndt + 1), (unsigned)nchunks);
-    stats_dmma_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(N, D, X, ldx, Zbar, M2, ws, rpc);
+    stats_dmma_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc);
     return cudaGetLastError();
 }
 
-cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
-                              const double *M2, double *ws_main, int nchunks, cudaStream_t st) {
+cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
+                              double *ws_main, int nchunks, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 8: return launch_stats_q<8>(N, D, X, ldx, Zbar, M2, ws_main, nchunks, st);
-        case 16: return launch_stats_q<16>(N, D, X, ldx, Zbar, M2, ws_main, nchunks, st);
-        case 32: return launch_stats_q<32>(N, D, X, ldx, Zbar, M2, ws_main, nchunks, st);
+        case 8: return launch_stats_q<8>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+        case 16: return launch_stats_q<16>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+        case 32: return launch_stats_q<32>(N, D, X, ldx, MZ, ws_main, nchunks, st);
     }
     return cudaErrorNotSupported;
 }

@@ -54,8 +54,9 @@ template <int NT, int WPB>
 __global__ void __launch_bounds__(32 * WPB)
 zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, long long ldx,
                      const double *__restrict__ Gw, int ldg, const double *__restrict__ P0,
-                     const double *__restrict__ h0, double *gl, double *__restrict__ Zbar,
-                     double *__restrict__ M2, double *__restrict__ Sig, double *__restrict__ logdet) {
+                     const double *__restrict__ h0, double *gl, double *__restrict__ Zbar, long long ldz,
+                     double *__restrict__ M2, long long ldm, double *__restrict__ Sig,
+                     double *__restrict__ logdet) {
     extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int P = tri(q), Pp = gw_woff(q), C = P + q;
@@ -139,14 +140,14 @@ zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
             double z = 0.0;
             for (int j = 0; j < q; ++j) z = fma(sv[r * pitch + j], eta[j], z);
             zb[r] = z;
-            Zbar[n * q + r] = z;
+            Zbar[n * ldz + r] = z;
         }
         __syncwarp();
         for (int p = lane; p < P; p += 32) {
             int i, j;
             unpack_p(p, i, j);
             const double sg = 0.5 * (sv[i * pitch + j] + sv[j * pitch + i]);
-            M2[n * P + p] = fma(zb[i], zb[j], sg);
+            M2[n * ldm + p] = fma(zb[i], zb[j], sg);
             if (Sig) Sig[n * P + p] = sg;
         }
         if (lane == 0) {
@@ -159,7 +160,8 @@ zstep_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
 
 cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                                  int ldg, const double *P0, const double *h0, double *gl, double *Zbar,
-                                 double *M2, double *Sig, double *logdet, cudaStream_t st) {
+                                 long long ldz, double *M2, long long ldm, double *Sig, double *logdet,
+                                 cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int C = tri(q) + q;
     const int nt = (C + 31) / 32;
@@ -173,7 +175,7 @@ cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, lon
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
         if (e != cudaSuccess) return e;                                                                        \
         zstep_generic_kernel<NT, WPB><<<(unsigned)blocks, 32 * WPB, smem, st>>>(                               \
-            N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, M2, Sig, logdet);                                      \
+            N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, ldz, M2, ldm, Sig, logdet);                            \
     } while (0)
     if (nt <= 1) PYVB_LAUNCH_Z(1, 4);
     else if (nt <= 2) PYVB_LAUNCH_Z(2, 4);
@@ -189,8 +191,8 @@ cudaError_t launch_zstep_generic(long long N, int D, int q, const double *X, lon
 // sums (deterministic two-stage reduction).
 __global__ void __launch_bounds__(256)
 stats_generic_kernel(long long N, int D, int q, const double *__restrict__ X, long long ldx,
-                     const double *__restrict__ Zbar, const double *__restrict__ M2, double *__restrict__ ws,
-                     long long rows_per_chunk) {
+                     const double *__restrict__ Zbar, long long ldz, const double *__restrict__ M2,
+                     long long ldm, double *__restrict__ ws, long long rows_per_chunk) {
     const StatLayout L(D, q);
     const int P = L.P;
     const int CT = P + 2 * q + 2;
@@ -207,21 +209,21 @@ stats_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
             if (c < P) {
                 for (long long n = r0; n < r1; ++n) {
                     const double x = X[n * ldx + d];
-                    if (x == x) acc += M2[n * P + c];
+                    if (x == x) acc += M2[n * ldm + c];
                 }
                 dest = L.t1 + (size_t)d * P + c;
             } else if (c < P + q) {
                 const int i = c - P;
                 for (long long n = r0; n < r1; ++n) {
                     const double x = X[n * ldx + d];
-                    if (x == x) acc += Zbar[n * q + i];
+                    if (x == x) acc += Zbar[n * ldz + i];
                 }
                 dest = L.bst + (size_t)d * q + i;
             } else if (c < P + 2 * q) {
                 const int i = c - P - q;
                 for (long long n = r0; n < r1; ++n) {
                     const double x = X[n * ldx + d];
-                    if (x == x) acc = fma(x, Zbar[n * q + i], acc);
+                    if (x == x) acc = fma(x, Zbar[n * ldz + i], acc);
                 }
                 dest = L.ast + (size_t)d * q + i;
             } else if (c == P + 2 * q) {
@@ -240,10 +242,10 @@ stats_generic_kernel(long long N, int D, int q, const double *__restrict__ X, lo
         } else {
             const int c = (int)(o - (long long)D * CT);
             if (c < P) {
-                for (long long n = r0; n < r1; ++n) acc += M2[n * P + c];
+                for (long long n = r0; n < r1; ++n) acc += M2[n * ldm + c];
                 dest = L.S + c;
             } else {
-                for (long long n = r0; n < r1; ++n) acc += Zbar[n * q + (c - P)];
+                for (long long n = r0; n < r1; ++n) acc += Zbar[n * ldz + (c - P)];
                 dest = L.zsum + (c - P);
             }
         }
@@ -259,14 +261,15 @@ int stats_generic_nchunks(long long N) {
 }
 
 cudaError_t launch_stats_generic(long long N, int D, int q, const double *X, long long ldx, const double *Zbar,
-                                 const double *M2, double *ws_main, int nchunks, cudaStream_t st) {
+                                 long long ldz, const double *M2, long long ldm, double *ws_main, int nchunks,
+                                 cudaStream_t st) {
     const int P = tri(q);
     const long long nout = (long long)D * (P + 2 * q + 2) + P + q;
     long long bx = (nout + 255) / 256;
     if (bx > 4096) bx = 4096;
     const long long rpc = (N + nchunks - 1) / nchunks;
     dim3 grid((unsigned)bx, (unsigned)nchunks);
-    stats_generic_kernel<<<grid, 256, 0, st>>>(N, D, q, X, ldx, Zbar, M2, ws_main, rpc > 0 ? rpc : 1);
+    stats_generic_kernel<<<grid, 256, 0, st>>>(N, D, q, X, ldx, Zbar, ldz, M2, ldm, ws_main, rpc > 0 ? rpc : 1);
     return cudaGetLastError();
 }
 
@@ -625,7 +628,7 @@ cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const d
 __global__ void __launch_bounds__(256)
 impute_kernel(long long N, int D, int q, const double *__restrict__ Xorig, long long ldx,
               const double *__restrict__ Wbar, const double *__restrict__ mu, const double *__restrict__ Zbar,
-              const double *__restrict__ gl, double *__restrict__ Xhat, double *__restrict__ V,
+              long long ldz, const double *__restrict__ gl, double *__restrict__ Xhat, double *__restrict__ V,
               double *__restrict__ qldX) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const double tau = gl[PYVB_GL_TAU];
@@ -636,7 +639,7 @@ impute_kernel(long long N, int D, int q, const double *__restrict__ Xorig, long 
         for (int d = lane; d < D; d += 32) nmiss += (xo[d] != xo[d]) ? 1 : 0;
         nmiss = __reduce_add_sync(0xffffffffu, nmiss);
         if (nmiss == 0) continue;  // fully observed rows are never updated (gaussian.py:109-110)
-        const double *z = Zbar + n * q;
+        const double *z = Zbar + n * ldz;
         for (int d = lane; d < D; d += 32) {
             const double x = xo[d];
             const bool miss = (x != x);
@@ -650,12 +653,12 @@ impute_kernel(long long N, int D, int q, const double *__restrict__ Xorig, long 
 }
 
 cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long long ldx, const double *Wbar,
-                          const double *mu, const double *Zbar, const double *gl, double *Xhat, double *V,
-                          double *qldX, cudaStream_t st) {
+                          const double *mu, const double *Zbar, long long ldz, const double *gl, double *Xhat,
+                          double *V, double *qldX, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     long long b = (N + 7) / 8;
     if (b > 148 * 8) b = 148 * 8;
-    impute_kernel<<<(unsigned)b, 256, 0, st>>>(N, D, q, Xorig, ldx, Wbar, mu, Zbar, gl, Xhat, V, qldX);
+    impute_kernel<<<(unsigned)b, 256, 0, st>>>(N, D, q, Xorig, ldx, Wbar, mu, Zbar, ldz, gl, Xhat, V, qldX);
     return cudaGetLastError();
 }
 

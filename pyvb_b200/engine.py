@@ -101,8 +101,12 @@ class PlateEngine(object):
         self.n_rows_total = int(self._allreduce_scalar(float(N)))
 
         # ---- latent state
-        self.Zbar = torch.zeros(N, q, dtype=f64, device=dev)
-        self.M2 = torch.zeros(N, self.P, dtype=f64, device=dev)
+        # <zz^T> (packed) and <z> interleaved in one array: one TMA tile feeds the statistics GEMM
+        self.ldmz = int(self.lib.pyvb_mz_pitch(q))
+        self.zoff = int(self.lib.pyvb_gw_woff(q))
+        self.MZ = torch.zeros(N, self.ldmz, dtype=f64, device=dev)
+        self.M2 = self.MZ[:, :self.P]
+        self.Zbar = self.MZ[:, self.zoff:self.zoff + q]
         self.Sig = torch.zeros(N, self.P, dtype=f64, device=dev) if keep_sigma else None
         self.logdet = torch.ones(N, dtype=f64, device=dev)
         self.Wbar = torch.zeros(D, q, dtype=f64, device=dev)
@@ -230,13 +234,13 @@ class PlateEngine(object):
         """Host copy of the state in the oracle's layout."""
         q = self.q
         ii, jj = tril_pack_index(q)
-        out = {k: getattr(self, k).cpu().numpy() for k in ("Wbar", "Wvar", "mu", "muvar", "Zbar")}
+        out = {k: getattr(self, k).contiguous().cpu().numpy() for k in ("Wbar", "Wvar", "mu", "muvar", "Zbar")}
         N = self.N
         if self.Sig is not None:
             sp = self.Sig.cpu().numpy()
         else:
             z = out["Zbar"]
-            sp = self.M2.cpu().numpy() - z[:, ii] * z[:, jj]
+            sp = self.M2.contiguous().cpu().numpy() - z[:, ii] * z[:, jj]
         Sig = np.zeros((N, q, q))
         Sig[:, ii, jj] = sp
         Sig[:, jj, ii] = sp
@@ -268,8 +272,8 @@ class PlateEngine(object):
         if self._stats_fresh:
             return
         rc = self.lib.pyvb_stats_f64(self.N, self.D, self.q, self.X.data_ptr(), self.D, self._p(self.V),
-                                     self._p(self.Xorig), self._p(self.qldX), self.Zbar.data_ptr(),
-                                     self.M2.data_ptr(), self.logdet.data_ptr(), self.stats.data_ptr(),
+                                     self._p(self.Xorig), self._p(self.qldX), self.Zbar.data_ptr(), self.ldmz,
+                                     self.M2.data_ptr(), self.ldmz, self.logdet.data_ptr(), self.stats.data_ptr(),
                                      self.ws.data_ptr(), self.ws_bytes, self.algo, self._stream())
         _cabi.check(rc, "pyvb_stats_f64")
         if self.distributed:
@@ -296,7 +300,8 @@ class PlateEngine(object):
         sig = 0 if self.Sig is None else self.Sig.data_ptr() + lo * P * 8
         rc = self.lib.pyvb_zstep_f64(hi - lo, D, q, self.X.data_ptr() + lo * D * 8, D, self.Gw.data_ptr(),
                                      self.ldg, self.P0.data_ptr(), self.h0.data_ptr(), self.gl.data_ptr(),
-                                     self.Zbar.data_ptr() + lo * q * 8, self.M2.data_ptr() + lo * P * 8, sig,
+                                     self.Zbar.data_ptr() + lo * self.ldmz * 8, self.ldmz,
+                                     self.M2.data_ptr() + lo * self.ldmz * 8, self.ldmz, sig,
                                      self.logdet.data_ptr() + lo * 8, self.algo, self._stream())
         _cabi.check(rc, "pyvb_zstep_f64")
         self._stats_fresh = False
@@ -311,7 +316,8 @@ class PlateEngine(object):
             return
         q, D = self.q, self.D
         rc = self.lib.pyvb_impute_f64(hi - lo, D, q, self.Xorig.data_ptr() + lo * D * 8, D, self.Wbar.data_ptr(),
-                                      self.mu.data_ptr(), self.Zbar.data_ptr() + lo * q * 8, self.gl.data_ptr(),
+                                      self.mu.data_ptr(), self.Zbar.data_ptr() + lo * self.ldmz * 8, self.ldmz,
+                                      self.gl.data_ptr(),
                                       self.X.data_ptr() + lo * D * 8, self.V.data_ptr() + lo * D * 8,
                                       self.qldX.data_ptr() + lo * 8, self._stream())
         _cabi.check(rc, "pyvb_impute_f64")
