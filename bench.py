@@ -250,7 +250,7 @@ def run_ours(a):
     sync()
     e0.record()
     for _ in range(e2e_steps):
-        eng.X.copy_(Xh, non_blocking=True)
+        eng.set_X(Xh)
         slot = eng.iterate_async()
         res_h.copy_(eng.trace[slot:slot + 1], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -315,7 +315,7 @@ def run_ours(a):
                            "l2": "inputs larger than L2 (X shard %.2f GB per GPU)" % (a.N * a.D * 8 / 1e9),
                            "parallelism": "rows sharded over %d GPU(s), one all-reduce of %d doubles per sweep"
                                           % (world, eng.L.len)},
-                "clocks": clocks, "gpu_launches": 8 * a.steps,
+                "clocks": clocks, "gpu_launches": 8 * a.steps,   # wupdate, pack_gw, zstep, stats GEMM, mzsums, rowscalars, reduce, global
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": a.N * a.D * 8, "d2h_bytes_per_step": 8,
                         "steps": e2e_steps},
                 "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}

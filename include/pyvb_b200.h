@@ -131,11 +131,15 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
                    int algo, void *stream);
 
 /* K3+K4 over rows [0,N) into `stats` (fully overwritten).  V, Xorig, qldX are mode-A only (NULL in
- * mode B).  ws: pyvb_stats_workspace_bytes(). */
+ * mode B).  ws: pyvb_stats_workspace_bytes().
+ * xcache (nullable, 2*D+2 doubles, caller-owned): the sums that depend on X alone -- cnt[D], colsumX[D],
+ * sum x^2, number of observed entries.  With xcache_valid = 0 they are computed and stored there; with
+ * xcache_valid = 1 (X unchanged since, i.e. mode B) the two passes over X are skipped and the cached local
+ * sums are used. */
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
                    const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
-                   long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo,
-                   void *stream);
+                   long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes,
+                   double *xcache, int xcache_valid, int algo, void *stream);
 
 /* Gauss-Seidel update of W columns [col_lo, col_hi) from the (all-reduced) stats. */
 int pyvb_wupdate_f64(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,

@@ -104,8 +104,8 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
 
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
                    const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
-                   long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, int algo,
-                   void *stream) {
+                   long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, double *xcache,
+                   int xcache_valid, int algo, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Zbar && M2 && logdet && stats && ws, "null pointer");
     ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
@@ -114,7 +114,7 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
     const StatLayout L(D, q);
     const int a = pick_algo(algo, D, q);
     cudaStream_t st = (cudaStream_t)stream;
-    int nch;
+    int nch, use_x = 0;
     cudaError_t e;
     double *ws_main = (double *)ws;
     if (a == PYVB_ALGO_DMMA) {
@@ -123,8 +123,10 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
         ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
             "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");
         nch = stats_dmma_nchunks(N, D, q);
+        use_x = (xcache != NULL && xcache_valid) ? 1 : 0;
         e = launch_stats_dmma(N, D, q, X, ldx, M2, ws_main, nch, st);
-        if (e == cudaSuccess) e = launch_colsums(N, D, q, X, ldx, ws_main, nch, st);
+        if (e == cudaSuccess) e = launch_mzsums(N, D, q, Zbar, ldz, M2, ldm, ws_main, nch, st);
+        if (e == cudaSuccess && !use_x) e = launch_colsums(N, D, q, X, ldx, ws_main, nch, st);
     } else if (a == PYVB_ALGO_GENERIC) {
         nch = stats_generic_nchunks(N);
         e = launch_stats_generic(N, D, q, X, ldx, Zbar, ldz, M2, ldm, ws_main, nch, st);
@@ -134,9 +136,9 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
     if (e != cudaSuccess) return cuda_fail(e, "stats");
     double *ws_sc = (double *)((char *)ws + align256((size_t)nch * L.len * sizeof(double)));
     const int nblk = rowscalars_nblk(N);
-    e = launch_rowscalars(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc, nblk, st);
+    e = launch_rowscalars(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc, nblk, use_x && Xorig == NULL, st);
     if (e != cudaSuccess) return cuda_fail(e, "rowscalars");
-    e = launch_stats_reduce(D, q, ws_main, nch, ws_sc, nblk, stats, st);
+    e = launch_stats_reduce(D, q, ws_main, nch, ws_sc, nblk, stats, xcache, use_x, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
 }
 

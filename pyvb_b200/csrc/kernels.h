@@ -25,9 +25,12 @@ cudaError_t launch_colsums(long long N, int D, int q, const double *X, long long
 int rowscalars_nblk(long long N);
 cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx, const double *V,
                               const double *Xorig, const double *qldX, const double *logdet, double *ws_sc,
-                              int nblk, cudaStream_t st);
+                              int nblk, int skip_x, cudaStream_t st);
+// column sums of the [M2 | zbar] rows -> S, zsum partials (DMMA path)
+cudaError_t launch_mzsums(long long N, int D, int q, const double *Zbar, long long ldz, const double *M2,
+                          long long ldm, double *ws_main, int nchunks, cudaStream_t st);
 cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
-                                double *stats, cudaStream_t st);
+                                double *stats, double *xcache, int use_xcache, cudaStream_t st);
 cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
                            const double *gl, double *Wbar, double *Wvar, cudaStream_t st);
 cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,

@@ -4,7 +4,7 @@
 //                         K2: per-row Cholesky / inverse / solve with the matrix row held in registers
 //                             (lane i owns row i; q lanes per matrix); each row leaves as ONE bulk store of
 //                             [<zz^T> packed | zbar]
-//   stats_dmma_kernel<Q>  K3: [O | O.X]^T (D x rows) @ [<zz^T> | zbar] (rows x (P+q)) -> T1, Bst, Ast (+ S, zsum)
+//   stats_dmma_kernel<Q>  K3: [O | O.X]^T (D x rows) @ [<zz^T> | zbar] (rows x (P+q)) -> T1, Bst, Ast
 //
 // Reference arithmetic: nodes/node.py:203-227 (K1), nodes/gaussian.py:117-123 (K2), nodes/nodes_todo.py:50-61 (K3).
 //
@@ -226,7 +226,9 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
                   double *__restrict__ MZ, double *__restrict__ Sig, double *__restrict__ logdet) {
     using T = ZT<Q>;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
+    // shared address space so that fragment loads compile to LDS, not generic LD
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char *xs_base = smem;                              // ST swizzled X tiles
     unsigned char *gs_base = smem + T::ST * T::XT_B;            // ST Gw chunks
     double *stg = reinterpret_cast<double *>(smem);             // epilogue staging aliases the pipeline buffers
@@ -479,25 +481,26 @@ template <int Q> struct STT {
     static_assert(DT % 16 == 0 && SUB_B % 1024 == 0, "sub-tiles must stay 1024-byte aligned");
 };
 
-// grid.x = number of d tiles + 1 (the last one is the "virtual" all-ones row that yields S and zsum),
-// grid.y = row chunks.  Partial sums go to ws[chunk][stat layout]; a second kernel adds the chunks.
+// grid.x = number of d tiles, grid.y = row chunks.  Partial sums go to ws[chunk][stat layout]; a second
+// kernel adds the chunks in a fixed order (deterministic).
 template <int Q>
 __global__ void __launch_bounds__(STT<Q>::NTHR, SC<Q>::OCC)
 stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV, long long N, int D,
                   const double *__restrict__ MZ, double *__restrict__ ws, long long rows_per_chunk) {
     using T = STT<Q>;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
+    // shared address space so that fragment loads compile to LDS, not generic LD
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char *as_base = smem;                          // ST x NSUB swizzled X sub-tiles
     unsigned char *vs_base = smem + T::ST * T::AS_B;        // ST MZ tiles [KC][VP]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + T::ST * (T::AS_B + T::VS_B));
     uint64_t *empty = full + T::ST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ndt = (D + T::DT - 1) / T::DT;
-    const bool virt = ((int)blockIdx.x == ndt);
+    constexpr bool virt = false;
     const int d0 = blockIdx.x * T::DT;
-    const int dvalid = virt ? 0 : ((D - d0 < T::DT) ? (D - d0) : T::DT);
+    const int dvalid = (D - d0 < T::DT) ? (D - d0) : T::DT;
     const int nsub = dvalid / 16;
     const long long r0 = (long long)blockIdx.y * rows_per_chunk;
     long long r1 = r0 + rows_per_chunk;
@@ -591,7 +594,7 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         } else {
                             const bool in = (blk0 + rg) * 8 < dvalid;
                             const int off = aoff[rg] + row * 128 + ((((dl[rg] >> 1) ^ (row & 7))) << 4);
-                            const double x = in ? *reinterpret_cast<const double *>(as + off) : 0.0;
+                            const double x = *reinterpret_cast<const double *>(as + off);   // stale data if !in
                             const bool ob = in && (x == x);
                             ao[rg] = ob ? 1.0 : 0.0;
                             ax[rg] = ob ? x : 0.0;
@@ -652,15 +655,21 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     }
 }
 
+static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : a; }
+
 int stats_dmma_nchunks(long long N, int D, int q) {
     int kc = 16, dt = 128;
     if (q == 32) { kc = 8; dt = 32; }
-    const int ndt = (D + dt - 1) / dt + 1;
-    long long target = (148LL * 4 + ndt - 1) / ndt;            // ~4 CTAs per SM overall
+    const int ndt = (D + dt - 1) / dt;
+    // CTAs = ndt * nchunks should be a whole number of waves of 148 SMs (1 CTA/SM): nchunks = k * step
+    const long long step = 148 / gcdll(148, ndt);
     long long by_rows = (N + 64LL * kc - 1) / (64LL * kc);     // at least 64 pipeline steps per chunk
-    long long c = target < by_rows ? target : by_rows;
-    if (c < 1) c = 1;
-    if (c > 512) c = 512;
+    long long k = (4 * 148LL) / (step * ndt);                  // ~4 waves
+    if (k < 1) k = 1;
+    long long c = k * step;
+    if (c > by_rows) c = (by_rows / step) * step;              // few rows: fewer whole waves ...
+    if (c < 1) c = by_rows < 1 ? 1 : by_rows;                  // ... or simply one chunk per 64 steps
+    if (c > 1024) c = 1024;
     return (int)c;
 }
 
@@ -683,7 +692,7 @@ static cudaError_t launch_stats_q(long long N, int D, const double *X, long long
     rpc = ((rpc + T::KC - 1) / T::KC) * T::KC;                 // chunk boundaries on pipeline-step boundaries
     if (rpc < T::KC) rpc = T::KC;
     const int ndt = (D + T::DT - 1) / T::DT;
-    dim3 grid((unsigned)(ndt + 1), (unsigned)nchunks);
+    dim3 grid((unsigned)ndt, (unsigned)nchunks);
     stats_dmma_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc);
     return cudaGetLastError();
 }

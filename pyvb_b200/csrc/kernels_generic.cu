@@ -326,11 +326,51 @@ cudaError_t launch_colsums(long long N, int D, int q, const double *X, long long
     return cudaGetLastError();
 }
 
+// =============================================================== column sums of [M2 | zbar] -> S, zsum
+template <int ROWS>
+__global__ void __launch_bounds__(128)
+mzsums_kernel(long long N, int D, int q, const double *__restrict__ Zbar, long long ldz,
+              const double *__restrict__ M2, long long ldm, double *__restrict__ ws, long long rows_per_chunk) {
+    const StatLayout L(D, q);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= L.P + q) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    long long r1 = r0 + rows_per_chunk;
+    if (r1 > N) r1 = N;
+    const double *src = (c < L.P) ? (M2 + c) : (Zbar + (c - L.P));
+    const long long ld = (c < L.P) ? ldm : ldz;
+    double s[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) s[u] = 0.0;
+    long long n = r0;
+    for (; n + ROWS <= r1; n += ROWS) {
+#pragma unroll
+        for (int u = 0; u < ROWS; ++u) s[u] += src[(n + u) * ld];
+    }
+    for (; n < r1; ++n) s[0] += src[n * ld];
+    double t = 0.0;
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) t += s[u];
+    double *out = ws + (size_t)blockIdx.y * L.len;
+    if (c < L.P) out[L.S + c] = t;
+    else out[L.zsum + (c - L.P)] = t;
+}
+
+cudaError_t launch_mzsums(long long N, int D, int q, const double *Zbar, long long ldz, const double *M2,
+                          long long ldm, double *ws_main, int nchunks, cudaStream_t st) {
+    long long rpc = (N + nchunks - 1) / nchunks;
+    if (rpc < 1) rpc = 1;
+    const int C = tri(q) + q;
+    dim3 grid((unsigned)((C + 127) / 128), (unsigned)nchunks);
+    mzsums_kernel<8><<<grid, 128, 0, st>>>(N, D, q, Zbar, ldz, M2, ldm, ws_main, rpc);
+    return cudaGetLastError();
+}
+
 // =============================================================== per-row scalars (K4)
 __global__ void __launch_bounds__(256)
 rowscalars_kernel(long long N, int D, const double *__restrict__ X, long long ldx, const double *__restrict__ V,
                   const double *__restrict__ Xorig, const double *__restrict__ qldX,
-                  const double *__restrict__ logdet, double *__restrict__ ws_sc) {
+                  const double *__restrict__ logdet, double *__restrict__ ws_sc, int skip_x) {
     __shared__ double sh[33];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     double sxx = 0, sumv = 0, ne = 0, qz = 0, ldz = 0, latq = 0, nlat = 0, pnm = 0, plnv = 0, nrows = 0;
@@ -338,7 +378,7 @@ rowscalars_kernel(long long N, int D, const double *__restrict__ X, long long ld
         const double *xr = X + n * ldx;
         int nmiss = 0;
         double lnv = 0.0;
-        for (int d = lane; d < D; d += 32) {
+        for (int d = lane; d < D && !skip_x; d += 32) {
             const double x = xr[d];
             if (x == x) {
                 sxx = fma(x, x, sxx);
@@ -397,34 +437,44 @@ int rowscalars_nblk(long long N) {
 
 cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx, const double *V,
                               const double *Xorig, const double *qldX, const double *logdet, double *ws_sc,
-                              int nblk, cudaStream_t st) {
-    rowscalars_kernel<<<nblk, 256, 0, st>>>(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc);
+                              int nblk, int skip_x, cudaStream_t st) {
+    rowscalars_kernel<<<nblk, 256, 0, st>>>(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc, skip_x);
     return cudaGetLastError();
 }
 
 // =============================================================== deterministic second stage
 __global__ void __launch_bounds__(256)
 stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunks, const double *__restrict__ ws_sc,
-                    int nblk, double *__restrict__ stats) {
+                    int nblk, double *__restrict__ stats, double *xcache, int use_xcache) {
     const StatLayout L(D, q);
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < L.len; o += (size_t)gridDim.x * blockDim.x) {
+        // slot of this entry in the X-only cache [cnt D | colx D | sxx | nE], or -1
+        long long xc = -1;
+        if (o >= L.cnt && o < L.S) xc = (long long)(o - L.cnt);
+        else if (o == L.scal + PYVB_SC_SXX) xc = 2LL * D;
+        else if (o == L.scal + PYVB_SC_NE) xc = 2LL * D + 1;
         double acc = 0.0;
-        if (o < L.scal) {
-            for (int c = 0; c < nchunks; ++c) acc += ws_main[(size_t)c * L.len + o];
+        if (xc >= 0 && xcache != nullptr && use_xcache) {
+            acc = xcache[xc];
         } else {
-            const size_t k = o - L.scal;
-            for (int b = 0; b < nblk; ++b) acc += ws_sc[(size_t)b * PYVB_NSCAL + k];
+            if (o < L.scal) {
+                for (int c = 0; c < nchunks; ++c) acc += ws_main[(size_t)c * L.len + o];
+            } else {
+                const size_t k = o - L.scal;
+                for (int b = 0; b < nblk; ++b) acc += ws_sc[(size_t)b * PYVB_NSCAL + k];
+            }
+            if (xc >= 0 && xcache != nullptr) xcache[xc] = acc;
         }
         stats[o] = acc;
     }
 }
 
 cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
-                                double *stats, cudaStream_t st) {
+                                double *stats, double *xcache, int use_xcache, cudaStream_t st) {
     const StatLayout L(D, q);
     size_t b = (L.len + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
-    stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats);
+    stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats, xcache, use_xcache);
     return cudaGetLastError();
 }
 

@@ -119,6 +119,8 @@ class PlateEngine(object):
         assert self.L.len == int(self.lib.pyvb_stats_len(D, q))
         self.ws_bytes = int(self.lib.pyvb_stats_workspace_bytes(N, D, q, self.algo))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
+        self.xcache = torch.zeros(2 * D + 2, dtype=f64, device=dev) if mode == "B" else None
+        self._xcache_valid = False
         self.gl = torch.zeros(GL_LEN, dtype=f64, device=dev)
         self.trace = torch.zeros(int(trace_len), dtype=f64, device=dev)
         self.trace_pos = 0
@@ -230,6 +232,13 @@ class PlateEngine(object):
         self.logdet.fill_(1.0)
         self.set_state({"qb": 0.5, "al_qb": np.ones(q)})
 
+    def set_X(self, X):
+        """Replace the (mode B) data shard, e.g. from pinned host memory; invalidates the cached X sums."""
+        assert self.mode == "B"
+        self.X.copy_(X, non_blocking=True)
+        self._xcache_valid = False
+        self._stats_fresh = False
+
     def get_state(self):
         """Host copy of the state in the oracle's layout."""
         q = self.q
@@ -274,8 +283,10 @@ class PlateEngine(object):
         rc = self.lib.pyvb_stats_f64(self.N, self.D, self.q, self.X.data_ptr(), self.D, self._p(self.V),
                                      self._p(self.Xorig), self._p(self.qldX), self.Zbar.data_ptr(), self.ldmz,
                                      self.M2.data_ptr(), self.ldmz, self.logdet.data_ptr(), self.stats.data_ptr(),
-                                     self.ws.data_ptr(), self.ws_bytes, self.algo, self._stream())
+                                     self.ws.data_ptr(), self.ws_bytes, self._p(self.xcache),
+                                     int(self._xcache_valid), self.algo, self._stream())
         _cabi.check(rc, "pyvb_stats_f64")
+        self._xcache_valid = self.xcache is not None
         if self.distributed:
             import torch.distributed as dist
             dist.all_reduce(self.stats)          # the ONE collective of a sweep (NCCL over NVLink)
