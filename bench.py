@@ -274,6 +274,18 @@ def run_ours(a):
 
     eng._ensure_gw()
     ms_z = time_calls(lambda: eng.update_Z(), 5)
+    ms_k1 = ms_k2 = None
+    if lib.pyvb_algo_supported(2, a.D, a.q):
+        def k1_only():
+            alg, eng.algo = eng.algo, 3          # PYVB_ALGO_DMMA_K1: contraction only
+            eng.update_Z()
+            eng.algo = alg
+        ms_k1 = time_calls(k1_only, 5)
+        def k2_only():                           # in place on rows left as [qprec | eta] by k1_only
+            _cabi.check(lib.pyvb_zsolve_f64(eng.N, eng.q, eng.MZ.data_ptr(), eng.ldmz, 0, eng.logdet.data_ptr(),
+                                            eng.gl.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "zsolve")
+        k1_only(); ms_k2 = time_calls(k2_only, 1)
+        eng.update_Z()                           # restore a consistent state
 
     def stats_call():
         eng._stats_fresh = False
@@ -288,9 +300,14 @@ def run_ours(a):
     peak_tf = 148 * 2 * 8 * iters * 8 * 512.0 / (ms_p * 1e-3) * 1e-12
     D, q = a.D, a.q
     P = q * (q + 1) // 2
-    fl_z = a.N * (2.0 * D * P + 2.0 * D * q + q ** 3 + 2.0 * q * q)      # K1 + K2 (SURVEY 8d terms)
+    fl_k1 = a.N * (2.0 * D * P + 2.0 * D * q)                            # K1 (SURVEY 8d terms)
+    fl_z = fl_k1 + a.N * (q ** 3 + 2.0 * q * q)                          # + K2
     fl_s = a.N * (2.0 * D * P + 4.0 * D * q)                              # K3
-    ach = fl_z / (ms_z * 1e-3) * 1e-12
+    if ms_k1 is not None:
+        kname, fl_dom, ms_dom = "zstep_dmma_kernel (K1: mask @ vec(G) contraction on FP64 tensor cores)", fl_k1, ms_k1
+    else:
+        kname, fl_dom, ms_dom = "zstep (generic K1+K2)", fl_z, ms_z
+    ach = fl_dom / (ms_dom * 1e-3) * 1e-12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
@@ -298,12 +315,13 @@ def run_ours(a):
             traffic = json.load(open(tpath)).get("zstep_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": "zstep_dmma_kernel (K1 contraction + K2 per-row solve)",
+    roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "peak_source": "FP64 DMMA.8x8x4 loop measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                "BASELINE.md section 4 asks for it to be measured on the box)",
-                "flops_per_launch": fl_z, "ms_per_launch": ms_z}
-    kernels = {"zstep_ms": ms_z, "stats_ms": ms_s, "stats_tflops": fl_s / (ms_s * 1e-3) * 1e-12,
+                "flops_per_launch": fl_dom, "ms_per_launch": ms_dom}
+    kernels = {"zstep_ms": ms_z, "zstep_k1_ms": ms_k1, "zsolve_k2_ms": ms_k2, "zstep_tflops": fl_z / (ms_z * 1e-3) * 1e-12,
+               "stats_ms": ms_s, "stats_tflops": fl_s / (ms_s * 1e-3) * 1e-12,
                "sweep_algorithmic_tflops": world * a.N * (4.0 * D * P + 6.0 * D * q + q ** 3 + 2.0 * q * q)
                * a.steps / (ms * 1e-3) * 1e-12 / world}
 
@@ -315,7 +333,7 @@ def run_ours(a):
                            "l2": "inputs larger than L2 (X shard %.2f GB per GPU)" % (a.N * a.D * 8 / 1e9),
                            "parallelism": "rows sharded over %d GPU(s), one all-reduce of %d doubles per sweep"
                                           % (world, eng.L.len)},
-                "clocks": clocks, "gpu_launches": 8 * a.steps,   # wupdate, pack_gw, zstep, stats GEMM, mzsums, rowscalars, reduce, global
+                "clocks": clocks, "gpu_launches": 9 * a.steps,   # wupdate, pack_gw, zstep K1, zsolve K2, stats GEMM, mzsums, rowscalars, reduce, global
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": a.N * a.D * 8, "d2h_bytes_per_step": 8,
                         "steps": e2e_steps},
                 "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}

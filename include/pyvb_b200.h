@@ -92,7 +92,9 @@ extern "C" {
 /* algorithm selector for zstep / stats */
 #define PYVB_ALGO_AUTO 0
 #define PYVB_ALGO_GENERIC 1  /* any D, q <= 64; FP64 FMA */
-#define PYVB_ALGO_DMMA 2     /* FP64 tensor-core (DMMA) + TMA bulk staging; q in {8,16,32}, D % 16 == 0 */
+#define PYVB_ALGO_DMMA 2     /* FP64 tensor-core (DMMA) + TMA staging; q in {8,16,32}, D % 16 == 0 */
+#define PYVB_ALGO_DMMA_K1 3  /* measurement only (zstep): the tensor-core contraction alone; the MZ rows are
+                                left as [qprec packed | eta] for pyvb_zsolve_f64 */
 
 typedef struct pyvb_consts {
     double alpha_mu;      /* prior precision of Mu (Constant alpha*I)                    */
@@ -129,6 +131,11 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
                    const double *P0, const double *h0, double *gl,
                    double *Zbar, long long ldz, double *M2, long long ldm, double *Sig, double *logdet,
                    int algo, void *stream);
+
+/* K2 alone (DMMA-path layout): rows of MZ = [qprec packed | pad | eta] are replaced in place by
+ * [<zz^T> packed | 0 | zbar]; batched q x q Cholesky / inverse / solve, q in {8,16,32}.  Sig may be NULL. */
+int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig, double *logdet, double *gl,
+                    void *stream);
 
 /* K3+K4 over rows [0,N) into `stats` (fully overwritten).  V, Xorig, qldX are mode-A only (NULL in
  * mode B).  ws: pyvb_stats_workspace_bytes().

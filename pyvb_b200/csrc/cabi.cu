@@ -26,6 +26,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int pick_algo(int algo, int D, int q) {
     if (algo == PYVB_ALGO_AUTO) return dmma_supported(D, q) ? PYVB_ALGO_DMMA : PYVB_ALGO_GENERIC;
+    if (algo == PYVB_ALGO_DMMA_K1) return PYVB_ALGO_DMMA;
     return algo;
 }
 
@@ -92,7 +93,8 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
         ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
             "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");
-        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, M2, Sig, logdet, (cudaStream_t)stream);
+        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, M2, Sig, logdet, algo == PYVB_ALGO_DMMA_K1,
+                              (cudaStream_t)stream);
     } else if (a == PYVB_ALGO_GENERIC) {
         e = launch_zstep_generic(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, ldz, M2, ldm, Sig, logdet,
                                  (cudaStream_t)stream);
@@ -100,6 +102,15 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
         return fail(PYVB_EINVAL, "%s", "unknown algo");
     }
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep");
+}
+
+int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig, double *logdet, double *gl,
+                    void *stream) {
+    ARG(N >= 0 && (q == 8 || q == 16 || q == 32), "N, q (8, 16 or 32)");
+    ARG(MZ && logdet && gl, "null pointer");
+    ARG(ldmz == pyvb_mz_pitch(q), "ldmz must equal pyvb_mz_pitch(q)");
+    cudaError_t e = launch_zsolve(N, q, MZ, Sig, logdet, gl, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zsolve");
 }
 
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,

@@ -44,7 +44,8 @@ cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long l
 bool dmma_supported(int D, int q);
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                               int ldg, const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                              double *logdet, cudaStream_t st);
+                              double *logdet, int k1_only, cudaStream_t st);
+cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, cudaStream_t st);
 int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                               double *ws_main, int nchunks, cudaStream_t st);

@@ -1,9 +1,12 @@
 // FP64 tensor-core (DMMA.8x8x4) kernels fed by TMA -- the throughput path.
 //
-//   zstep_dmma_kernel<Q>  K1: [O | O.(X-mu)] (rows x D)  @  Gw (D x (P+q))      -> per-row qprec (packed) and eta
-//                         K2: per-row Cholesky / inverse / solve with the matrix row held in registers
-//                             (lane i owns row i; q lanes per matrix); each row leaves as ONE bulk store of
-//                             [<zz^T> packed | zbar]
+//   zstep_dmma_kernel<Q>  K1: [O | O.(X-mu)] (rows x D)  @  Gw (D x (P+q))  -> per-row [qprec packed | eta],
+//                             written into the MZ row (one bulk store per row)
+//   zsolve_kernel<Q>      K2: per-row Cholesky / inverse / solve IN PLACE on the MZ rows with the matrix row
+//                             held in registers (lane i owns row i; q lanes per matrix):
+//                             [qprec | eta] -> [<zz^T> packed | zbar].  Separate kernel on purpose: K2 is a
+//                             latency-bound DFMA chain; fused behind K1 it kept the CTA's registers and the
+//                             DMMA pipe idle half of the time (profiles/r01_ncu_*.md)
 //   stats_dmma_kernel<Q>  K3: [O | O.X]^T (D x rows) @ [<zz^T> | zbar] (rows x (P+q)) -> T1, Bst, Ast
 //
 // Reference arithmetic: nodes/node.py:203-227 (K1), nodes/gaussian.py:117-123 (K2), nodes/nodes_todo.py:50-61 (K3).
@@ -103,14 +106,11 @@ template <int Q> struct ZT {
     static constexpr int MUCOL = PP + Q;
     static constexpr int XT_B = R * KC * 8;     // swizzled X tile (bytes), multiple of 1024
     static constexpr int GS_B = KC * LDG * 8;
-    static constexpr int SPL = Q * (Q + 2) / 2;
-    static constexpr int SROW = c_srow(SPL + Q);
+    static constexpr int SPL = Q * (Q + 2) / 2; // even-padded packed lower triangle (K2 work rows)
+    static constexpr int OROW = PP + Q;         // doubles per output row [packed | pad | eta]
+    static constexpr int SROW = c_srow(OROW);   // staging pitch
     static constexpr int MAIN_B = (c_max(ST * (XT_B + GS_B), R * SROW * 8) + 15) & ~15;
-    static constexpr int G = 32 / Q;            // matrices side by side in a warp
-    static constexpr int RPP = G * MI;          // rows per warp pass
-    static constexpr int XR_D = NCW * 2 * MI * 32;
-    static constexpr size_t SMEM = 1024 + (size_t)MAIN_B + (size_t)(P + Q + XR_D) * 8 + 2 * ST * 8 + ((P * 2 + 15) & ~15);
-    static_assert(R % (NCW * RPP) == 0, "rows must split evenly over the K2 passes");
+    static constexpr size_t SMEM = 1024 + (size_t)MAIN_B + (size_t)(P + Q) * 8 + 2 * ST * 8;
     static_assert(XT_B % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
 };
 
@@ -218,12 +218,12 @@ __device__ __forceinline__ void k2_solve(double *const (&A)[MI], double *xbuf, c
     }
 }
 
-// ------------------------------------------------------------------ Z step kernel
+// ------------------------------------------------------------------ Z step, part 1 (K1): tensor-core contraction
 template <int Q>
 __global__ void __launch_bounds__(ZT<Q>::NTHR, ZC<Q>::OCC)
 zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, const double *__restrict__ Gw,
-                  const double *__restrict__ P0, const double *__restrict__ h0, double *gl,
-                  double *__restrict__ MZ, double *__restrict__ Sig, double *__restrict__ logdet) {
+                  const double *__restrict__ P0, const double *__restrict__ h0, const double *__restrict__ gl,
+                  double *__restrict__ MZ) {
     using T = ZT<Q>;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
@@ -234,10 +234,8 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     double *stg = reinterpret_cast<double *>(smem);             // epilogue staging aliases the pipeline buffers
     double *p0v = reinterpret_cast<double *>(smem + T::MAIN_B);
     double *h0s = p0v + T::P;
-    double *xr = h0s + Q;
-    uint64_t *full = reinterpret_cast<uint64_t *>(xr + T::XR_D);
+    uint64_t *full = reinterpret_cast<uint64_t *>(h0s + Q);
     uint64_t *empty = full + T::ST;
-    uint16_t *soff = reinterpret_cast<uint16_t *>(empty + T::ST);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long row0 = (long long)blockIdx.x * T::R;
@@ -246,7 +244,6 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     for (int p = tid; p < T::P; p += T::NTHR) {
         int i, j;
         unpack_p(p, i, j);
-        soff[p] = (uint16_t)(c_off(i) + j);
         p0v[p] = P0[i * Q + j];
     }
     if (tid < Q) h0s[tid] = h0[tid];
@@ -330,8 +327,8 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         }
     }
 
-    // ===================== epilogue: accumulators -> staging (aliases the pipeline buffers) =====================
-    named_bar_sync(1, T::NCW * 32);
+    // ===================== epilogue: qprec = P0 + tau*acc, eta = h0 + tau*acc -> staging -> MZ rows ==========
+    __syncthreads();                                       // all warps are done with the pipeline buffers
     const double tau = gl[PYVB_GL_TAU];
 #pragma unroll
     for (int rg = 0; rg < T::RGW; ++rg) {
@@ -340,45 +337,118 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         for (int j = 0; j < T::NGW; ++j) {
             if (T::WN > 1 && j >= ncg) continue;
             const int cg = cg0 + j;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int c = cg * 8 + 2 * qd + e;
-                if (cg < T::NGO) {
-                    if (c < T::P) srow[soff[c]] = fma(tau, acc[rg][j][e], p0v[c]);
-                } else {
-                    const int i = c - T::PP;
-                    srow[T::SPL + i] = fma(tau, acc[rg][j][e], h0s[i]);
-                }
+            const int c = cg * 8 + 2 * qd;
+            double2 v;
+            if (cg < T::NGO) {   // packed qprec columns; the pad columns [P, PP) come out as exact zeros (Gw pad = 0)
+                v.x = (c < T::P) ? fma(tau, acc[rg][j][0], p0v[c]) : 0.0;
+                v.y = (c + 1 < T::P) ? fma(tau, acc[rg][j][1], p0v[c + 1]) : 0.0;
+            } else {
+                v.x = fma(tau, acc[rg][j][0], h0s[c - T::PP]);
+                v.y = fma(tau, acc[rg][j][1], h0s[c + 1 - T::PP]);
             }
+            *reinterpret_cast<double2 *>(srow + c) = v;
         }
     }
-    named_bar_sync(1, T::NCW * 32);
+    fence_async_smem();
+    __syncthreads();
+    for (int r = tid; r < T::R; r += T::NTHR)
+        if (row0 + r < N) bulk_s2g(MZ + (row0 + r) * T::LDG, stg + (size_t)r * T::SROW, T::OROW * 8);
+    bulk_commit();
+    bulk_wait_read_all();
+}
 
-    // ===================== K2 =====================
+// ------------------------------------------------------------------ Z step, part 2 (K2): batched q x q solve
+template <int Q> struct KC2;
+template <> struct KC2<8>  { static constexpr int MI = 2, WARPS = 4, OCC = 3; };
+template <> struct KC2<16> { static constexpr int MI = 2, WARPS = 4, OCC = 3; };
+template <> struct KC2<32> { static constexpr int MI = 1, WARPS = 4, OCC = 3; };
+
+template <int Q> struct K2T {
+    static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, OROW = PP + Q, LDG = c_gw_pitch(Q);
+    static constexpr int MI = KC2<Q>::MI, WARPS = KC2<Q>::WARPS;
+    static constexpr int G = 32 / Q, RPP = G * MI;           // rows per warp pass
+    static constexpr int SPL = Q * (Q + 2) / 2;
+    static constexpr int WROW = c_srow(SPL + Q);             // work row: even-padded packed matrix + eta
+    // per warp: 2 x RPP raw rows (double buffered in/out), RPP work rows, broadcast scratch, 2 mbarriers
+    static constexpr int WARP_D = 2 * RPP * OROW + RPP * WROW + 2 * MI * 32 + 2;
+    static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8 + 16;
+};
+
+// rows [0, N) of MZ hold [qprec packed | pad | eta]; they are replaced by [<zz^T> packed | 0 | zbar].
+// Each warp walks its own contiguous block of rows, RPP rows per pass; loads are bulk copies one pass ahead.
+template <int Q>
+__global__ void __launch_bounds__(32 * KC2<Q>::WARPS, KC2<Q>::OCC)
+zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, double *__restrict__ logdet,
+              double *gl, long long rows_per_warp) {
+    using T = K2T<Q>;
+    extern __shared__ __align__(16) double smem_k2[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *base = smem_k2 + (size_t)warp * T::WARP_D;
+    double *raw = base;                                      // [2][RPP][OROW]
+    double *work = raw + 2 * T::RPP * T::OROW;               // [RPP][WROW]
+    double *xbuf = work + T::RPP * T::WROW;                  // [2][MI*32]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(xbuf + 2 * T::MI * 32);   // [2]
     const int li = lane % Q, lg = lane / Q;
     const int offli = c_off(li);
-    double *xbuf = xr + warp * (2 * T::MI * 32);
-    for (int rb = warp * T::RPP; rb < T::R; rb += T::NCW * T::RPP) {
+    const long long wr0 = ((long long)blockIdx.x * T::WARPS + warp) * rows_per_warp;
+    long long wr1 = wr0 + rows_per_warp;
+    if (wr1 > N) wr1 = N;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (wr0 >= wr1) return;
+    const int npass = (int)((wr1 - wr0 + T::RPP - 1) / T::RPP);
+
+    auto load = [&](int pass) {      // lane 0: bulk loads of the pass' rows into raw[pass & 1]
+        const int b = pass & 1;
+        const long long r0 = wr0 + (long long)pass * T::RPP;
+        const int nv = (wr1 - r0 < T::RPP) ? (int)(wr1 - r0) : T::RPP;
+        mbar_arrive_expect_tx(&bar[b], (uint32_t)(nv * T::OROW * 8));
+        for (int r = 0; r < nv; ++r)
+            bulk_g2s(raw + (size_t)(b * T::RPP + r) * T::OROW, MZ + (r0 + r) * T::LDG, T::OROW * 8, &bar[b]);
+    };
+    if (lane == 0) load(0);
+    uint32_t ph[2] = {0, 0};
+    for (int pass = 0; pass < npass; ++pass) {
+        const int b = pass & 1;
+        if (lane == 0 && pass + 1 < npass) {
+            bulk_wait_read_all();    // the stores that read raw[b ^ 1] two passes ago have drained
+            load(pass + 1);
+        }
+        mbar_wait(&bar[b], ph[b]);
+        ph[b] ^= 1;
+        const long long r0 = wr0 + (long long)pass * T::RPP;
         double *A[T::MI];
+        double *O[T::MI];
         long long nrow[T::MI];
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) {
-            const int r = rb + lg * T::MI + m;
-            A[m] = stg + (size_t)r * T::SROW;
-            nrow[m] = row0 + r;
+            const int r = lg * T::MI + m;
+            A[m] = work + (size_t)r * T::WROW;
+            O[m] = raw + (size_t)(b * T::RPP + r) * T::OROW;
+            nrow[m] = r0 + r;
+            // re-layout: standard packed row li -> even-padded work row; eta behind it
+            const bool valid = nrow[m] < wr1;
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+                if (j <= li) A[m][offli + j] = valid ? O[m][c_tri(li) + j] : ((j == li) ? 1.0 : 0.0);
+            A[m][T::SPL + li] = valid ? O[m][T::PP + li] : 0.0;
         }
+        __syncwarp();
         double Sg[T::MI][Q], z[T::MI], ldet[T::MI];
         bool ok = true;
         k2_solve<Q, T::MI>(A, xbuf, li, offli, Sg, z, ldet, ok);
-        // publish z (buffer 0); the staging row becomes the output row [<zz^T> packed | 0 | zbar]
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) xbuf[m * 32 + lane] = z[m];
         __syncwarp();
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) {
-            const bool valid = nrow[m] < N;
+            const bool valid = nrow[m] < wr1;
             const double *zrow = xbuf + m * 32 + (lane - li);
-            double *orow = A[m] + c_tri(li);
+            double *orow = O[m] + c_tri(li);
             double *sgl = (Sig != nullptr && valid) ? (Sig + nrow[m] * T::P + c_tri(li)) : nullptr;
 #pragma unroll
             for (int j = 0; j < Q; ++j) {
@@ -387,8 +457,7 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
                     if (sgl) sgl[j] = Sg[m][j];
                 }
             }
-            if (li < T::PP - T::P) A[m][T::P + li] = 0.0;
-            A[m][T::PP + li] = z[m];
+            O[m][T::PP + li] = z[m];
             if (li == 0 && valid) {
                 logdet[nrow[m]] = ldet[m];
                 if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
@@ -396,14 +465,14 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         }
         fence_async_smem();
         __syncwarp();
-        if (li == 0) {
-#pragma unroll
-            for (int m = 0; m < T::MI; ++m)
-                if (nrow[m] < N) bulk_s2g(MZ + nrow[m] * T::LDG, A[m], (T::PP + Q) * 8);
+        if (lane == 0) {
+            const int nv = (wr1 - r0 < T::RPP) ? (int)(wr1 - r0) : T::RPP;
+            for (int r = 0; r < nv; ++r)
+                bulk_s2g(MZ + (r0 + r) * T::LDG, raw + (size_t)(b * T::RPP + r) * T::OROW, T::OROW * 8);
             bulk_commit();
         }
     }
-    if (li == 0) bulk_wait_read_all();
+    if (lane == 0) bulk_wait_read_all();
 }
 
 // pure-DMMA loop: the FP64 tensor roofline of the box (see pyvb_bench_dmma_f64)
@@ -429,9 +498,26 @@ cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream
 bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32) && D >= 16 && (D % 16) == 0; }
 
 template <int Q>
+static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double *logdet, double *gl,
+                                   cudaStream_t st) {
+    using T = K2T<Q>;
+    cudaError_t e = cudaFuncSetAttribute(zsolve_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    if (e != cudaSuccess) return e;
+    // ~8 waves of warps over 148 SMs x OCC x WARPS, rows per warp a multiple of the pass size
+    const long long warps_target = 148LL * KC2<Q>::OCC * T::WARPS * 8;
+    long long rpw = (N + warps_target - 1) / warps_target;
+    rpw = ((rpw + T::RPP - 1) / T::RPP) * T::RPP;
+    if (rpw < 4 * T::RPP) rpw = 4 * T::RPP;
+    const long long nwarps = (N + rpw - 1) / rpw;
+    const long long blocks = (nwarps + T::WARPS - 1) / T::WARPS;
+    zsolve_kernel<Q><<<(unsigned)blocks, 32 * T::WARPS, T::SMEM, st>>>(N, MZ, Sig, logdet, gl, rpw);
+    return cudaGetLastError();
+}
+
+template <int Q>
 static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long ldx, const double *Gw,
                                   const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                                  double *logdet, cudaStream_t st) {
+                                  double *logdet, int k1_only, cudaStream_t st) {
     using T = ZT<Q>;
     CUtensorMap tmX;
     cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, T::KC, T::R,
@@ -440,19 +526,31 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     const long long blocks = (N + T::R - 1) / T::R;
-    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, Sig, logdet);
-    return cudaGetLastError();
+    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || k1_only) return e;
+    return launch_zsolve_q<Q>(N, MZ, Sig, logdet, gl, st);
 }
 
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
                               const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                              double *logdet, cudaStream_t st) {
+                              double *logdet, int k1_only, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     if (ldg != c_gw_pitch(q)) return cudaErrorInvalidValue;
     switch (q) {
-        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, st);
-        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, st);
-        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, st);
+        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, k1_only, st);
+        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, k1_only, st);
+        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, k1_only, st);
+    }
+    return cudaErrorNotSupported;
+}
+
+cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    switch (q) {
+        case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, st);
+        case 16: return launch_zsolve_q<16>(N, MZ, Sig, logdet, gl, st);
+        case 32: return launch_zsolve_q<32>(N, MZ, Sig, logdet, gl, st);
     }
     return cudaErrorNotSupported;
 }
