@@ -106,7 +106,6 @@ template <int Q> struct ZT {
     static constexpr int MUCOL = PP + Q;
     static constexpr int XT_B = R * KC * 8;     // swizzled X tile (bytes), multiple of 1024
     static constexpr int GS_B = KC * LDG * 8;
-    static constexpr int SPL = Q * (Q + 2) / 2; // even-padded packed lower triangle (K2 work rows)
     static constexpr int OROW = PP + Q;         // doubles per output row [packed | pad | eta]
     static constexpr int SROW = c_srow(OROW);   // staging pitch
     static constexpr int MAIN_B = (c_max(ST * (XT_B + GS_B), R * SROW * 8) + 15) & ~15;
@@ -115,102 +114,130 @@ template <int Q> struct ZT {
 };
 
 // ------------------------------------------------------------------ K2: per-row Cholesky inverse in registers
-// Lane li of a Q-lane group owns row li.  The matrix (lower triangle, even-padded packed rows) lives in
-// the staging row `A`; the factor overwrites it in place (diagonal holds 1/L_kk) so that "row k of L" is a
-// contiguous broadcast read.  Pass 1: left-looking Cholesky.  Pass 2: X = L^-1 by forward substitution
-// (lane j owns column j) fused with Sigma = X^T X accumulated row by row.  Everything is statically
-// unrolled so the rows stay in registers.
+// Lane li of a Q-lane group owns row li of the matrix (registers, statically indexed: everything below is
+// fully unrolled).  Both passes are RIGHT-LOOKING so that the only serial dependence per step is
+// pivot -> rsqrt -> broadcast; all multiply-adds of a step are independent of each other:
+//   pass 1 (Cholesky):  l_ik = a_ik / sqrt(a_kk);  a_ij -= l_ik l_jk  for all j > k      (column k broadcast via smem)
+//   pass 2 (X = L^-1, lane j owns column j, fused with Sigma = X^T X):
+//                       x_k = (delta_jk - t_k) / l_kk;  t_i += l_ik x_k for all i > k;  Sigma_j. += x_k * (row k of X)
+// The factor is kept column-major in shared memory (packed: column k holds rows k..Q-1, its diagonal slot
+// holds 1/l_kk), which is exactly the order in which both passes broadcast it.
+__host__ __device__ constexpr int c_lcol(int k, int Q) { return k * Q - k * (k - 1) / 2 - k; }   // + i addresses (i,k), i >= k
+
 template <int Q, int MI>
-__device__ __forceinline__ void k2_solve(double *const (&A)[MI], double *xbuf, const int li, const int offli,
+__device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const double *const (&eta)[MI],
+                                         double *const (&Lc)[MI], double *xbuf, const int li,
                                          double (&Sg)[MI][Q], double (&z)[MI], double (&ldet)[MI], bool &ok) {
-    using T = ZT<Q>;
-    double Lr[MI][Q];
+    const int lane = threadIdx.x & 31;
+    double Ar[MI][Q];
     double mant[MI];
     int esum[MI];
 #pragma unroll
     for (int m = 0; m < MI; ++m) {
         mant[m] = 1.0;
         esum[m] = 0;
+#pragma unroll
+        for (int j = 0; j < Q; ++j) Ar[m][j] = (j <= li) ? Arow[m][j] : 0.0;   // row li of the lower triangle
     }
-    // ---- pass 1
+    // ---- pass 1: right-looking Cholesky
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
-            const double *Lk = A[m] + c_off(k);
-            double v0 = (li >= k) ? A[m][offli + k] : 0.0;
-            double v1 = 0.0;
-#pragma unroll
-            for (int mm = 0; mm + 1 < k; mm += 2) {
-                const double2 l2 = *reinterpret_cast<const double2 *>(Lk + mm);
-                v0 = fma(-Lr[m][mm], l2.x, v0);
-                v1 = fma(-Lr[m][mm + 1], l2.y, v1);
-            }
-            if (k & 1) v0 = fma(-Lr[m][k - 1], Lk[k - 1], v0);
-            const double v = v0 + v1;
-            const double d = __shfl_sync(0xffffffffu, v, k, Q);
+            const double d = __shfl_sync(0xffffffffu, Ar[m][k], k, Q);
             ok = ok && (d > 0.0);
             const long long bits = __double_as_longlong(d);
             esum[m] += (int)((bits >> 52) & 0x7ff) - 1023;
             mant[m] *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
             const double rinv = rsqrt(d);
-            const double l = v * rinv;
-            Lr[m][k] = l;
-            if (li > k) A[m][offli + k] = l;
-            else if (li == k) A[m][offli + k] = rinv;
+            const double l = Ar[m][k] * rinv;
+            Ar[m][k] = l;
+            if (li >= k) Lc[m][c_lcol(k, Q) + li] = (li == k) ? rinv : l;
         }
         __syncwarp();
+        if (k + 1 < Q) {
+#pragma unroll
+            for (int m = 0; m < MI; ++m) {
+                const double *col = Lc[m] + c_lcol(k, Q);
+                const double nl = -Ar[m][k];
+                constexpr int dummy = 0;
+                (void)dummy;
+                int j = k + 1;
+                if ((c_lcol(k, Q) + j) & 1) {   // compile-time parity: first element unaligned for a 16-byte load
+                    Ar[m][j] = fma(nl, col[j], Ar[m][j]);
+                    ++j;
+                }
+#pragma unroll
+                for (int jj = 0; jj < Q; jj += 2) {
+                    const int j2 = j + jj;
+                    if (j2 + 1 < Q) {
+                        const double2 l2 = *reinterpret_cast<const double2 *>(col + j2);
+                        Ar[m][j2] = fma(nl, l2.x, Ar[m][j2]);
+                        Ar[m][j2 + 1] = fma(nl, l2.y, Ar[m][j2 + 1]);
+                    } else if (j2 < Q) {
+                        Ar[m][j2] = fma(nl, col[j2], Ar[m][j2]);
+                    }
+                }
+            }
+        }
     }
 #pragma unroll
     for (int m = 0; m < MI; ++m) ldet[m] = 0.5 * (log(mant[m]) + (double)esum[m] * 0.69314718055994530942);
-    // ---- pass 2
+    // ---- pass 2: X = L^-1 (column li per lane) and Sigma = X^T X
+    double t[MI][Q];
 #pragma unroll
     for (int m = 0; m < MI; ++m)
 #pragma unroll
-        for (int j = 0; j < Q; ++j) Sg[m][j] = 0.0;
-    {
-        double xv[MI][Q];
+        for (int j = 0; j < Q; ++j) {
+            Sg[m][j] = 0.0;
+            t[m][j] = 0.0;
+        }
 #pragma unroll
-        for (int i = 0; i < Q; ++i) {
-            double xi[MI];
-            double *xb = xbuf + (i & 1) * (MI * 32);
+    for (int k = 0; k < Q; ++k) {
+        double xk[MI];
+        double *xb = xbuf + (k & 1) * (MI * 32);
 #pragma unroll
-            for (int m = 0; m < MI; ++m) {
-                const double *Li = A[m] + c_off(i);
-                double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-                for (int mm = 0; mm + 1 < i; mm += 2) {
-                    const double2 l2 = *reinterpret_cast<const double2 *>(Li + mm);
-                    t0 = fma(l2.x, xv[m][mm], t0);
-                    t1 = fma(l2.y, xv[m][mm + 1], t1);
-                }
-                if (i & 1) t0 = fma(Li[i - 1], xv[m][i - 1], t0);
-                xi[m] = (((li == i) ? 1.0 : 0.0) - (t0 + t1)) * Li[i];
-                xv[m][i] = xi[m];
-                xb[m * 32 + (threadIdx.x & 31)] = xi[m];
+        for (int m = 0; m < MI; ++m) {
+            const double *col = Lc[m] + c_lcol(k, Q);
+            xk[m] = (((li == k) ? 1.0 : 0.0) - t[m][k]) * col[k];
+            xb[m * 32 + lane] = xk[m];
+            int i = k + 1;
+            if (i < Q && ((c_lcol(k, Q) + i) & 1)) {
+                t[m][i] = fma(col[i], xk[m], t[m][i]);
+                ++i;
             }
-            __syncwarp();
 #pragma unroll
-            for (int m = 0; m < MI; ++m) {
-                const double *xrow = xb + m * 32 + ((threadIdx.x & 31) - li);
-#pragma unroll
-                for (int j = 0; j + 1 <= i; j += 2) {
-                    const double2 x2 = *reinterpret_cast<const double2 *>(xrow + j);
-                    Sg[m][j] = fma(xi[m], x2.x, Sg[m][j]);
-                    Sg[m][j + 1] = fma(xi[m], x2.y, Sg[m][j + 1]);
+            for (int ii = 0; ii < Q; ii += 2) {
+                const int i2 = i + ii;
+                if (i2 + 1 < Q) {
+                    const double2 l2 = *reinterpret_cast<const double2 *>(col + i2);
+                    t[m][i2] = fma(l2.x, xk[m], t[m][i2]);
+                    t[m][i2 + 1] = fma(l2.y, xk[m], t[m][i2 + 1]);
+                } else if (i2 < Q) {
+                    t[m][i2] = fma(col[i2], xk[m], t[m][i2]);
                 }
-                if (!(i & 1)) Sg[m][i] = fma(xi[m], xrow[i], Sg[m][i]);
             }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MI; ++m) {
+            const double *xrow = xb + m * 32 + (lane - li);       // row k of X: entries j <= k are non-zero
+#pragma unroll
+            for (int j = 0; j + 1 <= k; j += 2) {
+                const double2 x2 = *reinterpret_cast<const double2 *>(xrow + j);
+                Sg[m][j] = fma(xk[m], x2.x, Sg[m][j]);
+                Sg[m][j + 1] = fma(xk[m], x2.y, Sg[m][j + 1]);
+            }
+            if (!(k & 1)) Sg[m][k] = fma(xk[m], xrow[k], Sg[m][k]);
         }
     }
     // ---- posterior mean: z = Sigma . eta
 #pragma unroll
     for (int m = 0; m < MI; ++m) {
-        const double *eta = A[m] + T::SPL;
         double z0 = 0.0, z1 = 0.0;
 #pragma unroll
         for (int j = 0; j < Q; j += 2) {
-            const double2 e2 = *reinterpret_cast<const double2 *>(eta + j);
+            const double2 e2 = *reinterpret_cast<const double2 *>(eta[m] + j);
             z0 = fma(Sg[m][j], e2.x, z0);
             z1 = fma(Sg[m][j + 1], e2.y, z1);
         }
@@ -367,11 +394,11 @@ template <int Q> struct K2T {
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, OROW = PP + Q, LDG = c_gw_pitch(Q);
     static constexpr int MI = KC2<Q>::MI, WARPS = KC2<Q>::WARPS;
     static constexpr int G = 32 / Q, RPP = G * MI;           // rows per warp pass
-    static constexpr int SPL = Q * (Q + 2) / 2;
-    static constexpr int WROW = c_srow(SPL + Q);             // work row: even-padded packed matrix + eta
-    // per warp: 2 x RPP raw rows (double buffered in/out), RPP work rows, broadcast scratch, 2 mbarriers
-    static constexpr int WARP_D = 2 * RPP * OROW + RPP * WROW + 2 * MI * 32 + 2;
+    // per warp: 2 x RPP rows (double buffered, solved in place), RPP packed column-major factors,
+    // broadcast scratch, 2 mbarriers
+    static constexpr int WARP_D = 2 * RPP * OROW + RPP * P + 2 * MI * 32 + 2;
     static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8 + 16;
+    static_assert(WARP_D % 2 == 0 && OROW % 2 == 0 && P % 2 == 0, "16-byte alignment of the per-warp buffers");
 };
 
 // rows [0, N) of MZ hold [qprec packed | pad | eta]; they are replaced by [<zz^T> packed | 0 | zbar].
@@ -385,11 +412,10 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *base = smem_k2 + (size_t)warp * T::WARP_D;
     double *raw = base;                                      // [2][RPP][OROW]
-    double *work = raw + 2 * T::RPP * T::OROW;               // [RPP][WROW]
-    double *xbuf = work + T::RPP * T::WROW;                  // [2][MI*32]
+    double *lcs = raw + 2 * T::RPP * T::OROW;                // [RPP][P]
+    double *xbuf = lcs + T::RPP * T::P;                      // [2][MI*32]
     uint64_t *bar = reinterpret_cast<uint64_t *>(xbuf + 2 * T::MI * 32);   // [2]
     const int li = lane % Q, lg = lane / Q;
-    const int offli = c_off(li);
     const long long wr0 = ((long long)blockIdx.x * T::WARPS + warp) * rows_per_warp;
     long long wr1 = wr0 + rows_per_warp;
     if (wr1 > N) wr1 = N;
@@ -415,35 +441,39 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
     for (int pass = 0; pass < npass; ++pass) {
         const int b = pass & 1;
         if (lane == 0 && pass + 1 < npass) {
-            bulk_wait_read_all();    // the stores that read raw[b ^ 1] two passes ago have drained
+            bulk_wait_read_all();    // the stores that read raw[b ^ 1] one pass ago have drained
             load(pass + 1);
         }
         mbar_wait(&bar[b], ph[b]);
         ph[b] ^= 1;
         const long long r0 = wr0 + (long long)pass * T::RPP;
-        double *A[T::MI];
         double *O[T::MI];
+        const double *Arow[T::MI];
+        const double *eta[T::MI];
+        double *Lc[T::MI];
         long long nrow[T::MI];
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) {
             const int r = lg * T::MI + m;
-            A[m] = work + (size_t)r * T::WROW;
             O[m] = raw + (size_t)(b * T::RPP + r) * T::OROW;
             nrow[m] = r0 + r;
-            // re-layout: standard packed row li -> even-padded work row; eta behind it
-            const bool valid = nrow[m] < wr1;
+            if (nrow[m] >= wr1) {     // tail of the block: solve the identity instead of stale shared memory
 #pragma unroll
-            for (int j = 0; j < Q; ++j)
-                if (j <= li) A[m][offli + j] = valid ? O[m][c_tri(li) + j] : ((j == li) ? 1.0 : 0.0);
-            A[m][T::SPL + li] = valid ? O[m][T::PP + li] : 0.0;
+                for (int j = 0; j < Q; ++j)
+                    if (j <= li) O[m][c_tri(li) + j] = (j == li) ? 1.0 : 0.0;
+                O[m][T::PP + li] = 0.0;
+            }
+            Arow[m] = O[m] + c_tri(li);
+            eta[m] = O[m] + T::PP;
+            Lc[m] = lcs + (size_t)r * T::P;
         }
         __syncwarp();
         double Sg[T::MI][Q], z[T::MI], ldet[T::MI];
         bool ok = true;
-        k2_solve<Q, T::MI>(A, xbuf, li, offli, Sg, z, ldet, ok);
+        k2_solve<Q, T::MI>(Arow, eta, Lc, xbuf, li, Sg, z, ldet, ok);
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) xbuf[m * 32 + lane] = z[m];
-        __syncwarp();
+        __syncwarp();                // also: every lane has read eta before the row is overwritten
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) {
             const bool valid = nrow[m] < wr1;
