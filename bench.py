@@ -33,44 +33,53 @@ def workload_name(a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Polls NVML (clocks, power, throttle reasons) every ~4 ms from a thread while the timed region runs."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "hw_power_brake": 0x80, "sync_boost": 0x10}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.ok, self._stop = [], False, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2] or [r for (_, r) in self.rows]
-        sm, smax, reasons, pw = [], None, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
+    def _run(self):
+        nv = self.nv
+        while not self._stop:
             try:
-                sm.append(float(r[0])); smax = float(r[1]); pw.append(float(r[2]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.time(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, rs))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+            time.sleep(0.004)
+
+    def stop(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop = True
+        self.t.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= int(r[3])
+        reasons = sorted(n for n, bit in self.REASONS.items() if mask & bit)
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max), "reasons": reasons,
+                "power_w_max": max(r[2] for r in rows) if rows else None, "samples": len(rows)}
 
 
 # ----------------------------------------------------------------------------- CPU baselines
@@ -197,6 +206,10 @@ def make_data(torch, N, D, q, missing, seed, dev):
 
 
 def run_ours(a):
+    # exactly ONE line on stdout: libraries (NCCL banner ...) get stderr, the JSON line gets the real stdout
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from pyvb_b200 import PlateEngine, _cabi
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -339,7 +352,8 @@ def run_ours(a):
                 "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(a)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_out, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

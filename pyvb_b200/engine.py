@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+from .dist import allreduce_stats
 from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_LEN, GL_NONPD, GL_QA,
                       GL_QB, GL_TAU, OP_ALPHA, OP_BETA, OP_ELBO, OP_MU, QMAX, StatLayout)
 
@@ -263,6 +264,13 @@ class PlateEngine(object):
         out["al_qb"] = gl[GL_ALQB:GL_ALQB + q].copy()
         return out
 
+    def get_state_small(self):
+        """Host copy of the replicated (row-independent) state only."""
+        gl = self.gl.cpu().numpy()
+        return {"Wbar": self.Wbar.cpu().numpy(), "Wvar": self.Wvar.cpu().numpy(), "mu": self.mu.cpu().numpy(),
+                "muvar": self.muvar.cpu().numpy(), "qa": float(gl[GL_QA]), "qb": float(gl[GL_QB]),
+                "tau": float(gl[GL_TAU]), "alpha": gl[GL_ALPHA:GL_ALPHA + self.q].copy()}
+
     def check(self):
         """Raise LinAlgError if any posterior precision was not positive definite (gaussian.py:118)."""
         if float(self.gl[GL_NONPD].item()) > 0:
@@ -288,8 +296,7 @@ class PlateEngine(object):
         _cabi.check(rc, "pyvb_stats_f64")
         self._xcache_valid = self.xcache is not None
         if self.distributed:
-            import torch.distributed as dist
-            dist.all_reduce(self.stats)          # the ONE collective of a sweep (NCCL over NVLink)
+            allreduce_stats(self.stats)          # the ONE collective of a sweep (NCCL over NVLink)
         self._stats_fresh = True
 
     def update_W(self, col_lo=0, col_hi=None):

@@ -1,0 +1,106 @@
+"""GPU: BASELINE.json's full single-GPU size (config 2: N=1M, D=256, q=16, 20 % missing) through
+size-independent properties, plus oracle parity on a random sample of its rows."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import numpy_stats, tensor_rel
+from oracle.plate_oracle import PlateOracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import bench
+    from pyvb_b200 import PlateEngine
+    N, D, q = 1000000, 256, 16
+    dev = torch.device("cuda", 0)
+    X = bench.make_data(torch, N, D, q, 0.2, 1234, dev)
+    e = PlateEngine(X, q, mode="B", algo="dmma", keep_sigma=False, device=dev)
+    e.init_random(seed=4321)
+    return e
+
+
+def test_fullsize_sweeps_and_determinism(big):
+    e = big
+    tr = [e.iterate() for _ in range(4)]
+    assert np.all(np.isfinite(tr))
+    e.check()
+    # the Z step is a pure function of (X, Gw, tau): running it twice gives bit-identical rows
+    e.update_Z()
+    a = e.MZ.clone()
+    e.update_Z()
+    assert torch.equal(a, e.MZ)
+    # statistics are deterministic too (fixed-order two-stage reduction)
+    e._stats_fresh = False; e._ensure_stats(); s1 = e.stats.clone()
+    e._stats_fresh = False; e._ensure_stats()
+    assert torch.equal(s1, e.stats)
+
+
+def test_fullsize_stats_additive_and_checksums(big):
+    e = big
+    e.update_Z()
+    e._stats_fresh = False
+    e._ensure_stats()
+    full = e.stats.clone()
+    L = e.L
+    v = L.views(full.cpu().numpy())
+    # checksum of checksums: column sums of the masked statistics against plain torch reductions
+    obs = ~torch.isnan(e.X)
+    assert abs(v["cnt"].sum() - float(obs.sum())) < 0.5
+    assert tensor_rel(v["zsum"], e.Zbar.sum(0).cpu().numpy()) < 1e-10
+    assert tensor_rel(v["S"], e.M2.sum(0).cpu().numpy()) < 1e-10
+    x0 = torch.where(obs, e.X, torch.zeros((), dtype=e.X.dtype, device=e.X.device))
+    assert tensor_rel(v["colx"], x0.sum(0).cpu().numpy()) < 1e-10
+    # T1 summed over d == sum_n |O_n| <zz^T>_n
+    w = obs.sum(1).to(torch.float64)
+    assert tensor_rel(v["T1"].sum(0), (w[:, None] * e.M2).sum(0).cpu().numpy()) < 1e-10
+    assert tensor_rel(v["Ast"].sum(0), (x0.sum(1)[:, None] * e.Zbar).sum(0).cpu().numpy()) < 1e-9
+    # additivity over two row shards (what the all-reduce relies on), through the C-ABI on sub-ranges
+    from pyvb_b200 import _cabi
+    lib = e.lib
+    acc = torch.zeros_like(full)
+    cache = torch.zeros_like(e.xcache)
+    for lo, hi in [(0, 400003), (400003, e.N)]:
+        part = torch.zeros_like(full)
+        rc = lib.pyvb_stats_f64(hi - lo, e.D, e.q, e.X.data_ptr() + lo * e.D * 8, e.D, 0, 0, 0,
+                                e.Zbar.data_ptr() + lo * e.ldmz * 8, e.ldmz, e.M2.data_ptr() + lo * e.ldmz * 8, e.ldmz,
+                                e.logdet.data_ptr() + lo * 8, part.data_ptr(), e.ws.data_ptr(), e.ws_bytes,
+                                cache.data_ptr(), 0, e.algo, e._stream())
+        _cabi.check(rc, "stats")
+        acc += part
+    fin = torch.isfinite(full)
+    assert tensor_rel(acc[fin].cpu().numpy(), full[fin].cpu().numpy()) < 1e-11
+
+
+def test_fullsize_rows_match_oracle_on_a_sample(big):
+    e = big
+    e.update_Z()
+    rng = np.random.RandomState(0)
+    idx = np.sort(rng.choice(e.N, 1500, replace=False))
+    it = torch.as_tensor(idx, device=e.X.device)
+    Xs = e.X[it].cpu().numpy()
+    o = PlateOracle(Xs, e.q, mode="B")
+    st = e.get_state_small()
+    o.Wbar, o.Wvar, o.mu = st["Wbar"], st["Wvar"], st["mu"]
+    o.qa, o.qb = st["tau"], 1.0
+    o.update_Z()
+    z = e.Zbar[it].cpu().numpy()
+    assert tensor_rel(z, o.Zbar) < 1e-9
+    m2 = e.M2[it].cpu().numpy()
+    from oracle.plate_oracle import pack_sym
+    assert tensor_rel(m2, pack_sym(o.M2())) < 1e-9
+    ld = e.logdet[it].cpu().numpy()
+    assert tensor_rel(0.5 / ld, o.qldZ) < 1e-9
+    # and the statistics layout, on the sample, against the numpy definition
+    ref = numpy_stats(Xs, o.Zbar, o.Sig, e.q)
+    from pyvb_b200 import PlateEngine
+    small = PlateEngine(Xs, e.q, mode="B", algo="dmma", device=e.X.device)
+    small.set_state({"Zbar": o.Zbar, "Sig": o.Sig})
+    small._ensure_stats()
+    got = small.stats.cpu().numpy()
+    L = small.L
+    assert tensor_rel(got[:L.scal], ref[:L.scal]) < 1e-11
