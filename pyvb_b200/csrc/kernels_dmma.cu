@@ -130,12 +130,8 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
                                          double (&Sg)[MI][Q], double (&z)[MI], double (&ldet)[MI], bool &ok) {
     const int lane = threadIdx.x & 31;
     double Ar[MI][Q];
-    double mant[MI];
-    int esum[MI];
 #pragma unroll
     for (int m = 0; m < MI; ++m) {
-        mant[m] = 1.0;
-        esum[m] = 0;
 #pragma unroll
         for (int j = 0; j < Q; ++j) Ar[m][j] = (j <= li) ? Arow[m][j] : 0.0;   // row li of the lower triangle
     }
@@ -145,11 +141,7 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
 #pragma unroll
         for (int m = 0; m < MI; ++m) {
             const double d = __shfl_sync(0xffffffffu, Ar[m][k], k, Q);
-            ok = ok && (d > 0.0);
-            const long long bits = __double_as_longlong(d);
-            esum[m] += (int)((bits >> 52) & 0x7ff) - 1023;
-            mant[m] *= __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
-            const double rinv = rsqrt(d);
+            const double rinv = rsqrt(d);                 // d <= 0 -> NaN / inf, caught through the log-det below
             const double l = Ar[m][k] * rinv;
             Ar[m][k] = l;
             if (li >= k) Lc[m][c_lcol(k, Q) + li] = (li == k) ? rinv : l;
@@ -181,8 +173,15 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
             }
         }
     }
+    // ln prod diag chol = -sum_k ln(1/l_kk): lane li takes its own diagonal slot, the group adds up
 #pragma unroll
-    for (int m = 0; m < MI; ++m) ldet[m] = 0.5 * (log(mant[m]) + (double)esum[m] * 0.69314718055994530942);
+    for (int m = 0; m < MI; ++m) {
+        double v = -log(Lc[m][c_lcol(0, Q) + li * Q - li * (li - 1) / 2]);
+#pragma unroll
+        for (int o = Q / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        ldet[m] = v;
+        ok = ok && (v - v == 0.0);                        // finite <=> every pivot was positive
+    }
     // ---- pass 2: X = L^-1 (column li per lane) and Sigma = X^T X
     double t[MI][Q];
 #pragma unroll
