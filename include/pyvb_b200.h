@@ -66,6 +66,10 @@ extern "C" {
 #define PYVB_SC_PLNV 8       /* mode A: sum ln v over those entries             */
 #define PYVB_SC_NROWS 9
 
+/* K2 column-sum partials (zsums): per CTA [<zz^T> packed | pad | zbar] column sums followed by
+ * sum 0.5/logdet, sum logdet, rows, 0 */
+#define PYVB_ZS_EXTRA 4
+
 /* device globals */
 #define PYVB_GL_QA 0
 #define PYVB_GL_QB 1
@@ -120,33 +124,39 @@ int pyvb_gw_woff(int q);                               /* first <w_d> column of 
 int pyvb_mz_pitch(int q);                              /* doubles per row of the interleaved [M2 | zbar] array */
 size_t pyvb_stats_len(int D, int q);                   /* doubles */
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo);
+size_t pyvb_zsums_len(long long N, int q);             /* doubles; 0 when K2 has no fast path for q */
 int pyvb_algo_supported(int algo, int D, int q);       /* 1/0 */
 
 int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu,
                      double *Gw, int ldg, void *stream);
 
 /* K1+K2 for rows [0,N): reads X, Gw, tau = gl[PYVB_GL_TAU]; P0 [q][q] and h0 = P0 m0 [q] are the
- * (constant) prior of z.  Sig may be NULL.  Non-PD rows are counted into gl[PYVB_GL_NONPD]. */
+ * (constant) prior of z.  Sig may be NULL.  Non-PD rows are counted into gl[PYVB_GL_NONPD].
+ * zsums (nullable, pyvb_zsums_len(N, q) doubles, DMMA path only): K2 leaves per-CTA partial column sums of
+ * its output rows there (S = sum_n <zz^T>_n, zsum, sum 0.5/logdet, sum logdet); pyvb_stats_f64 called with the
+ * same buffer and zsums_valid = 1 then skips its own pass over the MZ rows. */
 int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
                    const double *P0, const double *h0, double *gl,
                    double *Zbar, long long ldz, double *M2, long long ldm, double *Sig, double *logdet,
-                   int algo, void *stream);
+                   double *zsums, int algo, void *stream);
 
 /* K2 alone (DMMA-path layout): rows of MZ = [qprec packed | pad | eta] are replaced in place by
  * [<zz^T> packed | 0 | zbar]; batched q x q Cholesky / inverse / solve, q in {8,16,32}.  Sig may be NULL. */
 int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig, double *logdet, double *gl,
-                    void *stream);
+                    double *zsums, void *stream);
 
 /* K3+K4 over rows [0,N) into `stats` (fully overwritten).  V, Xorig, qldX are mode-A only (NULL in
  * mode B).  ws: pyvb_stats_workspace_bytes().
  * xcache (nullable, 2*D+2 doubles, caller-owned): the sums that depend on X alone -- cnt[D], colsumX[D],
  * sum x^2, number of observed entries.  With xcache_valid = 0 they are computed and stored there; with
  * xcache_valid = 1 (X unchanged since, i.e. mode B) the two passes over X are skipped and the cached local
- * sums are used. */
+ * sums are used.
+ * zsums / zsums_valid: the K2 partials of a pyvb_zstep_f64 / pyvb_zsolve_f64 call that covered exactly these
+ * N rows (see there); with zsums_valid = 0 the sums over the MZ rows are recomputed here. */
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
                    const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
                    long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes,
-                   double *xcache, int xcache_valid, int algo, void *stream);
+                   double *xcache, int xcache_valid, const double *zsums, int zsums_valid, int algo, void *stream);
 
 /* Gauss-Seidel update of W columns [col_lo, col_hi) from the (all-reduced) stats. */
 int pyvb_wupdate_f64(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,

@@ -30,11 +30,12 @@ SIGNATURES = {
     "pyvb_stats_workspace_bytes": (c_sz, [c_ll, c_int, c_int, c_int]),
     "pyvb_algo_supported": (c_int, [c_int, c_int, c_int]),
     "pyvb_pack_gw_f64": (c_int, [c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
+    "pyvb_zsums_len": (c_sz, [c_ll, c_int]),
     "pyvb_zstep_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_int, c_dp, c_dp, c_dp,
-                               c_dp, c_ll, c_dp, c_ll, c_dp, c_dp, c_int, c_dp]),
-    "pyvb_zsolve_f64": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp]),
+                               c_dp, c_ll, c_dp, c_ll, c_dp, c_dp, c_dp, c_int, c_dp]),
+    "pyvb_zsolve_f64": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pyvb_stats_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_ll, c_dp, c_ll, c_dp,
-                               c_dp, c_dp, c_sz, c_dp, c_int, c_int, c_dp]),
+                               c_dp, c_dp, c_sz, c_dp, c_int, c_dp, c_int, c_int, c_dp]),
     "pyvb_wupdate_f64": (c_int, [c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pyvb_global_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                 ctypes.POINTER(Consts), c_dp, c_dp]),

@@ -68,6 +68,12 @@ size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo) {
            align256((size_t)rowscalars_nblk(N) * PYVB_NSCAL * sizeof(double));
 }
 
+size_t pyvb_zsums_len(long long N, int q) {
+    int nblk, kw;
+    zsolve_partials(N, q, nblk, kw);
+    return (size_t)nblk * kw;
+}
+
 int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu, double *Gw, int ldg,
                      void *stream) {
     ARG(D >= 1 && q >= 1 && q <= PYVB_QMAX, "D, q");
@@ -79,7 +85,7 @@ int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const
 
 int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
                    const double *P0, const double *h0, double *gl, double *Zbar, long long ldz, double *M2,
-                   long long ldm, double *Sig, double *logdet, int algo, void *stream) {
+                   long long ldm, double *Sig, double *logdet, double *zsums, int algo, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Gw && P0 && h0 && gl && Zbar && M2 && logdet, "null pointer");
     ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
@@ -93,8 +99,8 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
         ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
             "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");
-        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, M2, Sig, logdet, algo == PYVB_ALGO_DMMA_K1,
-                              (cudaStream_t)stream);
+        e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, M2, Sig, logdet, zsums,
+                              algo == PYVB_ALGO_DMMA_K1, (cudaStream_t)stream);
     } else if (a == PYVB_ALGO_GENERIC) {
         e = launch_zstep_generic(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, Zbar, ldz, M2, ldm, Sig, logdet,
                                  (cudaStream_t)stream);
@@ -105,18 +111,18 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
 }
 
 int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig, double *logdet, double *gl,
-                    void *stream) {
+                    double *zsums, void *stream) {
     ARG(N >= 0 && (q == 8 || q == 16 || q == 32), "N, q (8, 16 or 32)");
     ARG(MZ && logdet && gl, "null pointer");
     ARG(ldmz == pyvb_mz_pitch(q), "ldmz must equal pyvb_mz_pitch(q)");
-    cudaError_t e = launch_zsolve(N, q, MZ, Sig, logdet, gl, (cudaStream_t)stream);
+    cudaError_t e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zsolve");
 }
 
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
                    const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
                    long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, double *xcache,
-                   int xcache_valid, int algo, void *stream) {
+                   int xcache_valid, const double *zsums, int zsums_valid, int algo, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Zbar && M2 && logdet && stats && ws, "null pointer");
     ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
@@ -125,7 +131,7 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
     const StatLayout L(D, q);
     const int a = pick_algo(algo, D, q);
     cudaStream_t st = (cudaStream_t)stream;
-    int nch, use_x = 0;
+    int nch, use_x = 0, nzblk = 0, zkw = 0;
     cudaError_t e;
     double *ws_main = (double *)ws;
     if (a == PYVB_ALGO_DMMA) {
@@ -135,8 +141,9 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
             "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");
         nch = stats_dmma_nchunks(N, D, q);
         use_x = (xcache != NULL && xcache_valid) ? 1 : 0;
+        if (zsums != NULL && zsums_valid) zsolve_partials(N, q, nzblk, zkw);
         e = launch_stats_dmma(N, D, q, X, ldx, M2, ws_main, nch, st);
-        if (e == cudaSuccess) e = launch_mzsums(N, D, q, Zbar, ldz, M2, ldm, ws_main, nch, st);
+        if (e == cudaSuccess && nzblk == 0) e = launch_mzsums(N, D, q, Zbar, ldz, M2, ldm, ws_main, nch, st);
         if (e == cudaSuccess && !use_x) e = launch_colsums(N, D, q, X, ldx, ws_main, nch, st);
     } else if (a == PYVB_ALGO_GENERIC) {
         nch = stats_generic_nchunks(N);
@@ -147,9 +154,14 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
     if (e != cudaSuccess) return cuda_fail(e, "stats");
     double *ws_sc = (double *)((char *)ws + align256((size_t)nch * L.len * sizeof(double)));
     const int nblk = rowscalars_nblk(N);
-    e = launch_rowscalars(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc, nblk, use_x && Xorig == NULL, st);
-    if (e != cudaSuccess) return cuda_fail(e, "rowscalars");
-    e = launch_stats_reduce(D, q, ws_main, nch, ws_sc, nblk, stats, xcache, use_x, st);
+    // mode B with cached X sums and K2's partials: nothing is left for the per-row scalar pass
+    const int need_rows = !(use_x && Xorig == NULL && nzblk > 0);
+    if (need_rows) {
+        e = launch_rowscalars(N, D, X, ldx, V, Xorig, qldX, logdet, ws_sc, nblk, use_x && Xorig == NULL, st);
+        if (e != cudaSuccess) return cuda_fail(e, "rowscalars");
+    }
+    e = launch_stats_reduce(D, q, ws_main, nch, need_rows ? ws_sc : NULL, nblk, stats, xcache, use_x,
+                            nzblk > 0 ? zsums : NULL, nzblk, zkw, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
 }
 

@@ -30,7 +30,8 @@ cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx
 cudaError_t launch_mzsums(long long N, int D, int q, const double *Zbar, long long ldz, const double *M2,
                           long long ldm, double *ws_main, int nchunks, cudaStream_t st);
 cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
-                                double *stats, double *xcache, int use_xcache, cudaStream_t st);
+                                double *stats, double *xcache, int use_xcache, const double *zsums, int nzblk,
+                                int zkw, cudaStream_t st);
 cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
                            const double *gl, double *Wbar, double *Wvar, cudaStream_t st);
 cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,
@@ -44,8 +45,11 @@ cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long l
 bool dmma_supported(int D, int q);
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                               int ldg, const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                              double *logdet, int k1_only, cudaStream_t st);
-cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, cudaStream_t st);
+                              double *logdet, double *zsums, int k1_only, cudaStream_t st);
+cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
+                          cudaStream_t st);
+// K2 leaves nblk partials of kw doubles each in zsums (0, 0: no fast K2 for this q)
+void zsolve_partials(long long N, int q, int &nblk, int &kw);
 int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                               double *ws_main, int nchunks, cudaStream_t st);

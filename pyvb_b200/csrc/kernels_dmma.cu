@@ -395,8 +395,9 @@ template <int Q> struct K2T {
     static constexpr int G = 32 / Q, RPP = G * MI;           // rows per warp pass
     // per warp: 2 x RPP rows (double buffered, solved in place), RPP packed column-major factors,
     // broadcast scratch, 2 mbarriers
-    static constexpr int WARP_D = 2 * RPP * OROW + RPP * P + 2 * MI * 32 + 2;
+    static constexpr int WARP_D = 2 * RPP * OROW + RPP * P + 2 * MI * 32 + 2 + OROW;
     static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8 + 16;
+    static constexpr int KW = OROW + PYVB_ZS_EXTRA;           // doubles per CTA in the column-sum partials
     static_assert(WARP_D % 2 == 0 && OROW % 2 == 0 && P % 2 == 0, "16-byte alignment of the per-warp buffers");
 };
 
@@ -405,7 +406,7 @@ template <int Q> struct K2T {
 template <int Q>
 __global__ void __launch_bounds__(32 * KC2<Q>::WARPS, KC2<Q>::OCC)
 zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, double *__restrict__ logdet,
-              double *gl, long long rows_per_warp) {
+              double *gl, long long rows_per_warp, double *__restrict__ zsums) {
     using T = K2T<Q>;
     extern __shared__ __align__(16) double smem_k2[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -414,6 +415,7 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
     double *lcs = raw + 2 * T::RPP * T::OROW;                // [RPP][P]
     double *xbuf = lcs + T::RPP * T::P;                      // [2][MI*32]
     uint64_t *bar = reinterpret_cast<uint64_t *>(xbuf + 2 * T::MI * 32);   // [2]
+    double *csum = xbuf + 2 * T::MI * 32 + 2;                // [OROW] column sums of this warp's output rows
     const int li = lane % Q, lg = lane / Q;
     const long long wr0 = ((long long)blockIdx.x * T::WARPS + warp) * rows_per_warp;
     long long wr1 = wr0 + rows_per_warp;
@@ -423,9 +425,10 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
         mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
+    for (int c = lane; c < T::OROW; c += 32) csum[c] = 0.0;
+    double s_qld = 0.0, s_ld = 0.0, s_n = 0.0;               // sum 0.5/logdet, sum logdet, rows (lanes with li == 0)
     __syncwarp();
-    if (wr0 >= wr1) return;
-    const int npass = (int)((wr1 - wr0 + T::RPP - 1) / T::RPP);
+    const int npass = (wr1 > wr0) ? (int)((wr1 - wr0 + T::RPP - 1) / T::RPP) : 0;
 
     auto load = [&](int pass) {      // lane 0: bulk loads of the pass' rows into raw[pass & 1]
         const int b = pass & 1;
@@ -435,7 +438,7 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
         for (int r = 0; r < nv; ++r)
             bulk_g2s(raw + (size_t)(b * T::RPP + r) * T::OROW, MZ + (r0 + r) * T::LDG, T::OROW * 8, &bar[b]);
     };
-    if (lane == 0) load(0);
+    if (lane == 0 && npass > 0) load(0);
     uint32_t ph[2] = {0, 0};
     for (int pass = 0; pass < npass; ++pass) {
         const int b = pass & 1;
@@ -489,19 +492,49 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
             O[m][T::PP + li] = z[m];
             if (li == 0 && valid) {
                 logdet[nrow[m]] = ldet[m];
+                s_qld += 0.5 / ldet[m];
+                s_ld += ldet[m];
+                s_n += 1.0;
                 if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
             }
         }
         fence_async_smem();
         __syncwarp();
+        const int nv = (wr1 - r0 < T::RPP) ? (int)(wr1 - r0) : T::RPP;
         if (lane == 0) {
-            const int nv = (wr1 - r0 < T::RPP) ? (int)(wr1 - r0) : T::RPP;
             for (int r = 0; r < nv; ++r)
                 bulk_s2g(MZ + (r0 + r) * T::LDG, raw + (size_t)(b * T::RPP + r) * T::OROW, T::OROW * 8);
             bulk_commit();
         }
+        // column sums of the finished rows (S = sum <zz^T>, zsum = sum zbar): saves a pass over MZ
+        for (int c = lane; c < T::OROW; c += 32) {
+            double a = csum[c];
+            for (int r = 0; r < nv; ++r) a += raw[(size_t)(b * T::RPP + r) * T::OROW + c];
+            csum[c] = a;
+        }
+        __syncwarp();                // all lanes are done with raw[b] before it is reloaded
     }
     if (lane == 0) bulk_wait_read_all();
+    if (zsums == nullptr) return;    // kernel-uniform
+    // ---- CTA partial of the column sums and of the per-row scalars, fixed order
+    s_qld = warp_sum(s_qld);
+    s_ld = warp_sum(s_ld);
+    s_n = warp_sum(s_n);
+    if (lane == 0) {
+        xbuf[0] = s_qld;
+        xbuf[1] = s_ld;
+        xbuf[2] = s_n;
+    }
+    __syncthreads();
+    double *out = zsums + (size_t)blockIdx.x * T::KW;
+    for (int c = threadIdx.x; c < T::KW; c += 32 * T::WARPS) {
+        double a = 0.0;
+        for (int w = 0; w < T::WARPS; ++w) {
+            const double *wb = smem_k2 + (size_t)w * T::WARP_D + 2 * T::RPP * T::OROW + T::RPP * T::P;   // xbuf of warp w
+            a += (c < T::OROW) ? wb[2 * T::MI * 32 + 2 + c] : ((c - T::OROW < 3) ? wb[c - T::OROW] : 0.0);
+        }
+        out[c] = a;
+    }
 }
 
 // pure-DMMA loop: the FP64 tensor roofline of the box (see pyvb_bench_dmma_f64)
@@ -526,27 +559,49 @@ cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream
 
 bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32) && D >= 16 && (D % 16) == 0; }
 
+// Grid of K2: two waves of CTAs over 148 SMs x OCC (every row costs the same), each warp owns a contiguous
+// block of rows (a multiple of the pass size).  Also the number of column-sum partials.
 template <int Q>
-static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double *logdet, double *gl,
+static void zsolve_plan(long long N, long long &blocks, long long &rpw) {
+    using T = K2T<Q>;
+    const long long warps_target = 148LL * KC2<Q>::OCC * T::WARPS * 2;
+    rpw = (N + warps_target - 1) / warps_target;
+    rpw = ((rpw + T::RPP - 1) / T::RPP) * T::RPP;
+    if (rpw < 4 * T::RPP) rpw = 4 * T::RPP;
+    const long long nwarps = (N + rpw - 1) / rpw;
+    blocks = (nwarps + T::WARPS - 1) / T::WARPS;
+    if (blocks < 1) blocks = 1;
+}
+
+template <int Q>
+static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
                                    cudaStream_t st) {
     using T = K2T<Q>;
     cudaError_t e = cudaFuncSetAttribute(zsolve_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
-    // ~8 waves of warps over 148 SMs x OCC x WARPS, rows per warp a multiple of the pass size
-    const long long warps_target = 148LL * KC2<Q>::OCC * T::WARPS * 8;
-    long long rpw = (N + warps_target - 1) / warps_target;
-    rpw = ((rpw + T::RPP - 1) / T::RPP) * T::RPP;
-    if (rpw < 4 * T::RPP) rpw = 4 * T::RPP;
-    const long long nwarps = (N + rpw - 1) / rpw;
-    const long long blocks = (nwarps + T::WARPS - 1) / T::WARPS;
-    zsolve_kernel<Q><<<(unsigned)blocks, 32 * T::WARPS, T::SMEM, st>>>(N, MZ, Sig, logdet, gl, rpw);
+    long long blocks, rpw;
+    zsolve_plan<Q>(N, blocks, rpw);
+    zsolve_kernel<Q><<<(unsigned)blocks, 32 * T::WARPS, T::SMEM, st>>>(N, MZ, Sig, logdet, gl, rpw, zsums);
     return cudaGetLastError();
+}
+
+void zsolve_partials(long long N, int q, int &nblk, int &kw) {
+    long long b = 0, r = 0;
+    nblk = kw = 0;
+    if (N <= 0) return;
+    switch (q) {
+        case 8: zsolve_plan<8>(N, b, r); kw = K2T<8>::KW; break;
+        case 16: zsolve_plan<16>(N, b, r); kw = K2T<16>::KW; break;
+        case 32: zsolve_plan<32>(N, b, r); kw = K2T<32>::KW; break;
+        default: return;
+    }
+    nblk = (int)b;
 }
 
 template <int Q>
 static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long ldx, const double *Gw,
                                   const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                                  double *logdet, int k1_only, cudaStream_t st) {
+                                  double *logdet, double *zsums, int k1_only, cudaStream_t st) {
     using T = ZT<Q>;
     CUtensorMap tmX;
     cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, T::KC, T::R,
@@ -558,28 +613,29 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ);
     e = cudaGetLastError();
     if (e != cudaSuccess || k1_only) return e;
-    return launch_zsolve_q<Q>(N, MZ, Sig, logdet, gl, st);
+    return launch_zsolve_q<Q>(N, MZ, Sig, logdet, gl, zsums, st);
 }
 
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
                               const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                              double *logdet, int k1_only, cudaStream_t st) {
+                              double *logdet, double *zsums, int k1_only, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     if (ldg != c_gw_pitch(q)) return cudaErrorInvalidValue;
     switch (q) {
-        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, k1_only, st);
-        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, k1_only, st);
-        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, k1_only, st);
+        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
+        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
+        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
     }
     return cudaErrorNotSupported;
 }
 
-cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, cudaStream_t st) {
+cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
+                          cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, st);
-        case 16: return launch_zsolve_q<16>(N, MZ, Sig, logdet, gl, st);
-        case 32: return launch_zsolve_q<32>(N, MZ, Sig, logdet, gl, st);
+        case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);
+        case 16: return launch_zsolve_q<16>(N, MZ, Sig, logdet, gl, zsums, st);
+        case 32: return launch_zsolve_q<32>(N, MZ, Sig, logdet, gl, zsums, st);
     }
     return cudaErrorNotSupported;
 }

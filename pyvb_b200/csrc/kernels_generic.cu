@@ -443,26 +443,49 @@ cudaError_t launch_rowscalars(long long N, int D, const double *X, long long ldx
 }
 
 // =============================================================== deterministic second stage
+// sum of n partials p[k * stride], four independent chains combined in a fixed order
+__device__ inline double strided_sum(const double *p, int n, size_t stride) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        a0 += p[(size_t)k * stride];
+        a1 += p[(size_t)(k + 1) * stride];
+        a2 += p[(size_t)(k + 2) * stride];
+        a3 += p[(size_t)(k + 3) * stride];
+    }
+    for (; k < n; ++k) a0 += p[(size_t)k * stride];
+    return (a0 + a1) + (a2 + a3);
+}
+
 __global__ void __launch_bounds__(256)
 stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunks, const double *__restrict__ ws_sc,
-                    int nblk, double *__restrict__ stats, double *xcache, int use_xcache) {
+                    int nblk, double *__restrict__ stats, double *xcache, int use_xcache,
+                    const double *__restrict__ zsums, int nzblk, int zkw) {
     const StatLayout L(D, q);
+    const int PP = gw_woff(q);
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < L.len; o += (size_t)gridDim.x * blockDim.x) {
         // slot of this entry in the X-only cache [cnt D | colx D | sxx | nE], or -1
         long long xc = -1;
         if (o >= L.cnt && o < L.S) xc = (long long)(o - L.cnt);
         else if (o == L.scal + PYVB_SC_SXX) xc = 2LL * D;
         else if (o == L.scal + PYVB_SC_NE) xc = 2LL * D + 1;
+        // slot of this entry in the K2 partials [<zz^T> packed | pad | zbar | 0.5/logdet | logdet | rows], or -1
+        int zc = -1;
+        if (zsums != nullptr) {
+            if (o >= L.S && o < L.zsum) zc = (int)(o - L.S);
+            else if (o >= L.zsum && o < L.scal) zc = PP + (int)(o - L.zsum);
+            else if (o == L.scal + PYVB_SC_QLDZ) zc = PP + q;
+            else if (o == L.scal + PYVB_SC_LOGDETZ) zc = PP + q + 1;
+            else if (o == L.scal + PYVB_SC_NROWS) zc = PP + q + 2;
+        }
         double acc = 0.0;
         if (xc >= 0 && xcache != nullptr && use_xcache) {
             acc = xcache[xc];
+        } else if (zc >= 0) {
+            acc = strided_sum(zsums + zc, nzblk, (size_t)zkw);
         } else {
-            if (o < L.scal) {
-                for (int c = 0; c < nchunks; ++c) acc += ws_main[(size_t)c * L.len + o];
-            } else {
-                const size_t k = o - L.scal;
-                for (int b = 0; b < nblk; ++b) acc += ws_sc[(size_t)b * PYVB_NSCAL + k];
-            }
+            if (o < L.scal) acc = strided_sum(ws_main + o, nchunks, L.len);
+            else if (ws_sc != nullptr) acc = strided_sum(ws_sc + (o - L.scal), nblk, PYVB_NSCAL);
             if (xc >= 0 && xcache != nullptr) xcache[xc] = acc;
         }
         stats[o] = acc;
@@ -470,11 +493,13 @@ stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunk
 }
 
 cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
-                                double *stats, double *xcache, int use_xcache, cudaStream_t st) {
+                                double *stats, double *xcache, int use_xcache, const double *zsums, int nzblk,
+                                int zkw, cudaStream_t st) {
     const StatLayout L(D, q);
     size_t b = (L.len + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
-    stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats, xcache, use_xcache);
+    stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats, xcache, use_xcache,
+                                                     zsums, nzblk, zkw);
     return cudaGetLastError();
 }
 

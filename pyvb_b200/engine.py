@@ -122,6 +122,10 @@ class PlateEngine(object):
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         self.xcache = torch.zeros(2 * D + 2, dtype=f64, device=dev) if mode == "B" else None
         self._xcache_valid = False
+        # per-CTA column sums of the MZ rows left by the batched solve (K2) of a full-range Z update
+        nz = int(self.lib.pyvb_zsums_len(N, q)) if self.lib.pyvb_algo_supported(ALGO_DMMA, D, q) else 0
+        self.zsums = torch.zeros(nz, dtype=f64, device=dev) if nz > 0 and self.algo in (ALGO_AUTO, ALGO_DMMA) else None
+        self._zsums_valid = False
         self.gl = torch.zeros(GL_LEN, dtype=f64, device=dev)
         self.trace = torch.zeros(int(trace_len), dtype=f64, device=dev)
         self.trace_pos = 0
@@ -208,6 +212,7 @@ class PlateEngine(object):
         self.gl.copy_(gl.to(dev))
         self._stats_fresh = False
         self._gw_fresh = False
+        self._zsums_valid = False
 
     def init_random(self, seed=1234, rank=0):
         """Scale-run initialisation on the device: Wbar ~ N(0,1) (same on every rank),
@@ -292,7 +297,8 @@ class PlateEngine(object):
                                      self._p(self.Xorig), self._p(self.qldX), self.Zbar.data_ptr(), self.ldmz,
                                      self.M2.data_ptr(), self.ldmz, self.logdet.data_ptr(), self.stats.data_ptr(),
                                      self.ws.data_ptr(), self.ws_bytes, self._p(self.xcache),
-                                     int(self._xcache_valid), self.algo, self._stream())
+                                     int(self._xcache_valid), self._p(self.zsums), int(self._zsums_valid),
+                                     self.algo, self._stream())
         _cabi.check(rc, "pyvb_stats_f64")
         self._xcache_valid = self.xcache is not None
         if self.distributed:
@@ -316,12 +322,16 @@ class PlateEngine(object):
         self._ensure_gw()
         q, P, D = self.q, self.P, self.D
         sig = 0 if self.Sig is None else self.Sig.data_ptr() + lo * P * 8
+        full = (lo == 0 and hi == self.N and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA))
+        self._zsums_valid = False
         rc = self.lib.pyvb_zstep_f64(hi - lo, D, q, self.X.data_ptr() + lo * D * 8, D, self.Gw.data_ptr(),
                                      self.ldg, self.P0.data_ptr(), self.h0.data_ptr(), self.gl.data_ptr(),
                                      self.Zbar.data_ptr() + lo * self.ldmz * 8, self.ldmz,
                                      self.M2.data_ptr() + lo * self.ldmz * 8, self.ldmz, sig,
-                                     self.logdet.data_ptr() + lo * 8, self.algo, self._stream())
+                                     self.logdet.data_ptr() + lo * 8, self.zsums.data_ptr() if full else 0,
+                                     self.algo, self._stream())
         _cabi.check(rc, "pyvb_zstep_f64")
+        self._zsums_valid = full
         self._stats_fresh = False
 
     def update_X(self, lo=0, hi=None):
