@@ -112,7 +112,7 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
 
 int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig, double *logdet, double *gl,
                     double *zsums, void *stream) {
-    ARG(N >= 0 && (q == 8 || q == 16 || q == 32), "N, q (8, 16 or 32)");
+    ARG(N >= 0 && (q == 8 || q == 16 || q == 32 || q == 64), "N, q (8, 16, 32 or 64)");
     ARG(MZ && logdet && gl, "null pointer");
     ARG(ldmz == pyvb_mz_pitch(q), "ldmz must equal pyvb_mz_pitch(q)");
     cudaError_t e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, (cudaStream_t)stream);

@@ -50,6 +50,11 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
                           cudaStream_t st);
 // K2 leaves nblk partials of kw doubles each in zsums (0, 0: no fast K2 for this q)
 void zsolve_partials(long long N, int q, int &nblk, int &kw);
+// blocked tensor-core K2 (kernels_k2.cu): q in {8, 16, 32, 64}
+int zsolve_blocked_blocks(long long N, int q);
+int zsolve_blocked_kw(int q);
+cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl,
+                                  double *zsums, cudaStream_t st);
 int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                               double *ws_main, int nchunks, cudaStream_t st);

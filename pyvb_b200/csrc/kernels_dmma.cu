@@ -19,6 +19,7 @@
 // four rows a half-warp touches differ in the swizzle bits, and row pitches of the non-swizzled tiles are
 // 32 or 96 bytes mod 128.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -127,7 +128,7 @@ __host__ __device__ constexpr int c_lcol(int k, int Q) { return k * Q - k * (k -
 template <int Q, int MI>
 __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const double *const (&eta)[MI],
                                          double *const (&Lc)[MI], double *xbuf, const int li,
-                                         double (&Sg)[MI][Q], double (&z)[MI], double (&ldet)[MI], bool &ok) {
+                                         double (&Sg)[MI][Q], double (&z)[MI], double (&ldet)[MI], bool (&ok)[MI]) {
     const int lane = threadIdx.x & 31;
     double Ar[MI][Q];
 #pragma unroll
@@ -180,7 +181,7 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
 #pragma unroll
         for (int o = Q / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         ldet[m] = v;
-        ok = ok && (v - v == 0.0);                        // finite <=> every pivot was positive
+        ok[m] = (v - v == 0.0);                           // finite <=> every pivot was positive
     }
     // ---- pass 2: X = L^-1 (column li per lane) and Sigma = X^T X
     double t[MI][Q];
@@ -471,7 +472,7 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
         }
         __syncwarp();
         double Sg[T::MI][Q], z[T::MI], ldet[T::MI];
-        bool ok = true;
+        bool ok[T::MI];
         k2_solve<Q, T::MI>(Arow, eta, Lc, xbuf, li, Sg, z, ldet, ok);
 #pragma unroll
         for (int m = 0; m < T::MI; ++m) xbuf[m * 32 + lane] = z[m];
@@ -495,7 +496,7 @@ zsolve_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, do
                 s_qld += 0.5 / ldet[m];
                 s_ld += ldet[m];
                 s_n += 1.0;
-                if (!ok) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
+                if (!ok[m]) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);
             }
         }
         fence_async_smem();
@@ -585,10 +586,26 @@ static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double 
     return cudaGetLastError();
 }
 
+// Which batched solve runs for this q: the blocked tensor-core kernel (kernels_k2.cu) or the register-resident
+// one above.  q = 64 only exists blocked; PYVB_K2=blocked / PYVB_K2=reg overrides the default for the others.
+static bool k2_blocked(int q) {
+    const char *e = getenv("PYVB_K2");               // read per call: tests flip it
+    const int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 2 : 0;
+    if (q == 64) return true;
+    if (mode == 1) return true;
+    if (mode == 2) return false;
+    return q >= 32;                                  // measured: q = 32 6.4 ms vs 9.0 ms per 1M rows; q <= 16 the other way
+}
+
 void zsolve_partials(long long N, int q, int &nblk, int &kw) {
     long long b = 0, r = 0;
     nblk = kw = 0;
     if (N <= 0) return;
+    if (k2_blocked(q)) {
+        kw = zsolve_blocked_kw(q);
+        nblk = kw > 0 ? zsolve_blocked_blocks(N, q) : 0;
+        return;
+    }
     switch (q) {
         case 8: zsolve_plan<8>(N, b, r); kw = K2T<8>::KW; break;
         case 16: zsolve_plan<16>(N, b, r); kw = K2T<16>::KW; break;
@@ -613,7 +630,7 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ);
     e = cudaGetLastError();
     if (e != cudaSuccess || k1_only) return e;
-    return launch_zsolve_q<Q>(N, MZ, Sig, logdet, gl, zsums, st);
+    return launch_zsolve(N, Q, MZ, Sig, logdet, gl, zsums, st);
 }
 
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
@@ -632,6 +649,7 @@ cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long l
 cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
                           cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
+    if (k2_blocked(q)) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st);
     switch (q) {
         case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);
         case 16: return launch_zsolve_q<16>(N, MZ, Sig, logdet, gl, zsums, st);

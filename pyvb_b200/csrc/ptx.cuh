@@ -51,6 +51,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst_smem, const void *tmap, in
         "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// L2 prefetch of a contiguous block (bytes a multiple of 16, 16-byte aligned)
+__device__ __forceinline__ void prefetch_l2(const void *gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
