@@ -296,7 +296,7 @@ def run_ours(a):
         ms_k1 = time_calls(k1_only, 5)
         def k2_only():                           # in place on rows left as [qprec | eta] by k1_only
             _cabi.check(lib.pyvb_zsolve_f64(eng.N, eng.q, eng.MZ.data_ptr(), eng.ldmz, 0, eng.logdet.data_ptr(),
-                                            eng.gl.data_ptr(), eng.zsums.data_ptr(),
+                                            eng.gl.data_ptr(), eng.zsums.data_ptr() if eng.zsums is not None else 0,
                                             torch.cuda.current_stream(dev).cuda_stream), "zsolve")
         k1_only(); ms_k2 = time_calls(k2_only, 1)
         eng.update_Z()                           # restore a consistent state

@@ -90,24 +90,37 @@ static cudaError_t make_map(CUtensorMap *m, const void *base, uint64_t inner, ui
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// NCT > 1: the output columns are split into NCT column tiles, one CTA each (q = 64: 268 column groups do not
+// fit one CTA's accumulators); consecutive CTAs share the X tile through L2
 template <int Q> struct ZC;
-template <> struct ZC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, MI = 2, OCC = 2; };
-template <> struct ZC<16> { static constexpr int WM = 4, WN = 1, RGW = 2, KC = 16, ST = 3, MI = 2, OCC = 2; };
-template <> struct ZC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, MI = 1, OCC = 1; };
+template <> struct ZC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, OCC = 2, NCT = 1; };
+template <> struct ZC<16> { static constexpr int WM = 4, WN = 1, RGW = 2, KC = 16, ST = 3, OCC = 2, NCT = 1; };
+template <> struct ZC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 1; };
+template <> struct ZC<64> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 4; };
+
+__host__ __device__ constexpr int c_pitch4(int need) {      // smallest pitch >= need with pitch = 4 (mod 8)
+    int p = need;
+    while ((p % 8) != 4) ++p;
+    return p;
+}
 
 template <int Q> struct ZT {
     using C = ZC<Q>;
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, NGO = PP / 8, NGE = Q / 8, NG = NGO + NGE;
-    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST, MI = C::MI;
-    static constexpr int NGW = (NG + WN - 1) / WN;
+    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST, NCT = C::NCT;
+    static constexpr bool TILED = NCT > 1;
+    static constexpr int NGT = (NG + NCT - 1) / NCT;   // column groups per column tile
+    static constexpr int NGW = (NGT + WN - 1) / WN;
     static constexpr int R = WM * RGW * 8;
     static constexpr int NCW = WM * WN;
     static constexpr int NTHR = NCW * 32;       // no dedicated producer warp: warp 0 also issues the copies
     static constexpr int LDG = c_gw_pitch(Q);   // pitch of Gw rows and of the interleaved MZ rows
     static constexpr int MUCOL = PP + Q;
+    static constexpr int GP = TILED ? c_pitch4(NGT * 8 + 2) : LDG;   // pitch of the Gw tile in shared memory
+    static constexpr int MUL = TILED ? NGT * 8 : MUCOL;              // where mu sits in a shared-memory Gw row
     static constexpr int XT_B = R * KC * 8;     // swizzled X tile (bytes), multiple of 1024
-    static constexpr int GS_B = KC * LDG * 8;
-    static constexpr int OROW = PP + Q;         // doubles per output row [packed | pad | eta]
+    static constexpr int GS_B = KC * GP * 8;
+    static constexpr int OROW = NGT * 8;        // doubles per output row (segment) [packed | pad | eta]
     static constexpr int SROW = c_srow(OROW);   // staging pitch
     static constexpr int MAIN_B = (c_max(ST * (XT_B + GS_B), R * SROW * 8) + 15) & ~15;
     static constexpr size_t SMEM = 1024 + (size_t)MAIN_B + (size_t)(P + Q) * 8 + 2 * ST * 8;
@@ -265,7 +278,11 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     uint64_t *empty = full + T::ST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long row0 = (long long)blockIdx.x * T::R;
+    const int ct = T::TILED ? (int)(blockIdx.x % T::NCT) : 0;          // column tile
+    const long long row0 = (long long)(blockIdx.x / T::NCT) * T::R;
+    const int cgb = ct * T::NGT;                                        // first column group of the tile
+    const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;    // groups in this tile
+    const bool need_mu = cgb + ngt > T::NGO;                            // the tile has eta columns
     const int nk = D / T::KC;
 
     for (int p = tid; p < T::P; p += T::NTHR) {
@@ -289,10 +306,25 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         const int s = kc % T::ST;
         const uint32_t ph = (uint32_t)((kc / T::ST) & 1);
         mbar_wait(&empty[s], ph ^ 1);
-        if (lane == 0) {
-            mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::GS_B));
-            tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);   // rows past N: zero fill
-            bulk_g2s(gs_base + s * T::GS_B, Gw + (size_t)kc * T::KC * T::LDG, T::GS_B, &full[s]);
+        if (!T::TILED) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::GS_B));
+                tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);   // rows past N: zero fill
+                bulk_g2s(gs_base + s * T::GS_B, Gw + (size_t)kc * T::KC * T::LDG, T::GS_B, &full[s]);
+            }
+        } else {
+            // one Gw row segment per lane (+ the mu pair for the tile that holds the eta columns)
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::KC * (ngt * 64 + (need_mu ? 16 : 0))));
+                tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);
+            }
+            __syncwarp();
+            if (lane < T::KC) {
+                double *dst = reinterpret_cast<double *>(gs_base + s * T::GS_B) + lane * T::GP;
+                const double *src = Gw + (size_t)(kc * T::KC + lane) * T::LDG;
+                bulk_g2s(dst, src + cgb * 8, (uint32_t)(ngt * 64), &full[s]);
+                if (need_mu) bulk_g2s(dst + T::MUL, src + T::MUCOL, 16, &full[s]);
+            }
         }
         __syncwarp();
     };
@@ -303,8 +335,9 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     const int wm = warp / T::WN, wn = warp % T::WN;
     const int gid = lane >> 2, qd = lane & 3;
     const int prow = row_perm<T::KC>(gid);                 // tile row (within a group of 8) of MMA row gid
-    const int cg0 = wn * T::NGW;
-    const int ncg = (T::NG - cg0 < T::NGW) ? (T::NG - cg0) : T::NGW;
+    const int lg0 = wn * T::NGW;                            // first group of this warp inside the tile
+    const int cg0 = cgb + lg0;
+    const int ncg = (ngt - lg0 < T::NGW) ? (ngt - lg0) : T::NGW;
     double acc[T::RGW][T::NGW][2];
 #pragma unroll
     for (int rg = 0; rg < T::RGW; ++rg)
@@ -320,11 +353,11 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
             if (warp == 0 && kc + T::ST - 1 < nk) produce(kc + T::ST - 1);
             mbar_wait(&full[s], ph);
             const unsigned char *xs = xs_base + s * T::XT_B;
-            const double *gs = reinterpret_cast<const double *>(gs_base + s * T::GS_B) + qd * T::LDG;
+            const double *gs = reinterpret_cast<const double *>(gs_base + s * T::GS_B) + qd * T::GP;
 #pragma unroll
             for (int kk = 0; kk < T::KC / 4; ++kk) {
-                const double *grow = gs + kk * 4 * T::LDG;
-                const double muv = grow[T::MUCOL];
+                const double *grow = gs + kk * 4 * T::GP;
+                const double muv = grow[T::MUL];
                 double ao[T::RGW], ax[T::RGW];
 #pragma unroll
                 for (int rg = 0; rg < T::RGW; ++rg) {
@@ -338,7 +371,7 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
                 for (int j = 0; j < T::NGW; ++j) {
                     if (T::WN > 1 && j >= ncg) continue;
                     const int cg = cg0 + j;
-                    const double b = grow[cg * 8 + gid];
+                    const double b = grow[(lg0 + j) * 8 + gid];
                     const bool otype = cg < T::NGO;
 #pragma unroll
                     for (int rg = 0; rg < T::RGW; ++rg)
@@ -373,13 +406,14 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
                 v.x = fma(tau, acc[rg][j][0], h0s[c - T::PP]);
                 v.y = fma(tau, acc[rg][j][1], h0s[c + 1 - T::PP]);
             }
-            *reinterpret_cast<double2 *>(srow + c) = v;
+            *reinterpret_cast<double2 *>(srow + (lg0 + j) * 8 + 2 * qd) = v;
         }
     }
     fence_async_smem();
     __syncthreads();
     for (int r = tid; r < T::R; r += T::NTHR)
-        if (row0 + r < N) bulk_s2g(MZ + (row0 + r) * T::LDG, stg + (size_t)r * T::SROW, T::OROW * 8);
+        if (row0 + r < N)
+            bulk_s2g(MZ + (row0 + r) * T::LDG + cgb * 8, stg + (size_t)r * T::SROW, (uint32_t)(ngt * 64));
     bulk_commit();
     bulk_wait_read_all();
 }
@@ -558,7 +592,7 @@ cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream
     return cudaGetLastError();
 }
 
-bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32) && D >= 16 && (D % 16) == 0; }
+bool dmma_supported(int D, int q) { return (q == 8 || q == 16 || q == 32 || q == 64) && D >= 16 && (D % 16) == 0; }
 
 // Grid of K2: two waves of CTAs over 148 SMs x OCC (every row costs the same), each warp owns a contiguous
 // block of rows (a multiple of the pass size).  Also the number of column-sum partials.
@@ -626,7 +660,7 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
-    const long long blocks = (N + T::R - 1) / T::R;
+    const long long blocks = ((N + T::R - 1) / T::R) * T::NCT;
     zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ);
     e = cudaGetLastError();
     if (e != cudaSuccess || k1_only) return e;
@@ -642,6 +676,7 @@ cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long l
         case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
         case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
         case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
+        case 64: return launch_zstep_q<64>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
     }
     return cudaErrorNotSupported;
 }
@@ -660,24 +695,28 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
 
 // ------------------------------------------------------------------ statistics kernel (K3)
 template <int Q> struct SC;
-template <> struct SC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, OCC = 1; };
-template <> struct SC<16> { static constexpr int WM = 8, WN = 1, RGW = 2, KC = 16, ST = 3, OCC = 1; };
-template <> struct SC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1; };
+template <> struct SC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, OCC = 1, NCT = 1; };
+template <> struct SC<16> { static constexpr int WM = 8, WN = 1, RGW = 2, KC = 16, ST = 3, OCC = 1, NCT = 1; };
+template <> struct SC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 1; };
+template <> struct SC<64> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 4; };
 
 template <int Q> struct STT {
     using C = SC<Q>;
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7;
     static constexpr int NGO = (PP + Q) / 8, NGX = Q / 8, NG = NGO + NGX;   // O-type: [<zz^T> | pad | zbar]; X-type: zbar
-    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST;
-    static constexpr int NGW = (NG + WN - 1) / WN;
+    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST, NCT = C::NCT;
+    static constexpr bool TILED = NCT > 1;      // output columns split over NCT CTAs (q = 64)
+    static constexpr int NGT = (NG + NCT - 1) / NCT;
+    static constexpr int NGW = (NGT + WN - 1) / WN;
     static constexpr int DT = WM * RGW * 8;     // data dimensions per CTA (multiple of 16)
     static constexpr int NSUB = DT / 16;        // swizzled X sub-tiles [KC rows][16 d] per stage
     static constexpr int NCW = WM * WN;
     static constexpr int NTHR = NCW * 32;       // warp 0 doubles as the producer
-    static constexpr int VP = c_gw_pitch(Q);    // pitch of the MZ rows (global and in shared memory)
+    static constexpr int VP = c_gw_pitch(Q);    // pitch of the MZ rows in global memory
+    static constexpr int VPS = TILED ? c_pitch4(NGT * 8) : VP;   // ... and of the (column tile of the) rows in shared memory
     static constexpr bool BTILE = VP <= 256;    // MZ tile through one tensor copy (box dims are limited to 256)
     static constexpr int SUB_B = KC * 128;
-    static constexpr int AS_B = NSUB * SUB_B, VS_B = KC * VP * 8;
+    static constexpr int AS_B = NSUB * SUB_B, VS_B = KC * VPS * 8;
     static constexpr size_t SMEM = 1024 + (size_t)ST * (AS_B + VS_B) + 2 * ST * 8;
     static_assert(DT % 16 == 0 && SUB_B % 1024 == 0, "sub-tiles must stay 1024-byte aligned");
 };
@@ -700,7 +739,13 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr bool virt = false;
-    const int d0 = blockIdx.x * T::DT;
+    const int ct = T::TILED ? (int)(blockIdx.x % T::NCT) : 0;            // column tile
+    const int cgb = ct * T::NGT;
+    const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;
+    // MZ columns the tile needs: its O-type groups (the X-type groups re-use the zbar columns, which are the
+    // last O-type groups of the same -- the last -- tile)
+    const int vcols = (((cgb + ngt < T::NGO) ? (cgb + ngt) : T::NGO) - cgb) * 8;
+    const int d0 = (int)(blockIdx.x / T::NCT) * T::DT;
     const int dvalid = (D - d0 < T::DT) ? (D - d0) : T::DT;
     const int nsub = dvalid / 16;
     const long long r0 = (long long)blockIdx.y * rows_per_chunk;
@@ -735,16 +780,18 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         } else {
             const int nval = (N - nb < T::KC) ? (int)(N - nb) : T::KC;
+            const int wcols = T::TILED ? vcols : (T::PP + Q);
             for (int r = nval; r < T::KC; ++r)
-                for (int c = lane; c < T::VP; c += 32) vs[r * T::VP + c] = 0.0;
+                for (int c = lane; c < T::VPS; c += 32) vs[r * T::VPS + c] = 0.0;
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(&full[s], (uint32_t)(nsub * T::SUB_B + nval * (T::PP + Q) * 8));
+                mbar_arrive_expect_tx(&full[s], (uint32_t)(nsub * T::SUB_B + nval * wcols * 8));
                 for (int t = 0; t < nsub; ++t)
                     tma_load_2d(as_base + s * T::AS_B + t * T::SUB_B, &tmX, d0 + t * 16, (int)nb, &full[s]);
             }
             __syncwarp();
-            if (lane < nval) bulk_g2s(vs + lane * T::VP, MZ + (nb + lane) * T::VP, (T::PP + Q) * 8, &full[s]);
+            if (lane < nval)
+                bulk_g2s(vs + lane * T::VPS, MZ + (nb + lane) * T::VP + cgb * 8, (uint32_t)(wcols * 8), &full[s]);
         }
         __syncwarp();
     };
@@ -754,8 +801,9 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // ===================== DMMA main loop =====================
     const int wm = warp / T::WN, wn = warp % T::WN;
     const int gid = lane >> 2, qd = lane & 3;
-    const int cg0 = wn * T::NGW;
-    const int ncg = (T::NG - cg0 < T::NGW) ? (T::NG - cg0) : T::NGW;
+    const int lg0 = wn * T::NGW;                            // first group of this warp inside the column tile
+    const int cg0 = cgb + lg0;
+    const int ncg = (ngt - lg0 < T::NGW) ? (ngt - lg0) : T::NGW;
     const int blk0 = wm * T::RGW;                           // first group of 8 d's of this warp inside the tile
     // MMA row gid -> d inside a 16-wide sub-tile (first or second half chosen by the group parity): the four
     // rows of a half-warp must sit in chunks that differ in bit 2 -> {0,1,8,9 | 2,3,10,11} (+4 for odd groups)
@@ -782,7 +830,7 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             mbar_wait(&full[s], ph);
             if (active) {
                 const unsigned char *as = as_base + s * T::AS_B;
-                const double *vs = reinterpret_cast<const double *>(vs_base + s * T::VS_B) + qd * T::VP + gid;
+                const double *vs = reinterpret_cast<const double *>(vs_base + s * T::VS_B) + qd * T::VPS + gid;
 #pragma unroll
                 for (int kk = 0; kk < T::KC / 4; ++kk) {
                     const int row = kk * 4 + qd;
@@ -807,8 +855,8 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const int cg = cg0 + j;
                         const bool otype = cg < T::NGO;
                         // X-type groups re-use the zbar columns of the tile
-                        const int col = otype ? cg * 8 : (T::PP + (cg - T::NGO) * 8);
-                        const double b = vs[kk * 4 * T::VP + col];
+                        const int col = (otype ? cg * 8 : (T::PP + (cg - T::NGO) * 8)) - cgb * 8;
+                        const double b = vs[kk * 4 * T::VPS + col];
 #pragma unroll
                         for (int rg = 0; rg < T::RGW; ++rg)
                             dmma884(acc[rg][j][0], acc[rg][j][1], otype ? ao[rg] : ax[rg], b);
@@ -859,9 +907,10 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 static long long gcdll(long long a, long long b) { return b ? gcdll(b, a % b) : a; }
 
 int stats_dmma_nchunks(long long N, int D, int q) {
-    int kc = 16, dt = 128;
-    if (q == 32) { kc = 8; dt = 32; }
-    const int ndt = (D + dt - 1) / dt;
+    int kc = 16, dt = 128, nct = 1;
+    if (q >= 32) { kc = 8; dt = 32; }
+    if (q == 64) nct = SC<64>::NCT;
+    const int ndt = ((D + dt - 1) / dt) * nct;               // CTAs per row chunk
     // CTAs = ndt * nchunks should be a whole number of waves of 148 SMs (1 CTA/SM): nchunks = k * step
     const long long step = 148 / gcdll(148, ndt);
     long long by_rows = (N + 64LL * kc - 1) / (64LL * kc);     // at least 64 pipeline steps per chunk
@@ -892,7 +941,7 @@ static cudaError_t launch_stats_q(long long N, int D, const double *X, long long
     long long rpc = (N + nchunks - 1) / nchunks;
     rpc = ((rpc + T::KC - 1) / T::KC) * T::KC;                 // chunk boundaries on pipeline-step boundaries
     if (rpc < T::KC) rpc = T::KC;
-    const int ndt = (D + T::DT - 1) / T::DT;
+    const int ndt = ((D + T::DT - 1) / T::DT) * T::NCT;
     dim3 grid((unsigned)ndt, (unsigned)nchunks);
     stats_dmma_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc);
     return cudaGetLastError();
@@ -905,6 +954,7 @@ cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long l
         case 8: return launch_stats_q<8>(N, D, X, ldx, MZ, ws_main, nchunks, st);
         case 16: return launch_stats_q<16>(N, D, X, ldx, MZ, ws_main, nchunks, st);
         case 32: return launch_stats_q<32>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+        case 64: return launch_stats_q<64>(N, D, X, ldx, MZ, ws_main, nchunks, st);
     }
     return cudaErrorNotSupported;
 }

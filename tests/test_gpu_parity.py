@@ -154,7 +154,8 @@ def test_stats_are_additive_over_row_shards(eng):
 
 
 # ---------------------------------------------------------------- DMMA (FP64 tensor core) path
-DMMA_SHAPES = [(5000, 256, 16), (64, 16, 16), (1, 32, 16), (777, 64, 32), (2100, 128, 32), (1000, 48, 8), (4099, 80, 8)]
+DMMA_SHAPES = [(5000, 256, 16), (64, 16, 16), (1, 32, 16), (777, 64, 32), (2100, 128, 32), (1000, 48, 8), (4099, 80, 8),
+               (333, 48, 64), (1500, 128, 64)]
 
 
 @pytest.mark.parametrize("shape", DMMA_SHAPES)
@@ -186,7 +187,7 @@ def test_dmma_zstep_and_stats_match_generic(eng, shape):
     ed.check()
 
 
-@pytest.mark.parametrize("shape", [(3000, 256, 16), (1200, 64, 32), (900, 32, 8)])
+@pytest.mark.parametrize("shape", [(3000, 256, 16), (1200, 64, 32), (900, 32, 8), (700, 96, 64)])
 def test_dmma_iterations_match_oracle(eng, shape):
     N, D, q = shape
     X = synth_pca(N, D, q, 0.25, seed=N)
