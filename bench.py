@@ -33,7 +33,9 @@ def workload_name(a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """Polls NVML (clocks, power, throttle reasons) every ~4 ms from a thread while the timed region runs."""
+    """Polls NVML (clocks, power, throttle reasons) every ~20 ms from a thread while the timed region runs.
+    (Polling every 4 ms slowed the sweeps of a multi-GPU run by 0.28 ms each -- NVML queries disturb the peer
+    traffic of the exchange kernel; tools/comm_probe.sh.)"""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                "hw_power_brake": 0x80, "sync_boost": 0x10}
 
@@ -65,7 +67,7 @@ class ClockSampler(object):
                                   nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, rs))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.02)
 
     def stop(self, t0, t1):
         if not self.ok:
@@ -228,6 +230,8 @@ def run_ours(a):
                       row_offset=rank * a.N, device=dev)
     del X
     eng.init_random(seed=4321, rank=rank)
+    if os.environ.get("PYVB_NOCOMM"):          # diagnosis only: time the sweeps without the exchange
+        eng.distributed = False
 
     def sync():
         if dist is not None:
@@ -237,7 +241,7 @@ def run_ours(a):
     for _ in range(max(a.warmup, 3)):
         eng.iterate_async()
     sync()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("PYVB_NOSAMPLER")) else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
@@ -355,6 +359,7 @@ def run_ours(a):
             line["cpu_baseline"] = cpu_baseline(a)
         sys.stdout.flush()
         os.write(real_out, (json.dumps(line) + "\n").encode())
+    eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -362,7 +367,7 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--N", type=int, default=1000000)

@@ -66,6 +66,9 @@ extern "C" {
 #define PYVB_SC_PLNV 8       /* mode A: sum ln v over those entries             */
 #define PYVB_SC_NROWS 9
 
+/* multi-GPU exchange: per-CTA flags in a peer buffer (see pyvb_peer_bytes) */
+#define PYVB_PEER_MAXBLK 512
+
 /* K2 column-sum partials (zsums): per CTA [<zz^T> packed | pad | zbar] column sums followed by
  * sum 0.5/logdet, sum logdet, rows, 0 */
 #define PYVB_ZS_EXTRA 4
@@ -115,6 +118,16 @@ typedef struct pyvb_consts {
     int mode_a;           /* 1: reference-exact imputation mode (adds the X entropy terms) */
 } pyvb_consts;
 
+/* Multi-GPU exchange of the statistics over NVLink peer memory (one process per GPU, one box).  bufs is a DEVICE
+ * array of `world` pointers: entry r is rank r's exchange buffer (pyvb_peer_bytes(stats_len) bytes, from
+ * pyvb_peer_alloc on rank r, opened here through pyvb_peer_import).  epoch: 1, 2, 3, ... -- the same on every rank,
+ * incremented by the caller for every pyvb_stats_f64 call that carries the struct. */
+typedef struct pyvb_peers {
+    void *const *bufs;            /* device pointer */
+    int world, rank;
+    unsigned long long epoch;
+} pyvb_peers;
+
 int pyvb_version(void);
 const char *pyvb_last_error(void);
 
@@ -125,6 +138,14 @@ int pyvb_mz_pitch(int q);                              /* doubles per row of the
 size_t pyvb_stats_len(int D, int q);                   /* doubles */
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo);
 size_t pyvb_zsums_len(long long N, int q);             /* doubles; 0 when K2 has no fast path for q */
+
+/* peer exchange buffers: cudaMalloc'd (zeroed) so that the CUDA IPC handle (64 bytes) names exactly this buffer */
+size_t pyvb_peer_bytes(size_t stats_len);
+int pyvb_peer_alloc(size_t bytes, void **dptr /* host out */);
+int pyvb_peer_free(void *dptr);
+int pyvb_peer_export(void *dptr, unsigned char *handle64 /* host out, 64 bytes */);
+int pyvb_peer_import(const unsigned char *handle64 /* host */, void **dptr /* host out */);
+int pyvb_peer_close(void *dptr);
 int pyvb_algo_supported(int algo, int D, int q);       /* 1/0 */
 
 int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu,
@@ -151,12 +172,16 @@ int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig,
  * sum x^2, number of observed entries.  With xcache_valid = 0 they are computed and stored there; with
  * xcache_valid = 1 (X unchanged since, i.e. mode B) the two passes over X are skipped and the cached local
  * sums are used.
+ * peers (nullable): with it, the second-stage kernel also performs the all-reduce(SUM) over the ranks -- it
+ * publishes the local sums in this rank's exchange buffer and adds the peers' buffers over NVLink in rank order,
+ * so `stats` holds the global statistics, bit-identical on every rank, when the call's kernels finish.
  * zsums / zsums_valid: the K2 partials of a pyvb_zstep_f64 / pyvb_zsolve_f64 call that covered exactly these
  * N rows (see there); with zsums_valid = 0 the sums over the MZ rows are recomputed here. */
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
                    const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
                    long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes,
-                   double *xcache, int xcache_valid, const double *zsums, int zsums_valid, int algo, void *stream);
+                   double *xcache, int xcache_valid, const double *zsums, int zsums_valid,
+                   const pyvb_peers *peers /* host, nullable */, int algo, void *stream);
 
 /* Gauss-Seidel update of W columns [col_lo, col_hi) from the (all-reduced) stats. */
 int pyvb_wupdate_f64(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,

@@ -20,6 +20,10 @@ class Consts(ctypes.Structure):
         "psi_alqa", "lgam_alqa", "lgam_ard_a0", "lndet_P0", "m0P0m0")] + [("ard", c_int), ("mode_a", c_int)]
 
 
+class Peers(ctypes.Structure):
+    _fields_ = [("bufs", ctypes.c_void_p), ("world", c_int), ("rank", c_int), ("epoch", ctypes.c_ulonglong)]
+
+
 SIGNATURES = {
     "pyvb_version": (c_int, []),
     "pyvb_last_error": (ctypes.c_char_p, []),
@@ -35,7 +39,13 @@ SIGNATURES = {
                                c_dp, c_ll, c_dp, c_ll, c_dp, c_dp, c_dp, c_int, c_dp]),
     "pyvb_zsolve_f64": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pyvb_stats_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_ll, c_dp, c_ll, c_dp,
-                               c_dp, c_dp, c_sz, c_dp, c_int, c_dp, c_int, c_int, c_dp]),
+                               c_dp, c_dp, c_sz, c_dp, c_int, c_dp, c_int, ctypes.POINTER(Peers), c_int, c_dp]),
+    "pyvb_peer_bytes": (c_sz, [c_sz]),
+    "pyvb_peer_alloc": (c_int, [c_sz, ctypes.POINTER(ctypes.c_void_p)]),
+    "pyvb_peer_free": (c_int, [c_dp]),
+    "pyvb_peer_export": (c_int, [c_dp, ctypes.c_char_p]),
+    "pyvb_peer_import": (c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "pyvb_peer_close": (c_int, [c_dp]),
     "pyvb_wupdate_f64": (c_int, [c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pyvb_global_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                 ctypes.POINTER(Consts), c_dp, c_dp]),

@@ -74,6 +74,40 @@ size_t pyvb_zsums_len(long long N, int q) {
     return (size_t)nblk * kw;
 }
 
+size_t pyvb_peer_bytes(size_t stats_len) { return peer_buffer_bytes(stats_len); }
+
+int pyvb_peer_alloc(size_t bytes, void **dptr) {
+    ARG(bytes > 0 && dptr, "bytes, dptr");
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*dptr, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "peer_alloc");
+}
+int pyvb_peer_free(void *dptr) {
+    cudaError_t e = cudaFree(dptr);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "peer_free");
+}
+int pyvb_peer_export(void *dptr, unsigned char *handle64) {
+    ARG(dptr && handle64, "null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, dptr);
+    if (e != cudaSuccess) return cuda_fail(e, "peer_export");
+    memcpy(handle64, &h, 64);
+    return PYVB_OK;
+}
+int pyvb_peer_import(const unsigned char *handle64, void **dptr) {
+    ARG(dptr && handle64, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "peer_import");
+}
+int pyvb_peer_close(void *dptr) {
+    cudaError_t e = cudaIpcCloseMemHandle(dptr);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "peer_close");
+}
+
 int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu, double *Gw, int ldg,
                      void *stream) {
     ARG(D >= 1 && q >= 1 && q <= PYVB_QMAX, "D, q");
@@ -122,12 +156,16 @@ int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig,
 int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, const double *V,
                    const double *Xorig, const double *qldX, const double *Zbar, long long ldz, const double *M2,
                    long long ldm, const double *logdet, double *stats, void *ws, size_t ws_bytes, double *xcache,
-                   int xcache_valid, const double *zsums, int zsums_valid, int algo, void *stream) {
+                   int xcache_valid, const double *zsums, int zsums_valid, const pyvb_peers *peers, int algo,
+                   void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
     ARG(X && Zbar && M2 && logdet && stats && ws, "null pointer");
     ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
     ARG((Xorig == NULL) || (V != NULL && qldX != NULL), "mode A needs V and qldX with Xorig");
     ARG(ws_bytes >= pyvb_stats_workspace_bytes(N, D, q, algo), "workspace too small");
+    ARG(peers == NULL || (peers->bufs != NULL && peers->world >= 1 && peers->rank >= 0 && peers->rank < peers->world &&
+                          peers->world <= 256 && peers->epoch >= 1),
+        "peers");
     const StatLayout L(D, q);
     const int a = pick_algo(algo, D, q);
     cudaStream_t st = (cudaStream_t)stream;
@@ -161,7 +199,8 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
         if (e != cudaSuccess) return cuda_fail(e, "rowscalars");
     }
     e = launch_stats_reduce(D, q, ws_main, nch, need_rows ? ws_sc : NULL, nblk, stats, xcache, use_x,
-                            nzblk > 0 ? zsums : NULL, nzblk, zkw, st);
+                            nzblk > 0 ? zsums : NULL, nzblk, zkw, peers ? peers->bufs : NULL, peers ? peers->world : 1,
+                            peers ? peers->rank : 0, peers ? peers->epoch : 0ULL, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
 }
 

@@ -31,7 +31,9 @@ cudaError_t launch_mzsums(long long N, int D, int q, const double *Zbar, long lo
                           long long ldm, double *ws_main, int nchunks, cudaStream_t st);
 cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
                                 double *stats, double *xcache, int use_xcache, const double *zsums, int nzblk,
-                                int zkw, cudaStream_t st);
+                                int zkw, void *const *peer_bufs, int world, int rank, unsigned long long epoch,
+                                cudaStream_t st);
+size_t peer_buffer_bytes(size_t len);
 cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
                            const double *gl, double *Wbar, double *Wvar, cudaStream_t st);
 cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,

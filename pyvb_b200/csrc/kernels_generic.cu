@@ -457,12 +457,43 @@ __device__ inline double strided_sum(const double *p, int n, size_t stride) {
     return (a0 + a1) + (a2 + a3);
 }
 
+// ---- peer exchange (multi-GPU, one process per GPU on one NVLink/NVSwitch box)
+// Every rank owns a cudaMalloc'd exchange buffer that all other ranks have opened through CUDA IPC:
+//   [ flags: uint64 [2][PYVB_PEER_MAXBLK] | slot 0: len doubles | slot 1: len doubles ]   (slots 256-byte aligned)
+// The second stage below writes the rank's reduced statistics into its own slot (parity = epoch & 1), publishes a
+// per-CTA flag (release, system scope), waits for the same CTA's flag on every peer (acquire over NVLink) and adds the
+// peers' slices in rank order: the reduction of the partial sums and the all-reduce are ONE kernel, the result is
+// bit-identical on every rank, and there is no host round trip.  Two slots suffice: a rank can only be one exchange
+// ahead of the slowest one (it needs everybody's flags of exchange t+1 before it starts t+2).
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__host__ __device__ inline size_t peer_slot_bytes(size_t len) { return (len * sizeof(double) + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t peer_flag_bytes() { return 2 * (size_t)PYVB_PEER_MAXBLK * sizeof(unsigned long long); }
+
 __global__ void __launch_bounds__(256)
 stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunks, const double *__restrict__ ws_sc,
                     int nblk, double *__restrict__ stats, double *xcache, int use_xcache,
-                    const double *__restrict__ zsums, int nzblk, int zkw) {
+                    const double *__restrict__ zsums, int nzblk, int zkw, void *const *peer_bufs, int world, int rank,
+                    unsigned long long epoch) {
     const StatLayout L(D, q);
     const int PP = gw_woff(q);
+    const bool xchg = (peer_bufs != nullptr) && world > 1;
+    const int par = (int)(epoch & 1ULL);
+    double *mine = stats;                                   // where the local sums go
+    if (xchg) mine = reinterpret_cast<double *>(static_cast<char *>(peer_bufs[rank]) + peer_flag_bytes() +
+                                                (size_t)par * peer_slot_bytes(L.len));
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < L.len; o += (size_t)gridDim.x * blockDim.x) {
         // slot of this entry in the X-only cache [cnt D | colx D | sxx | nE], or -1
         long long xc = -1;
@@ -488,18 +519,45 @@ stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunk
             else if (ws_sc != nullptr) acc = strided_sum(ws_sc + (o - L.scal), nblk, PYVB_NSCAL);
             if (xc >= 0 && xcache != nullptr) xcache[xc] = acc;
         }
+        mine[o] = acc;
+    }
+    if (!xchg) return;
+    // ---- publish this CTA's slice, wait for the same slice on every peer, add in rank order
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        unsigned long long *flags = static_cast<unsigned long long *>(peer_bufs[rank]);
+        st_release_sys(flags + (size_t)par * PYVB_PEER_MAXBLK + blockIdx.x, epoch);
+    }
+    if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
+        const unsigned long long *pf = static_cast<const unsigned long long *>(peer_bufs[threadIdx.x]) +
+                                       (size_t)par * PYVB_PEER_MAXBLK + blockIdx.x;
+        while (ld_acquire_sys(pf) < epoch) __nanosleep(64);
+    }
+    __syncthreads();
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < L.len; o += (size_t)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const double *src = reinterpret_cast<const double *>(static_cast<const char *>(peer_bufs[r]) +
+                                                                 peer_flag_bytes() + (size_t)par * peer_slot_bytes(L.len));
+            acc += (r == rank) ? src[o] : ld_relaxed_sys(src + o);
+        }
         stats[o] = acc;
     }
 }
 
+size_t peer_buffer_bytes(size_t len) { return peer_flag_bytes() + 2 * peer_slot_bytes(len); }
+
 cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks, const double *ws_sc, int nblk,
                                 double *stats, double *xcache, int use_xcache, const double *zsums, int nzblk,
-                                int zkw, cudaStream_t st) {
+                                int zkw, void *const *peer_bufs, int world, int rank, unsigned long long epoch,
+                                cudaStream_t st) {
     const StatLayout L(D, q);
     size_t b = (L.len + 255) / 256;
-    if (b > 148 * 8) b = 148 * 8;
+    // all CTAs must be co-resident when they wait for their peers: at most 2 per SM (and <= PYVB_PEER_MAXBLK)
+    if (b > 148 * 2) b = 148 * 2;
     stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats, xcache, use_xcache,
-                                                     zsums, nzblk, zkw);
+                                                     zsums, nzblk, zkw, peer_bufs, world, rank, epoch);
     return cudaGetLastError();
 }
 

@@ -23,7 +23,9 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .dist import allreduce_stats
+import os
+
+from .dist import PeerExchange, allreduce_stats
 from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_LEN, GL_NONPD, GL_QA,
                       GL_QB, GL_TAU, OP_ALPHA, OP_BETA, OP_ELBO, OP_MU, QMAX, StatLayout)
 
@@ -126,6 +128,13 @@ class PlateEngine(object):
         nz = int(self.lib.pyvb_zsums_len(N, q)) if self.lib.pyvb_algo_supported(ALGO_DMMA, D, q) else 0
         self.zsums = torch.zeros(nz, dtype=f64, device=dev) if nz > 0 and self.algo in (ALGO_AUTO, ALGO_DMMA) else None
         self._zsums_valid = False
+        # multi-GPU: the all-reduce happens inside the statistics kernel over NVLink peer memory
+        # (PYVB_COMM=nccl: plain torch.distributed all_reduce instead, for comparison)
+        self.peers = None
+        if self.distributed and os.environ.get("PYVB_COMM", "peer") == "peer":
+            import torch.distributed as dist
+            if dist.get_world_size() > 1 and dist.get_backend() == "nccl":
+                self.peers = PeerExchange(self.lib, self.L.len, dev)
         self.gl = torch.zeros(GL_LEN, dtype=f64, device=dev)
         self.trace = torch.zeros(int(trace_len), dtype=f64, device=dev)
         self.trace_pos = 0
@@ -152,6 +161,12 @@ class PlateEngine(object):
         self.set_state({"qb": 0.5, "al_qb": np.ones(q)})
         self._stats_fresh = False
         self._gw_fresh = False
+
+    def close(self):
+        """Release the peer exchange buffers (collective: every rank must call it)."""
+        if self.peers is not None:
+            self.peers.close()
+            self.peers = None
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -298,11 +313,12 @@ class PlateEngine(object):
                                      self.M2.data_ptr(), self.ldmz, self.logdet.data_ptr(), self.stats.data_ptr(),
                                      self.ws.data_ptr(), self.ws_bytes, self._p(self.xcache),
                                      int(self._xcache_valid), self._p(self.zsums), int(self._zsums_valid),
+                                     self.peers.next() if (self.peers is not None and self.distributed) else None,
                                      self.algo, self._stream())
         _cabi.check(rc, "pyvb_stats_f64")
         self._xcache_valid = self.xcache is not None
-        if self.distributed:
-            allreduce_stats(self.stats)          # the ONE collective of a sweep (NCCL over NVLink)
+        if self.distributed and self.peers is None:
+            allreduce_stats(self.stats)          # fallback exchange: NCCL all-reduce
         self._stats_fresh = True
 
     def update_W(self, col_lo=0, col_hi=None):

@@ -69,7 +69,7 @@ def test_fullsize_stats_additive_and_checksums(big):
         rc = lib.pyvb_stats_f64(hi - lo, e.D, e.q, e.X.data_ptr() + lo * e.D * 8, e.D, 0, 0, 0,
                                 e.Zbar.data_ptr() + lo * e.ldmz * 8, e.ldmz, e.M2.data_ptr() + lo * e.ldmz * 8, e.ldmz,
                                 e.logdet.data_ptr() + lo * 8, part.data_ptr(), e.ws.data_ptr(), e.ws_bytes,
-                                cache.data_ptr(), 0, 0, 0, e.algo, e._stream())
+                                cache.data_ptr(), 0, 0, 0, None, e.algo, e._stream())
         _cabi.check(rc, "stats")
         acc += part
     fin = torch.isfinite(full)
