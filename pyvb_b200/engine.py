@@ -420,6 +420,36 @@ class PlateEngine(object):
         self.trace_pos += 1
         return slot
 
+    def iterate_from_host(self, Xh, nchunks=8):
+        """One mode-B sweep whose data shard comes from (pinned) HOST memory: the upload is cut into row chunks on
+        a copy stream and the Z step of chunk c (K1 + K2) runs while chunk c+1 is still on the PCIe bus.  The W
+        update needs no data (it uses the statistics of the previous sweep), so it goes first; the statistics
+        pass needs all rows and goes last.  Returns the trace slot of the bound (no host synchronisation)."""
+        assert self.mode == "B"
+        N = self.N
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(cur)                      # the previous sweep has finished reading X
+        self.update_W()
+        self._ensure_gw()
+        self._xcache_valid = False
+        step = (N + nchunks - 1) // nchunks
+        step = (step + 63) // 64 * 64
+        for lo in range(0, N, step):
+            hi = min(N, lo + step)
+            with torch.cuda.stream(cs):
+                self.X[lo:hi].copy_(Xh[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            cur.wait_event(ev)
+            self.update_Z(lo, hi)
+        slot = self.trace_pos % self.trace.numel()
+        self._global(OP_MU | OP_ALPHA | OP_BETA | OP_ELBO, self.trace.data_ptr() + slot * 8)
+        self.trace_pos += 1
+        return slot
+
     def iterate(self):
         slot = self.iterate_async()
         return float(self.trace[slot].item())
