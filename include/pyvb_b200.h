@@ -199,6 +199,21 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
                     const double *mu, const double *Zbar, long long ldz, const double *gl,
                     double *Xhat, double *V, double *qldX, void *stream);
 
+/* ---- FP32 variant of the Z-step contraction (tcgen05 tensor cores, TMEM accumulators, TMA-staged bf16 x 3 splits) ----
+ * Same reference arithmetic as pyvb_zstep_f64's K1 (nodes/node.py:203-227).  q in {16, 32, 64}, D % 32 == 0.
+ *   planes  bf16 [3][N][D]    mask | x_h | x_m  (x = x_h + x_m to 16 bits; zeros where not observed); static over sweeps
+ *   GT      bf16 [3][NCP][D]  three-way split of [G_d packed | pad | -mu_d <w_d> | pad]^T,  NCP = pyvb_f32_pitch(q)
+ *   WT      bf16 [3][q][D]    three-way split of <W>^T
+ *   MZ32    float [N][NCP]    out: [qprec packed (P) | pad | eta (q) at column pyvb_f32_zoff(q) | pad] */
+int pyvb_f32_pitch(int q);
+int pyvb_f32_zoff(int q);
+int pyvb_f32_supported(int D, int q);
+int pyvb_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, void *stream);
+int pyvb_pack_gw_f32(int D, int q, const double *Wbar, const double *Wvar, const double *mu, void *GT, void *WT,
+                     void *stream);
+int pyvb_zstep_k1_f32(long long N, int D, int q, const void *planes, const void *GT, const void *WT, const double *P0,
+                      const double *h0, const double *gl, float *MZ32, void *stream);
+
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
  * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.
  * bench.py times it with CUDA events to obtain the FP64 tensor roofline of the box it runs on. */

@@ -235,6 +235,32 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "impute");
 }
 
+int pyvb_f32_pitch(int q) { return f32_ncp(q); }
+int pyvb_f32_zoff(int q) { return f32_zoff(q); }
+int pyvb_f32_supported(int D, int q) { return f32_supported(D, q) ? 1 : 0; }
+
+int pyvb_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, void *stream) {
+    ARG(N >= 0 && D >= 1 && X && planes && ldx >= D, "N, D, X, planes, ldx");
+    cudaError_t e = launch_prepare_x_f32(N, D, X, ldx, planes, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "prepare_x_f32");
+}
+
+int pyvb_pack_gw_f32(int D, int q, const double *Wbar, const double *Wvar, const double *mu, void *GT, void *WT,
+                     void *stream) {
+    ARG(f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
+    ARG(Wbar && Wvar && mu && GT && WT, "null pointer");
+    cudaError_t e = launch_pack_gw_f32(D, q, Wbar, Wvar, mu, GT, WT, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "pack_gw_f32");
+}
+
+int pyvb_zstep_k1_f32(long long N, int D, int q, const void *planes, const void *GT, const void *WT, const double *P0,
+                      const double *h0, const double *gl, float *MZ32, void *stream) {
+    ARG(N >= 0 && f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
+    ARG(planes && GT && WT && P0 && h0 && gl && MZ32, "null pointer");
+    cudaError_t e = launch_zstep_f32(N, D, q, planes, GT, WT, P0, h0, gl, MZ32, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_k1_f32");
+}
+
 int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch, void *stream) {
     ARG(blocks >= 1 && iters >= 1 && scratch, "blocks, iters, scratch");
     cudaError_t e = launch_bench_dmma(blocks, iters, scratch, (cudaStream_t)stream);

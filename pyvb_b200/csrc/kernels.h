@@ -61,6 +61,16 @@ int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                               double *ws_main, int nchunks, cudaStream_t st);
 
+// ---- FP32 variant: tcgen05 / TMEM contraction on bf16 x 3 splits (kernels_f32.cu) ----
+int f32_ncp(int q);                 // floats per MZ32 row
+int f32_zoff(int q);                // first eta / zbar column of an MZ32 row
+bool f32_supported(int D, int q);
+cudaError_t launch_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, cudaStream_t st);
+cudaError_t launch_pack_gw_f32(int D, int q, const double *Wbar, const double *Wvar, const double *mu, void *GT, void *WT,
+                               cudaStream_t st);
+cudaError_t launch_zstep_f32(long long N, int D, int q, const void *planes, const void *GT, const void *WT,
+                             const double *P0, const double *h0, const double *gl, float *MZ, cudaStream_t st);
+
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
 
 }  // namespace pyvb
