@@ -100,6 +100,7 @@ extern "C" {
 #define PYVB_ALGO_AUTO 0
 #define PYVB_ALGO_GENERIC 1  /* any D, q <= 64; FP64 FMA */
 #define PYVB_ALGO_DMMA 2     /* FP64 tensor-core (DMMA) + TMA staging; q in {8,16,32}, D % 16 == 0 */
+#define PYVB_ALGO_F32 4      /* FP32 variant (tcgen05): only for pyvb_stats_workspace_bytes */
 #define PYVB_ALGO_DMMA_K1 3  /* measurement only (zstep): the tensor-core contraction alone; the MZ rows are
                                 left as [qprec packed | eta] for pyvb_zsolve_f64 */
 
@@ -202,17 +203,36 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
 /* ---- FP32 variant of the Z-step contraction (tcgen05 tensor cores, TMEM accumulators, TMA-staged bf16 x 3 splits) ----
  * Same reference arithmetic as pyvb_zstep_f64's K1 (nodes/node.py:203-227).  q in {16, 32, 64}, D % 32 == 0.
  *   planes  bf16 [3][N][D]    mask | x_h | x_m  (x = x_h + x_m to 16 bits; zeros where not observed); static over sweeps
- *   GT      bf16 [3][NCP][D]  three-way split of [G_d packed | pad | -mu_d <w_d> | pad]^T,  NCP = pyvb_f32_pitch(q)
+ *   GT      bf16 [3][NCP][D]  three-way split of [-mu_d <w_d> (q) | G_d packed (P) | pad]^T,  NCP = pyvb_f32_pitch(q)
  *   WT      bf16 [3][q][D]    three-way split of <W>^T
- *   MZ32    float [N][NCP]    out: [qprec packed (P) | pad | eta (q) at column pyvb_f32_zoff(q) | pad] */
+ *   MZ32    float [N][NCP]    out: [eta (q) | qprec packed (P) | pad]: the FP32 rows keep zbar / eta FIRST
+ *                             (pyvb_f32_zoff(q) = 0, packed part at pyvb_f32_poff(q) = q) */
 int pyvb_f32_pitch(int q);
 int pyvb_f32_zoff(int q);
+int pyvb_f32_poff(int q);
 int pyvb_f32_supported(int D, int q);
+size_t pyvb_zsums_len_f32(long long N, int q);        /* K2 partials of the FP32 path (always the blocked kernel) */
 int pyvb_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, void *stream);
 int pyvb_pack_gw_f32(int D, int q, const double *Wbar, const double *Wvar, const double *mu, void *GT, void *WT,
                      void *stream);
 int pyvb_zstep_k1_f32(long long N, int D, int q, const void *planes, const void *GT, const void *WT, const double *P0,
                       const double *h0, const double *gl, float *MZ32, void *stream);
+
+/* FP32 Z step for rows [0,N) of arrays whose planes hold `nalloc` rows each (pointers already offset to the first
+ * row): the tcgen05 contraction, then the batched solve IN PLACE on the FP32 rows (FP64 arithmetic inside the solve:
+ * the q x q systems have condition numbers ~1e4): MZ32 rows become [zbar | <zz^T> packed | 0], MP bf16 [3][nalloc][NCP]
+ * receives their three-way bf16 split (the B operand of pyvb_stats_f32).  Sig (double [N][P]) may be NULL; zsums as
+ * in pyvb_zstep_f64. */
+int pyvb_zstep_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *GT, const void *WT,
+                   const double *P0, const double *h0, double *gl, float *MZ32, void *MP, double *Sig, double *logdet,
+                   double *zsums, void *stream);
+
+/* FP32 statistics: T1, Bst, Ast partial sums on the tensor cores (MN-major bf16 tiles, FP32 accumulation per row
+ * chunk, FP64 across chunks), then the shared fixed-order second stage (+ the peer exchange).  The sums that depend
+ * on X alone (xcache) and K2's column sums (zsums) must be valid: the FP32 path has no other source for them. */
+int pyvb_stats_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *MP, double *stats,
+                   void *ws, size_t ws_bytes, double *xcache, const double *zsums, const pyvb_peers *peers /* host */,
+                   void *stream);
 
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
  * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.

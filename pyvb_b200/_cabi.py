@@ -42,10 +42,14 @@ SIGNATURES = {
                                c_dp, c_dp, c_sz, c_dp, c_int, c_dp, c_int, ctypes.POINTER(Peers), c_int, c_dp]),
     "pyvb_f32_pitch": (c_int, [c_int]),
     "pyvb_f32_zoff": (c_int, [c_int]),
+    "pyvb_f32_poff": (c_int, [c_int]),
     "pyvb_f32_supported": (c_int, [c_int, c_int]),
     "pyvb_prepare_x_f32": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp]),
     "pyvb_pack_gw_f32": (c_int, [c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "pyvb_zstep_k1_f32": (c_int, [c_ll, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "pyvb_zsums_len_f32": (c_sz, [c_ll, c_int]),
+    "pyvb_zstep_f32": (c_int, [c_ll, c_ll, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    "pyvb_stats_f32": (c_int, [c_ll, c_ll, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_sz, c_dp, c_dp, ctypes.POINTER(Peers), c_dp]),
     "pyvb_peer_bytes": (c_sz, [c_sz]),
     "pyvb_peer_alloc": (c_int, [c_sz, ctypes.POINTER(ctypes.c_void_p)]),
     "pyvb_peer_free": (c_int, [c_dp]),

@@ -11,7 +11,7 @@ GL_ALQB = 80
 GL_LEN = 144
 
 OP_MU, OP_BETA, OP_ALPHA, OP_ELBO = 1, 2, 4, 8
-ALGO_AUTO, ALGO_GENERIC, ALGO_DMMA, ALGO_DMMA_K1 = 0, 1, 2, 3
+ALGO_AUTO, ALGO_GENERIC, ALGO_DMMA, ALGO_DMMA_K1, ALGO_F32 = 0, 1, 2, 3, 4
 QMAX = 64
 
 

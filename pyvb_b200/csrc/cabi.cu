@@ -59,6 +59,7 @@ int pyvb_algo_supported(int algo, int D, int q) {
 
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo) {
     const StatLayout L(D, q);
+    if (algo == PYVB_ALGO_F32) return align256((size_t)stats_f32_nchunks(N, D, q) * L.len * sizeof(double));
     int nch = stats_generic_nchunks(N);
     if (pick_algo(algo, D, q) == PYVB_ALGO_DMMA) {
         const int n2 = stats_dmma_nchunks(N, D, q);
@@ -66,6 +67,12 @@ size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo) {
     }
     return align256((size_t)nch * L.len * sizeof(double)) +
            align256((size_t)rowscalars_nblk(N) * PYVB_NSCAL * sizeof(double));
+}
+
+size_t pyvb_zsums_len_f32(long long N, int q) {
+    int nblk, kw;
+    zsolve_partials_f32(N, q, nblk, kw);
+    return (size_t)nblk * kw;
 }
 
 size_t pyvb_zsums_len(long long N, int q) {
@@ -237,6 +244,7 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
 
 int pyvb_f32_pitch(int q) { return f32_ncp(q); }
 int pyvb_f32_zoff(int q) { return f32_zoff(q); }
+int pyvb_f32_poff(int q) { return f32_poff(q); }
 int pyvb_f32_supported(int D, int q) { return f32_supported(D, q) ? 1 : 0; }
 
 int pyvb_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, void *stream) {
@@ -257,8 +265,40 @@ int pyvb_zstep_k1_f32(long long N, int D, int q, const void *planes, const void 
                       const double *h0, const double *gl, float *MZ32, void *stream) {
     ARG(N >= 0 && f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
     ARG(planes && GT && WT && P0 && h0 && gl && MZ32, "null pointer");
-    cudaError_t e = launch_zstep_f32(N, D, q, planes, GT, WT, P0, h0, gl, MZ32, (cudaStream_t)stream);
+    cudaError_t e = launch_zstep_f32(N, N, D, q, planes, GT, WT, P0, h0, gl, MZ32, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_k1_f32");
+}
+
+int pyvb_zstep_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *GT, const void *WT,
+                   const double *P0, const double *h0, double *gl, float *MZ32, void *MP, double *Sig, double *logdet,
+                   double *zsums, void *stream) {
+    ARG(N >= 0 && nalloc >= N && f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
+    ARG(planes && GT && WT && P0 && h0 && gl && MZ32 && MP && logdet, "null pointer");
+    cudaError_t e = launch_zstep_f32(N, nalloc, D, q, planes, GT, WT, P0, h0, gl, MZ32, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = launch_zsolve_f32(N, q, MZ32, MP, Sig, logdet, gl, zsums, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_f32");
+}
+
+int pyvb_stats_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *MP, double *stats,
+                   void *ws, size_t ws_bytes, double *xcache, const double *zsums, const pyvb_peers *peers,
+                   void *stream) {
+    ARG(N >= 0 && nalloc >= N && f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
+    ARG(planes && MP && stats && ws && xcache && zsums, "null pointer (xcache and zsums are required)");
+    ARG(ws_bytes >= pyvb_stats_workspace_bytes(N, D, q, PYVB_ALGO_F32), "workspace too small");
+    ARG(peers == NULL || (peers->bufs != NULL && peers->world >= 1 && peers->rank >= 0 && peers->rank < peers->world &&
+                          peers->world <= 256 && peers->epoch >= 1),
+        "peers");
+    int nzblk = 0, zkw = 0;
+    zsolve_partials_f32(N, q, nzblk, zkw);
+    ARG(nzblk > 0, "no K2 column sums for this q in the FP32 path");
+    const int nch = stats_f32_nchunks(N, D, q);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_stats_f32(N, nalloc, D, q, planes, MP, (double *)ws, nch, st);
+    if (e != cudaSuccess) return cuda_fail(e, "stats_f32");
+    e = launch_stats_reduce(D, q, (const double *)ws, nch, NULL, 0, stats, xcache, 1, zsums, nzblk, zkw,
+                            peers ? peers->bufs : NULL, peers ? peers->world : 1, peers ? peers->rank : 0,
+                            peers ? peers->epoch : 0ULL, st);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
 }
 
 int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch, void *stream) {

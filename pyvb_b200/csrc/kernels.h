@@ -57,19 +57,29 @@ int zsolve_blocked_blocks(long long N, int q);
 int zsolve_blocked_kw(int q);
 cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl,
                                   double *zsums, cudaStream_t st);
+cudaError_t launch_zsolve_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
+                              double *zsums, cudaStream_t st);
 int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                               double *ws_main, int nchunks, cudaStream_t st);
 
 // ---- FP32 variant: tcgen05 / TMEM contraction on bf16 x 3 splits (kernels_f32.cu) ----
 int f32_ncp(int q);                 // floats per MZ32 row
-int f32_zoff(int q);                // first eta / zbar column of an MZ32 row
+int f32_zoff(int q);                // first eta / zbar column of an MZ32 row (0)
+int f32_poff(int q);                // first packed column (q)
 bool f32_supported(int D, int q);
 cudaError_t launch_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, cudaStream_t st);
 cudaError_t launch_pack_gw_f32(int D, int q, const double *Wbar, const double *Wvar, const double *mu, void *GT, void *WT,
                                cudaStream_t st);
-cudaError_t launch_zstep_f32(long long N, int D, int q, const void *planes, const void *GT, const void *WT,
-                             const double *P0, const double *h0, const double *gl, float *MZ, cudaStream_t st);
+// nalloc: rows per plane in the planes / MP allocations (N <= nalloc: row sub-ranges keep the plane stride)
+cudaError_t launch_zstep_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *GT,
+                             const void *WT, const double *P0, const double *h0, const double *gl, float *MZ,
+                             cudaStream_t st);
+
+int stats_f32_nchunks(long long N, int D, int q);
+void zsolve_partials_f32(long long N, int q, int &nblk, int &kw);
+cudaError_t launch_stats_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *MP, double *ws,
+                             int nchunks, cudaStream_t st);
 
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
 

@@ -10,7 +10,8 @@
 // * x is kept as two bf16 planes (16-bit mantissa), W as three; products x_h W_{h,m,l} + x_m W_{h,m}
 // Data (static over the sweeps, prepared once):  planes bf16 [3][N][D] = mask | x_h | x_m  (0 where missing)
 // Per sweep (tiny):                               GT bf16 [3][NCP][D] (K-major B operand), WT bf16 [3][q][D]
-// Output: MZ32 float [N][NCP] rows [qprec packed (P) | pad | eta (q) | pad], NCP = (PP + q) rounded up to 64.
+// Output: MZ32 float [N][NCP] rows [eta (q) | qprec packed (P) | pad], NCP = (q + P) rounded up to 64.  (eta / zbar
+// come FIRST in the FP32 row: the statistics kernel then finds zbar in the first 64-column atom of its B tiles.)
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -24,8 +25,7 @@ namespace pyvb {
 namespace {
 
 __host__ __device__ constexpr int f_tri(int i) { return i * (i + 1) / 2; }
-__host__ __device__ constexpr int f_pp(int q) { return (f_tri(q) + 15) & ~15; }   // first eta / zbar column
-__host__ __device__ constexpr int f_ncp(int q) { return (f_pp(q) + q + 63) & ~63; }
+__host__ __device__ constexpr int f_ncp(int q) { return (q + f_tri(q) + 63) & ~63; }   // floats per FP32 row
 
 // ------------------------------------------------------------------ operand preparation
 __device__ __forceinline__ void split3(double v, __nv_bfloat16 &h, __nv_bfloat16 &m, __nv_bfloat16 &l) {
@@ -54,12 +54,12 @@ prepare_x_kernel(long long N, int D, const double *__restrict__ X, long long ldx
     }
 }
 
-// GT[p][c][d]: column c of the accumulator row ([G_d packed | pad | -mu_d w_d | pad]) for data dimension d, plane p;
+// GT[p][c][d]: column c of the accumulator row ([-mu_d w_d (q) | G_d packed (P) | pad]) for data dimension d, plane p;
 // WT[p][i][d] = plane p of <w_di>.  One thread per (c, d), d fastest (coalesced writes).
 __global__ void __launch_bounds__(256)
 pack_gw_f32_kernel(int D, int q, const double *__restrict__ Wbar, const double *__restrict__ Wvar,
                    const double *__restrict__ mu, __nv_bfloat16 *__restrict__ GT, __nv_bfloat16 *__restrict__ WT) {
-    const int P = f_tri(q), PP = f_pp(q), NCP = f_ncp(q);
+    const int P = f_tri(q), NCP = f_ncp(q);
     const long long total = (long long)(NCP + q) * D;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(e / D), d = (int)(e % D);
@@ -67,13 +67,13 @@ pack_gw_f32_kernel(int D, int q, const double *__restrict__ Wbar, const double *
         __nv_bfloat16 *dst;
         size_t plane;
         if (c < NCP) {
-            if (c < P) {
+            if (c < q) {
+                v = -mu[d] * Wbar[(size_t)d * q + c];
+            } else if (c < q + P) {
                 int i, j;
-                unpack_p(c, i, j);
+                unpack_p(c - q, i, j);
                 v = Wbar[(size_t)d * q + i] * Wbar[(size_t)d * q + j];
                 if (i == j) v += Wvar[(size_t)d * q + i];
-            } else if (c >= PP && c < PP + q) {
-                v = -mu[d] * Wbar[(size_t)d * q + (c - PP)];
             }
             dst = GT + (size_t)c * D + d;
             plane = (size_t)NCP * D;
@@ -105,12 +105,13 @@ EncodeTiledFn get_encode_f32() {
     }
     return fn;
 }
-cudaError_t make_map_bf16_3d(CUtensorMap *m, const void *base, uint64_t cols, uint64_t rows, uint64_t planes,
-                             uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
+// rows_alloc: rows per plane in the allocation (>= rows: a row sub-range of a bigger array keeps its plane stride)
+cudaError_t make_map_bf16_3d(CUtensorMap *m, const void *base, uint64_t cols, uint64_t rows, uint64_t rows_alloc,
+                             uint64_t planes, uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc = get_encode_f32();
     if (!enc) return cudaErrorNotSupported;
     cuuint64_t dims[3] = {cols, rows, planes};
-    cuuint64_t strides[2] = {cols * 2, cols * rows * 2};
+    cuuint64_t strides[2] = {cols * 2, cols * rows_alloc * 2};
     cuuint32_t box[3] = {box_cols, box_rows, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, es,
@@ -134,10 +135,10 @@ template <> struct FC<32> { static constexpr int NT = 192, ST = 3; };
 template <> struct FC<64> { static constexpr int NT = 256, ST = 2; };
 
 template <int Q> struct FT {
-    static constexpr int P = f_tri(Q), PP = f_pp(Q), NCP = f_ncp(Q);
+    static constexpr int P = f_tri(Q), NCP = f_ncp(Q);
     static constexpr int NT = FC<Q>::NT, ST = FC<Q>::ST;
     static constexpr int NCT = (NCP + NT - 1) / NT;          // column tiles
-    static constexpr int ECT = PP / NT;                      // the column tile that holds the eta columns
+    static constexpr int ECT = 0;                            // the column tile that holds the eta columns [0, q)
     static constexpr int BM = 128, BK = 32;                  // rows per tile, K elements per stage (64-byte rows)
     static constexpr int A_B = BM * BK * 2;                  // one A plane tile (bytes)
     static constexpr int G_B = NT * BK * 2;                  // one G plane tile
@@ -145,7 +146,6 @@ template <int Q> struct FT {
     static constexpr int STAGE_B = 3 * A_B + 3 * G_B + 3 * W_B;
     static constexpr int NTHR = 6 * 32;                      // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
     static constexpr size_t SMEM = 1024 + (size_t)ST * STAGE_B + (size_t)(P + Q) * 4 + (2 * ST + 4) * 8 + 16;
-    static_assert((PP + Q - 1) / NT == ECT, "the eta columns must not straddle two column tiles");
     static_assert(A_B % 512 == 0 && G_B % 512 == 0 && W_B % 512 == 0, "SWIZZLE_64B tiles must stay 512-byte aligned");
 };
 
@@ -232,7 +232,7 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));
                 umma::fence_after_sync();
                 const uint32_t dacc = tmem + (uint32_t)(buf * 256);
-                const uint32_t deta = dacc + (uint32_t)(T::PP - T::ECT * T::NT);
+                const uint32_t deta = dacc;                     // eta = the first q accumulator columns
                 const uint32_t id_g = umma::idesc_bf16_f32(T::BM, nt, 0, 0);
                 const uint32_t id_w = umma::idesc_bf16_f32(T::BM, Q, 0, 0);
                 for (int kb = 0; kb < nk; ++kb, ++it) {
@@ -287,7 +287,7 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int j = 0; j < 16; ++j) {
                         const int c = c0 + cc + j;
                         const float a = __uint_as_float(v[j]);
-                        o[j] = (c < T::P) ? fmaf(tau, a, p0v[c]) : (c >= T::PP && c < T::PP + Q) ? fmaf(tau, a, h0s[c - T::PP]) : 0.0f;
+                        o[j] = (c < Q) ? fmaf(tau, a, h0s[c]) : (c < Q + T::P) ? fmaf(tau, a, p0v[c - Q]) : 0.0f;
                     }
 #pragma unroll
                     for (int j = 0; j < 16; j += 4)
@@ -306,15 +306,16 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int Q>
-cudaError_t launch_zstep_f32_q(long long N, int D, const void *planes, const void *GT, const void *WT, const double *P0,
-                               const double *h0, const double *gl, float *MZ, cudaStream_t st) {
+cudaError_t launch_zstep_f32_q(long long N, long long nalloc, int D, const void *planes, const void *GT, const void *WT,
+                               const double *P0, const double *h0, const double *gl, float *MZ, cudaStream_t st) {
     using T = FT<Q>;
     CUtensorMap tmA, tmG, tmW;
-    cudaError_t e = make_map_bf16_3d(&tmA, planes, (uint64_t)D, (uint64_t)N, 3, T::BK, T::BM, CU_TENSOR_MAP_SWIZZLE_64B);
+    cudaError_t e = make_map_bf16_3d(&tmA, planes, (uint64_t)D, (uint64_t)N, (uint64_t)nalloc, 3, T::BK, T::BM,
+                                     CU_TENSOR_MAP_SWIZZLE_64B);
     if (e != cudaSuccess) return e;
-    e = make_map_bf16_3d(&tmG, GT, (uint64_t)D, (uint64_t)T::NCP, 3, T::BK, T::NT, CU_TENSOR_MAP_SWIZZLE_64B);
+    e = make_map_bf16_3d(&tmG, GT, (uint64_t)D, (uint64_t)T::NCP, (uint64_t)T::NCP, 3, T::BK, T::NT, CU_TENSOR_MAP_SWIZZLE_64B);
     if (e != cudaSuccess) return e;
-    e = make_map_bf16_3d(&tmW, WT, (uint64_t)D, (uint64_t)Q, 3, T::BK, Q, CU_TENSOR_MAP_SWIZZLE_64B);
+    e = make_map_bf16_3d(&tmW, WT, (uint64_t)D, (uint64_t)Q, (uint64_t)Q, 3, T::BK, Q, CU_TENSOR_MAP_SWIZZLE_64B);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(zstep_f32_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
@@ -324,10 +325,216 @@ cudaError_t launch_zstep_f32_q(long long N, int D, const void *planes, const voi
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ K3, FP32 variant: statistics GEMM
+// T[d][c] = sum_n A[n][d] B[n][c] over a chunk of rows: hstack.pass_up_m1_m2's sums over the rows
+// (nodes/nodes_todo.py:50-61).  A = mask (O-type: T1 = O^T vec<zz^T>, Bst = O^T zbar) or x_h + x_m (X-type:
+// Ast = (O.X)^T zbar); B = the three-way bf16 split of the finished FP32 rows [zbar | <zz^T> packed] (planes MP
+// written by the batched solve).  Both operands sit in memory with the contraction index (the row n) OUTERMOST, so
+// they are fed to tcgen05.mma as MN-major tiles: TMA boxes of [rows][64 elements] with SWIZZLE_128B are exactly
+// the canonical MN-major atoms, no transposition anywhere.  Accumulators: 128 d (TMEM lanes) x NT columns + 64
+// columns for the X-type product (zbar = the first q columns of the first 64-column atom).  Partial sums per row
+// chunk leave as FP64 into the same workspace layout as the FP64 path; the fixed-order second stage is shared.
+template <int Q> struct SFC;
+template <> struct SFC<16> { static constexpr int NT = 192, ST = 3; };
+template <> struct SFC<32> { static constexpr int NT = 192, ST = 3; };
+template <> struct SFC<64> { static constexpr int NT = 256, ST = 3; };
+
+template <int Q> struct SFT {
+    static constexpr int P = f_tri(Q), NCP = f_ncp(Q);
+    static constexpr int NT = SFC<Q>::NT, ST = SFC<Q>::ST;
+    static constexpr int NCT = (NCP + NT - 1) / NT;
+    static constexpr int BD = 128, BKN = 32;                  // data dimensions per tile, rows per stage
+    static constexpr int BLK_B = BKN * 128;                   // one [BKN rows][64 elements] box (bytes)
+    static constexpr int A_B = 2 * BLK_B;                     // one A plane tile: 128 d
+    static constexpr int B_B = (NT / 64) * BLK_B;             // one B plane tile: NT columns
+    static constexpr int STAGE_B = 3 * A_B + 3 * B_B;
+    static constexpr int NTHR = 6 * 32;
+    static constexpr int TCOLS = (NT + 64 <= 256) ? 256 : 512;
+    static constexpr size_t SMEM = 1024 + (size_t)ST * STAGE_B + (2 * ST + 2) * 8 + 16;
+    static_assert(NT % 64 == 0 && BLK_B % 1024 == 0, "MN-major SWIZZLE_128B atoms");
+};
+
+template <int Q>
+__global__ void __launch_bounds__(SFT<Q>::NTHR, 1)
+stats_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long N, int D,
+                 double *__restrict__ ws, long long rows_per_chunk) {
+    using T = SFT<Q>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char *stage0 = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + T::ST * T::STAGE_B);
+    uint64_t *empty = full + T::ST;
+    uint64_t *tfull = empty + T::ST;
+    uint32_t *tbase = reinterpret_cast<uint32_t *>(tfull + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ct = (int)(blockIdx.x % T::NCT);
+    const int d0 = (int)(blockIdx.x / T::NCT) * T::BD;
+    const int c0 = ct * T::NT;
+    const int nt = (T::NCP - c0 < T::NT) ? (T::NCP - c0) : T::NT;
+    const bool xt = (ct == 0);                                // this tile also carries the X-type product
+    const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+    long long r1 = r0 + rows_per_chunk;
+    if (r1 > N) r1 = N;
+    const int nsteps = (r1 > r0) ? (int)((r1 - r0 + T::BKN - 1) / T::BKN) : 0;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < T::ST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&tfull[0], 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tbase, T::TCOLS);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tbase;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % T::ST;
+                umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / T::ST) & 1) ^ 1));
+                unsigned char *st = stage0 + s * T::STAGE_B;
+                const int nb = (int)(r0 + (long long)it * T::BKN);       // rows >= N are zero-filled by the copies
+                mbar_arrive_expect_tx(&full[s], (uint32_t)((xt ? 3 : 1) * T::A_B + 3 * (nt / 64) * T::BLK_B));
+                for (int p = 0; p < (xt ? 3 : 1); ++p)
+                    for (int j = 0; j < 2; ++j)
+                        tma_load_3d(st + p * T::A_B + j * T::BLK_B, &tmA, d0 + j * 64, nb, p, &full[s]);
+                for (int p = 0; p < 3; ++p)
+                    for (int j = 0; j < nt / 64; ++j)
+                        tma_load_3d(st + 3 * T::A_B + p * T::B_B + j * T::BLK_B, &tmB, c0 + j * 64, nb, p, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t id_t = umma::idesc_bf16_f32(T::BD, nt, 1, 1);
+            const uint32_t id_x = umma::idesc_bf16_f32(T::BD, 64, 1, 1);
+            const uint32_t dT = tmem, dX = tmem + (uint32_t)T::NT;
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it % T::ST;
+                umma::mbar_wait_bounded(&full[s], (uint32_t)((it / T::ST) & 1));
+                umma::fence_after_sync();
+                const uint32_t a0 = smem_u32(stage0 + s * T::STAGE_B);
+                const uint32_t b0 = a0 + 3 * T::A_B;
+#pragma unroll
+                for (int ks = 0; ks < T::BKN / 16; ++ks) {
+                    const uint64_t am = umma::desc_mnmajor_sw128(a0, ks, T::BLK_B);
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+                        umma::mma_bf16(dT, am, umma::desc_mnmajor_sw128(b0 + p * T::B_B, ks, T::BLK_B), id_t,
+                                       (it | ks | p) ? 1u : 0u);
+                    if (xt) {
+                        const uint64_t xh = umma::desc_mnmajor_sw128(a0 + T::A_B, ks, T::BLK_B);
+                        const uint64_t xm = umma::desc_mnmajor_sw128(a0 + 2 * T::A_B, ks, T::BLK_B);
+                        const uint64_t zh = umma::desc_mnmajor_sw128(b0, ks, T::BLK_B);
+                        const uint64_t zm = umma::desc_mnmajor_sw128(b0 + T::B_B, ks, T::BLK_B);
+                        const uint64_t zl = umma::desc_mnmajor_sw128(b0 + 2 * T::B_B, ks, T::BLK_B);
+                        umma::mma_bf16(dX, xh, zh, id_x, (it | ks) ? 1u : 0u);
+                        umma::mma_bf16(dX, xh, zm, id_x, 1u);
+                        umma::mma_bf16(dX, xm, zh, id_x, 1u);
+                        umma::mma_bf16(dX, xh, zl, id_x, 1u);
+                        umma::mma_bf16(dX, xm, zm, id_x, 1u);
+                    }
+                }
+                umma::mma_commit(&empty[s]);
+            }
+            umma::mma_commit(&tfull[0]);
+        }
+    } else {
+        // ===================== epilogue: lane = data dimension d, columns -> T1 / Bst / Ast partials (FP64) ==========
+        const int wq = warp & 3;
+        const int d = d0 + wq * 32 + lane;
+        const StatLayout L(D, Q);
+        double *out = ws + (size_t)blockIdx.y * L.len;
+        const bool live = nsteps > 0;                          // an empty chunk contributes zeros
+        if (live) umma::mbar_wait_bounded(&tfull[0], 0u);
+        umma::fence_after_sync();
+        const uint32_t taddr = tmem + ((uint32_t)(wq * 32) << 16);
+        for (int cc = 0; cc < nt; cc += 16) {
+            uint32_t v[16];
+            umma::tmem_ld16(taddr + (uint32_t)cc, v);
+            umma::tmem_ld_wait();
+            if (d < D) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + cc + j;
+                    const double a = live ? (double)__uint_as_float(v[j]) : 0.0;
+                    if (c < Q) out[L.bst + (size_t)d * Q + c] = a;
+                    else if (c < Q + T::P) out[L.t1 + (size_t)d * T::P + (c - Q)] = a;
+                }
+            }
+        }
+        if (xt) {
+            for (int cc = 0; cc < Q; cc += 16) {
+                uint32_t v[16];
+                umma::tmem_ld16(taddr + (uint32_t)(T::NT + cc), v);
+                umma::tmem_ld_wait();
+                if (d < D) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        out[L.ast + (size_t)d * Q + cc + j] = live ? (double)__uint_as_float(v[j]) : 0.0;
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, T::TCOLS);
+}
+
+template <int Q>
+cudaError_t launch_stats_f32_q(long long N, long long nalloc, int D, const void *planes, const void *MP, double *ws,
+                               int nchunks, cudaStream_t st) {
+    using T = SFT<Q>;
+    CUtensorMap tmA, tmB;
+    cudaError_t e = make_map_bf16_3d(&tmA, planes, (uint64_t)D, (uint64_t)N, (uint64_t)nalloc, 3, 64, T::BKN,
+                                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e != cudaSuccess) return e;
+    e = make_map_bf16_3d(&tmB, MP, (uint64_t)T::NCP, (uint64_t)N, (uint64_t)nalloc, 3, 64, T::BKN, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(stats_f32_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    if (e != cudaSuccess) return e;
+    long long rpc = (N + nchunks - 1) / nchunks;
+    rpc = ((rpc + T::BKN - 1) / T::BKN) * T::BKN;
+    if (rpc < T::BKN) rpc = T::BKN;
+    dim3 grid((unsigned)(((D + T::BD - 1) / T::BD) * T::NCT), (unsigned)nchunks);
+    stats_f32_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(tmA, tmB, N, D, ws, rpc);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
+// row chunks of the FP32 statistics kernel: ~2 waves of CTAs, at least 64 pipeline steps (2048 rows) per chunk
+int stats_f32_nchunks(long long N, int D, int q) {
+    const int nct = (f_ncp(q) + (q == 64 ? 256 : 192) - 1) / (q == 64 ? 256 : 192);
+    const long long per = (long long)((D + 127) / 128) * nct;
+    long long c = (2 * 148 + per - 1) / per;
+    const long long by_rows = (N + 2047) / 2048;
+    if (c > by_rows) c = by_rows;
+    if (c < 1) c = 1;
+    if (c > 1024) c = 1024;
+    return (int)c;
+}
+
+cudaError_t launch_stats_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *MP, double *ws,
+                             int nchunks, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    switch (q) {
+        case 16: return launch_stats_f32_q<16>(N, nalloc, D, planes, MP, ws, nchunks, st);
+        case 32: return launch_stats_f32_q<32>(N, nalloc, D, planes, MP, ws, nchunks, st);
+        case 64: return launch_stats_f32_q<64>(N, nalloc, D, planes, MP, ws, nchunks, st);
+    }
+    return cudaErrorNotSupported;
+}
+
 int f32_ncp(int q) { return f_ncp(q); }
-int f32_zoff(int q) { return f_pp(q); }
+int f32_zoff(int q) { (void)q; return 0; }
+int f32_poff(int q) { return q; }
 bool f32_supported(int D, int q) { return (q == 16 || q == 32 || q == 64) && D >= 32 && (D % 32) == 0; }
 
 cudaError_t launch_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, cudaStream_t st) {
@@ -347,13 +554,14 @@ cudaError_t launch_pack_gw_f32(int D, int q, const double *Wbar, const double *W
     return cudaGetLastError();
 }
 
-cudaError_t launch_zstep_f32(long long N, int D, int q, const void *planes, const void *GT, const void *WT,
-                             const double *P0, const double *h0, const double *gl, float *MZ, cudaStream_t st) {
+cudaError_t launch_zstep_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *GT,
+                             const void *WT, const double *P0, const double *h0, const double *gl, float *MZ,
+                             cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 16: return launch_zstep_f32_q<16>(N, D, planes, GT, WT, P0, h0, gl, MZ, st);
-        case 32: return launch_zstep_f32_q<32>(N, D, planes, GT, WT, P0, h0, gl, MZ, st);
-        case 64: return launch_zstep_f32_q<64>(N, D, planes, GT, WT, P0, h0, gl, MZ, st);
+        case 16: return launch_zstep_f32_q<16>(N, nalloc, D, planes, GT, WT, P0, h0, gl, MZ, st);
+        case 32: return launch_zstep_f32_q<32>(N, nalloc, D, planes, GT, WT, P0, h0, gl, MZ, st);
+        case 64: return launch_zstep_f32_q<64>(N, nalloc, D, planes, GT, WT, P0, h0, gl, MZ, st);
     }
     return cudaErrorNotSupported;
 }

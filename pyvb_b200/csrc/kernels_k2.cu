@@ -12,6 +12,8 @@
 //   3. Sigma = X^T X:           S_ij = sum_k X_ki^T X_kj       (DMMA)
 // then zbar = Sigma eta, <zz^T> = Sigma + zbar zbar^T, ln prod diag chol from the pivots.  Only the 8 x 8 diagonal
 // blocks run on the FP64 FMA pipe (8 sequential pivots each); everything else is tensor-core work.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -48,6 +50,30 @@ template <int Q> struct KB {
     static constexpr int UNR = (P / 32 >= 16) ? 16 : (P + 31) / 32;            // global loads in flight per lane
     static constexpr size_t SMEM = (size_t)TAB_B + (size_t)WARPS * WARP_D * 8;
 };
+
+// Row format of the batched solve.  FP64: the interleaved MZ rows [packed (P) | pad | eta/zbar (q)], pitch
+// pyvb_mz_pitch(q).  FP32 variant: float rows [eta/zbar (q) | packed (P) | pad] of pitch pyvb_f32_pitch(q); the
+// arithmetic stays FP64 (the rows are converted on load / store), and the finished row is also written as a
+// three-way bf16 split (planes [3][N][pitch]) -- the B operand of the FP32 statistics kernel.
+template <int Q, bool F32> struct KIO;
+template <int Q> struct KIO<Q, false> {
+    using type = double;
+    static constexpr int PITCH = kb_pitch(Q), POFF = 0, ZOFF = (kb_tri(Q) + 7) & ~7, USED = ZOFF + Q;
+};
+template <int Q> struct KIO<Q, true> {
+    using type = float;
+    static constexpr int PITCH = (Q + kb_tri(Q) + 63) & ~63, POFF = Q, ZOFF = 0, USED = Q + kb_tri(Q);
+};
+
+__device__ __forceinline__ void store_split3(__nv_bfloat16 *dst, size_t plane, float v) {
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    dst[0] = h;
+    dst[plane] = m;
+    dst[2 * plane] = __float2bfloat16(r2);
+}
 
 // 8 x 8 diagonal block, accumulator layout (lane l: row l/4, columns 2(l%4), 2(l%4)+1).  In: the SPD block A
 // (lower triangle valid).  Out: X = chol(A)^-1 (lower triangular, exact zeros above the diagonal); lprod is
@@ -86,11 +112,14 @@ __device__ __forceinline__ void diag_chol_inv(double c0, double c1, double &x0, 
     if (gid < 2 * qd + 1) x1 = 0.0;
 }
 
-template <int Q>
+template <int Q, bool F32>
 __global__ void __launch_bounds__(32 * KB<Q>::WARPS, KB<Q>::OCC)
-zsolve_blocked_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig, double *__restrict__ logdet,
-                      double *gl, double *__restrict__ zsums) {
+zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, double *__restrict__ Sig,
+                      double *__restrict__ logdet, double *gl, double *__restrict__ zsums,
+                      __nv_bfloat16 *__restrict__ MP) {
     using T = KB<Q>;
+    using IO = KIO<Q, F32>;
+    using io_t = typename IO::type;
     constexpr int NB = T::NB;
     extern __shared__ __align__(16) unsigned char smem_kb[];
     // packed index p -> offset in the block storage (bits 0-11) | i (bits 12-17) | j (bits 18-23)
@@ -119,20 +148,21 @@ zsolve_blocked_kernel(long long N, double *__restrict__ MZ, double *__restrict__
 
     const long long nwarps = (long long)gridDim.x * T::WARPS;
     for (long long n = (long long)blockIdx.x * T::WARPS + warp; n < N; n += nwarps) {
-        double *row = MZ + n * T::LDG;
+        io_t *row = MZ + n * IO::PITCH;
         // the row after this one: pull it into L2 now, it is read ~50k cycles from now
-        if (lane == 0 && n + nwarps < N) prefetch_l2(row + nwarps * T::LDG, T::OROW * 8);
+        if (lane == 0 && n + nwarps < N)
+            prefetch_l2(row + nwarps * IO::PITCH, (uint32_t)((IO::USED * sizeof(io_t) + 15) & ~15u));
         // ---- unpack [qprec packed | eta] into the block storage (coalesced global reads, UNR in flight)
         {
-            const double e0 = (lane < Q) ? row[T::PP + lane] : 0.0;
-            const double e1 = (Q > 32) ? row[T::PP + 32 + (lane & 31)] : 0.0;
+            const double e0 = (lane < Q) ? (double)row[IO::ZOFF + lane] : 0.0;
+            const double e1 = (Q > 32) ? (double)row[IO::ZOFF + 32 + (lane & 31)] : 0.0;
 #pragma unroll 1
             for (int base = 0; base < T::P; base += 32 * T::UNR) {
                 double v[T::UNR];
 #pragma unroll
                 for (int u = 0; u < T::UNR; ++u) {
                     const int p = base + 32 * u + lane;
-                    v[u] = (p < T::P) ? row[p] : 0.0;
+                    v[u] = (p < T::P) ? (double)row[IO::POFF + p] : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < T::UNR; ++u) {
@@ -289,13 +319,15 @@ zsolve_blocked_kernel(long long N, double *__restrict__ MZ, double *__restrict__
             const uint32_t t = tab[p];
             const double s = blk[t & 0xfff];
             const double m = fma(zv[(t >> 12) & 63], zv[t >> 18], s);
-            row[p] = m;
+            row[IO::POFF + p] = (io_t)m;
+            if (F32) store_split3(MP + n * IO::PITCH + IO::POFF + p, (size_t)N * IO::PITCH, (float)m);
             if (sg) sg[p] = s;
             if (T::ZS) csum[p] += m;
         }
         for (int c = lane; c < Q; c += 32) {
             const double z = zv[c];
-            row[T::PP + c] = z;
+            row[IO::ZOFF + c] = (io_t)z;
+            if (F32) store_split3(MP + n * IO::PITCH + IO::ZOFF + c, (size_t)N * IO::PITCH, (float)z);
             if (T::ZS) csum[T::PP + c] += z;
         }
         if (lane == 0) {
@@ -325,15 +357,17 @@ zsolve_blocked_kernel(long long N, double *__restrict__ MZ, double *__restrict__
     }
 }
 
-template <int Q>
-cudaError_t launch_blocked_q(long long N, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
+template <int Q, bool F32>
+cudaError_t launch_blocked_q(long long N, void *MZ, double *Sig, double *logdet, double *gl, double *zsums, void *MP,
                              cudaStream_t st) {
     using T = KB<Q>;
-    cudaError_t e =
-        cudaFuncSetAttribute(zsolve_blocked_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(zsolve_blocked_kernel<Q, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)T::SMEM);
     if (e != cudaSuccess) return e;
     const int blocks = zsolve_blocked_blocks(N, Q);
-    zsolve_blocked_kernel<Q><<<blocks, 32 * T::WARPS, T::SMEM, st>>>(N, MZ, Sig, logdet, gl, T::ZS ? zsums : nullptr);
+    zsolve_blocked_kernel<Q, F32><<<blocks, 32 * T::WARPS, T::SMEM, st>>>(
+        N, static_cast<typename KIO<Q, F32>::type *>(MZ), Sig, logdet, gl, T::ZS ? zsums : nullptr,
+        static_cast<__nv_bfloat16 *>(MP));
     return cudaGetLastError();
 }
 
@@ -367,10 +401,27 @@ cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, d
                                   double *zsums, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 8: return launch_blocked_q<8>(N, MZ, Sig, logdet, gl, zsums, st);
-        case 16: return launch_blocked_q<16>(N, MZ, Sig, logdet, gl, zsums, st);
-        case 32: return launch_blocked_q<32>(N, MZ, Sig, logdet, gl, zsums, st);
-        case 64: return launch_blocked_q<64>(N, MZ, Sig, logdet, gl, zsums, st);
+        case 8: return launch_blocked_q<8, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
+        case 16: return launch_blocked_q<16, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
+        case 32: return launch_blocked_q<32, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
+        case 64: return launch_blocked_q<64, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
+    }
+    return cudaErrorNotSupported;
+}
+
+void zsolve_partials_f32(long long N, int q, int &nblk, int &kw) {
+    kw = (q == 16 || q == 32) ? zsolve_blocked_kw(q) : 0;
+    nblk = (kw > 0 && N > 0) ? zsolve_blocked_blocks(N, q) : 0;
+}
+
+// FP32 rows (see KIO): in place on MZ32, plus the bf16 x 3 split of the finished rows into MP [3][N][pitch]
+cudaError_t launch_zsolve_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
+                              double *zsums, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    switch (q) {
+        case 16: return launch_blocked_q<16, true>(N, MZ32, Sig, logdet, gl, zsums, MP, st);
+        case 32: return launch_blocked_q<32, true>(N, MZ32, Sig, logdet, gl, zsums, MP, st);
+        case 64: return launch_blocked_q<64, true>(N, MZ32, Sig, logdet, gl, zsums, MP, st);
     }
     return cudaErrorNotSupported;
 }

@@ -26,7 +26,7 @@ from . import _cabi
 import os
 
 from .dist import PeerExchange, allreduce_stats
-from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_LEN, GL_NONPD, GL_QA,
+from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_F32, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_LEN, GL_NONPD, GL_QA,
                       GL_QB, GL_TAU, OP_ALPHA, OP_BETA, OP_ELBO, OP_MU, QMAX, StatLayout)
 
 _ALGOS = {"auto": ALGO_AUTO, "generic": ALGO_GENERIC, "dmma": ALGO_DMMA}
@@ -59,12 +59,14 @@ class PlateEngine(object):
 
     def __init__(self, X, q, mode="B", alpha0=1e-3, alpha_mu=1e-3, a0=1e-3, b0=1e-3, ard=False,
                  ard_a0=1e-3, ard_b0=1e-3, P0=None, m0=None, device=None, algo="auto",
-                 keep_sigma=True, distributed=False, row_offset=0, trace_len=4096):
+                 keep_sigma=True, distributed=False, row_offset=0, trace_len=4096, precision="f64"):
         if not torch.cuda.is_available():
             raise RuntimeError("pyvb_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _cabi.lib()
         assert mode in ("A", "B")
         assert 1 <= q <= QMAX, "latent dimension must be in [1, %d]" % QMAX
+        assert precision in ("f64", "f32")
+        self.f32 = (precision == "f32")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.mode, self.q, self.ard = mode, int(q), bool(ard)
         self.algo = _ALGOS[algo] if isinstance(algo, str) else int(algo)
@@ -86,7 +88,22 @@ class PlateEngine(object):
         # ---- data
         obs = ~torch.isnan(Xt)
         n_obs_local = int(obs.sum().item())
-        if mode == "A":
+        if self.f32:
+            # FP32 variant (tcgen05): the data live as three bf16 planes (mask | x_h | x_m); the sums that depend on
+            # X alone are taken once, here, in FP64
+            if mode != "B" or not self.lib.pyvb_f32_supported(self.D, q) or q not in (16, 32):
+                raise ValueError("precision='f32' needs mode B, q in (16, 32) and D % 32 == 0")
+            x0 = torch.where(obs, Xt, torch.zeros((), dtype=f64, device=dev))
+            self.xcache = torch.cat([obs.sum(0).to(f64), x0.sum(0), (x0 * x0).sum().reshape(1),
+                                     torch.tensor([float(n_obs_local)], dtype=f64, device=dev)]).contiguous()
+            del x0
+            self.planes = torch.zeros(3, N, D, dtype=torch.bfloat16, device=dev)
+            _cabi.check(self.lib.pyvb_prepare_x_f32(N, D, Xt.data_ptr(), D, self.planes.data_ptr(), self._stream()),
+                        "pyvb_prepare_x_f32")
+            torch.cuda.current_stream(dev).synchronize()
+            self.Xorig, self.X, self.V, self.qldX = None, None, None, None
+            n_eff_local = n_obs_local
+        elif mode == "A":
             self.Xorig = Xt
             self.X = torch.where(obs, Xt, torch.zeros((), dtype=f64, device=dev)).contiguous()   # Xhat
             self.V = torch.where(obs, torch.zeros((), dtype=f64, device=dev),
@@ -105,10 +122,19 @@ class PlateEngine(object):
 
         # ---- latent state
         # <zz^T> (packed) and <z> interleaved in one array: one TMA tile feeds the statistics GEMM
-        self.ldmz = int(self.lib.pyvb_mz_pitch(q))
-        self.zoff = int(self.lib.pyvb_gw_woff(q))
-        self.MZ = torch.zeros(N, self.ldmz, dtype=f64, device=dev)
-        self.M2 = self.MZ[:, :self.P]
+        if self.f32:
+            # FP32 rows [zbar (q) | <zz^T> packed (P) | pad] + their three-way bf16 split (B operand of the statistics)
+            self.ldmz = int(self.lib.pyvb_f32_pitch(q))
+            self.zoff, self.poff = int(self.lib.pyvb_f32_zoff(q)), int(self.lib.pyvb_f32_poff(q))
+            self.MZ = torch.zeros(N, self.ldmz, dtype=torch.float32, device=dev)
+            self.MP = torch.zeros(3, N, self.ldmz, dtype=torch.bfloat16, device=dev)
+            self.GT = torch.zeros(3, self.ldmz, D, dtype=torch.bfloat16, device=dev)
+            self.WT = torch.zeros(3, q, D, dtype=torch.bfloat16, device=dev)
+        else:
+            self.ldmz = int(self.lib.pyvb_mz_pitch(q))
+            self.zoff, self.poff = int(self.lib.pyvb_gw_woff(q)), 0
+            self.MZ = torch.zeros(N, self.ldmz, dtype=f64, device=dev)
+        self.M2 = self.MZ[:, self.poff:self.poff + self.P]
         self.Zbar = self.MZ[:, self.zoff:self.zoff + q]
         self.Sig = torch.zeros(N, self.P, dtype=f64, device=dev) if keep_sigma else None
         self.logdet = torch.ones(N, dtype=f64, device=dev)
@@ -120,13 +146,19 @@ class PlateEngine(object):
         self.Gw = torch.zeros(D, self.ldg, dtype=f64, device=dev)
         self.stats = torch.zeros(self.L.len, dtype=f64, device=dev)
         assert self.L.len == int(self.lib.pyvb_stats_len(D, q))
-        self.ws_bytes = int(self.lib.pyvb_stats_workspace_bytes(N, D, q, self.algo))
+        self.ws_bytes = int(self.lib.pyvb_stats_workspace_bytes(N, D, q, ALGO_F32 if self.f32 else self.algo))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
-        self.xcache = torch.zeros(2 * D + 2, dtype=f64, device=dev) if mode == "B" else None
-        self._xcache_valid = False
-        # per-CTA column sums of the MZ rows left by the batched solve (K2) of a full-range Z update
-        nz = int(self.lib.pyvb_zsums_len(N, q)) if self.lib.pyvb_algo_supported(ALGO_DMMA, D, q) else 0
-        self.zsums = torch.zeros(nz, dtype=f64, device=dev) if nz > 0 and self.algo in (ALGO_AUTO, ALGO_DMMA) else None
+        if self.f32:
+            self._xcache_valid = True
+            nz = int(self.lib.pyvb_zsums_len_f32(N, q))
+            self.zsums = torch.zeros(nz, dtype=f64, device=dev)
+        else:
+            self.xcache = torch.zeros(2 * D + 2, dtype=f64, device=dev) if mode == "B" else None
+            self._xcache_valid = False
+            # per-CTA column sums of the MZ rows left by the batched solve (K2) of a full-range Z update
+            nz = int(self.lib.pyvb_zsums_len(N, q)) if self.lib.pyvb_algo_supported(ALGO_DMMA, D, q) else 0
+            self.zsums = (torch.zeros(nz, dtype=f64, device=dev)
+                          if nz > 0 and self.algo in (ALGO_AUTO, ALGO_DMMA) else None)
         self._zsums_valid = False
         # multi-GPU: the all-reduce happens inside the statistics kernel over NVLink peer memory
         # (PYVB_COMM=nccl: plain torch.distributed all_reduce instead, for comparison)
@@ -212,7 +244,10 @@ class PlateEngine(object):
             if self.Sig is not None:
                 self.Sig.copy_(sig_t)
             it, jt = torch.as_tensor(ii, device=dev), torch.as_tensor(jj, device=dev)
-            self.M2.copy_(sig_t + self.Zbar[:, it] * self.Zbar[:, jt])
+            zb = self.Zbar.to(f64)
+            self.M2.copy_(sig_t + zb[:, it] * zb[:, jt])
+        if self.f32:
+            self._resplit()
         gl = self.gl.cpu()
         gl[GL_QA] = self.qa
         if "qb" in st:
@@ -228,6 +263,30 @@ class PlateEngine(object):
         self._stats_fresh = False
         self._gw_fresh = False
         self._zsums_valid = False
+
+    def _resplit(self, step=1 << 16):
+        """FP32 variant: refresh the bf16 x 3 planes after the FP32 rows were written from outside the kernels."""
+        for lo in range(0, self.N, step):
+            v = self.MZ[lo:lo + step]
+            h = v.to(torch.bfloat16)
+            r = v - h.float()
+            m = r.to(torch.bfloat16)
+            self.MP[0, lo:lo + step] = h
+            self.MP[1, lo:lo + step] = m
+            self.MP[2, lo:lo + step] = (r - m.float()).to(torch.bfloat16)
+
+    def _zsums_from_state(self):
+        """FP32 variant: the column sums K2 would have left, from an injected state (one partial, rest zero)."""
+        kw = self.lib.pyvb_gw_woff(self.q) + self.q + 4
+        z = self.zsums.view(-1, kw)
+        z.zero_()
+        pp = int(self.lib.pyvb_gw_woff(self.q))
+        z[0, :self.P] = self.M2.to(torch.float64).sum(0)
+        z[0, pp:pp + self.q] = self.Zbar.to(torch.float64).sum(0)
+        z[0, pp + self.q] = (0.5 / self.logdet).sum()
+        z[0, pp + self.q + 1] = self.logdet.sum()
+        z[0, pp + self.q + 2] = float(self.N)
+        self._zsums_valid = True
 
     def init_random(self, seed=1234, rank=0):
         """Scale-run initialisation on the device: Wbar ~ N(0,1) (same on every rank),
@@ -246,8 +305,8 @@ class PlateEngine(object):
         eye = (it == jt).to(torch.float64)
         step = 1 << 16
         for lo in range(0, self.N, step):
-            z = self.Zbar[lo:lo + step]
-            self.M2[lo:lo + step] = z[:, it] * z[:, jt] + eye
+            z = self.Zbar[lo:lo + step].to(torch.float64)
+            self.M2[lo:lo + step] = (z[:, it] * z[:, jt] + eye).to(self.M2.dtype)
             if self.Sig is not None:
                 self.Sig[lo:lo + step] = eye
         self.logdet.fill_(1.0)
@@ -255,7 +314,7 @@ class PlateEngine(object):
 
     def set_X(self, X):
         """Replace the (mode B) data shard, e.g. from pinned host memory; invalidates the cached X sums."""
-        assert self.mode == "B"
+        assert self.mode == "B" and not self.f32
         self.X.copy_(X, non_blocking=True)
         self._xcache_valid = False
         self._stats_fresh = False
@@ -264,13 +323,14 @@ class PlateEngine(object):
         """Host copy of the state in the oracle's layout."""
         q = self.q
         ii, jj = tril_pack_index(q)
-        out = {k: getattr(self, k).contiguous().cpu().numpy() for k in ("Wbar", "Wvar", "mu", "muvar", "Zbar")}
+        out = {k: getattr(self, k).contiguous().to(torch.float64).cpu().numpy()
+               for k in ("Wbar", "Wvar", "mu", "muvar", "Zbar")}
         N = self.N
         if self.Sig is not None:
             sp = self.Sig.cpu().numpy()
         else:
             z = out["Zbar"]
-            sp = self.M2.contiguous().cpu().numpy() - z[:, ii] * z[:, jj]
+            sp = self.M2.contiguous().to(torch.float64).cpu().numpy() - z[:, ii] * z[:, jj]
         Sig = np.zeros((N, q, q))
         Sig[:, ii, jj] = sp
         Sig[:, jj, ii] = sp
@@ -299,6 +359,11 @@ class PlateEngine(object):
 
     # ------------------------------------------------------------------ operators
     def _ensure_gw(self):
+        if not self._gw_fresh and self.f32:
+            rc = self.lib.pyvb_pack_gw_f32(self.D, self.q, self.Wbar.data_ptr(), self.Wvar.data_ptr(),
+                                           self.mu.data_ptr(), self.GT.data_ptr(), self.WT.data_ptr(), self._stream())
+            _cabi.check(rc, "pyvb_pack_gw_f32")
+            self._gw_fresh = True
         if not self._gw_fresh:
             rc = self.lib.pyvb_pack_gw_f64(self.D, self.q, self.Wbar.data_ptr(), self.Wvar.data_ptr(),
                                            self.mu.data_ptr(), self.Gw.data_ptr(), self.ldg, self._stream())
@@ -307,6 +372,19 @@ class PlateEngine(object):
 
     def _ensure_stats(self):
         if self._stats_fresh:
+            return
+        if self.f32:
+            if not self._zsums_valid:
+                self._zsums_from_state()
+            rc = self.lib.pyvb_stats_f32(self.N, self.N, self.D, self.q, self.planes.data_ptr(), self.MP.data_ptr(),
+                                         self.stats.data_ptr(), self.ws.data_ptr(), self.ws_bytes,
+                                         self.xcache.data_ptr(), self.zsums.data_ptr(),
+                                         self.peers.next() if (self.peers is not None and self.distributed) else None,
+                                         self._stream())
+            _cabi.check(rc, "pyvb_stats_f32")
+            if self.distributed and self.peers is None:
+                allreduce_stats(self.stats)
+            self._stats_fresh = True
             return
         rc = self.lib.pyvb_stats_f64(self.N, self.D, self.q, self.X.data_ptr(), self.D, self._p(self.V),
                                      self._p(self.Xorig), self._p(self.qldX), self.Zbar.data_ptr(), self.ldmz,
@@ -338,6 +416,19 @@ class PlateEngine(object):
         self._ensure_gw()
         q, P, D = self.q, self.P, self.D
         sig = 0 if self.Sig is None else self.Sig.data_ptr() + lo * P * 8
+        if self.f32:
+            full = (lo == 0 and hi == self.N)
+            if not full and not self._zsums_valid:
+                pass                                        # the sums are rebuilt from the state before the next statistics
+            self._zsums_valid = False
+            rc = self.lib.pyvb_zstep_f32(hi - lo, self.N, D, q, self.planes.data_ptr() + lo * D * 2, self.GT.data_ptr(),
+                                         self.WT.data_ptr(), self.P0.data_ptr(), self.h0.data_ptr(), self.gl.data_ptr(),
+                                         self.MZ.data_ptr() + lo * self.ldmz * 4, self.MP.data_ptr() + lo * self.ldmz * 2,
+                                         sig, self.logdet.data_ptr() + lo * 8, self.zsums.data_ptr() if full else 0,
+                                         self._stream())
+            _cabi.check(rc, "pyvb_zstep_f32")
+            self._zsums_valid = full
+            return
         full = (lo == 0 and hi == self.N and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA))
         self._zsums_valid = False
         rc = self.lib.pyvb_zstep_f64(hi - lo, D, q, self.X.data_ptr() + lo * D * 8, D, self.Gw.data_ptr(),
