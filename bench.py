@@ -207,6 +207,58 @@ def make_data(torch, N, D, q, missing, seed, dev):
     return X
 
 
+def bench_f32(torch, a, dev, eng64, _cabi, lib, time_calls):
+    """The FP32 variant on the same data: sweeps/s and its three kernels (CUDA events)."""
+    from pyvb_b200 import PlateEngine
+    X = eng64.X
+    e = PlateEngine(X, a.q, mode="B", keep_sigma=False, device=dev, precision="f32")
+    e.init_random(seed=4321, rank=0)
+    for _ in range(3):
+        e.iterate_async()
+    torch.cuda.synchronize(dev)
+    K = max(3, min(a.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    slots = [e.iterate_async() for _ in range(K)]
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / K
+    e.check()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    e._ensure_gw()
+
+    def k1():
+        _cabi.check(lib.pyvb_zstep_k1_f32(e.N, e.D, e.q, e.planes.data_ptr(), e.GT.data_ptr(), e.WT.data_ptr(),
+                                          e.P0.data_ptr(), e.h0.data_ptr(), e.gl.data_ptr(), e.MZ.data_ptr(), st), "k1")
+    ms_k1 = time_calls(k1, 5)
+    ms_z = time_calls(lambda: e.update_Z(), 5)
+
+    def stats_call():
+        e._stats_fresh = False
+        e._ensure_stats()
+    ms_s = time_calls(stats_call, 5)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    ncp = e.ldmz
+    by_k1 = e.N * (3.0 * 2 * e.D + 4.0 * ncp)           # the three bf16 planes once + the FP32 row out
+    by_k3 = e.N * (3.0 * 2 * e.D + 3.0 * 2 * ncp)       # the planes + the bf16 x 3 rows once
+    out = {"value": e.N / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "elbo_last": float(e.trace[slots[-1]].item()),
+           "dtype": "f32 rows, bf16x3 tcgen05 contraction with FP32 TMEM accumulation, FP64 batched solve",
+           "tolerance": "one sweep from a shared state: 5e-5 tensor-wise on W, mu, Z, Sigma; 5e-3 on qb; see tests/test_gpu_f32.py",
+           "kernels": {"k1_ms": ms_k1, "zstep_ms": ms_z, "k2_ms": ms_z - ms_k1, "stats_ms": ms_s},
+           "roofline_k1": {"bound": "hbm", "achieved": by_k1 / (ms_k1 * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
+                           "frac": by_k1 / (ms_k1 * 1e-3) * 1e-9 / hbm, "bytes_per_launch": by_k1,
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+           "roofline_k3": {"bound": "hbm", "achieved": by_k3 / (ms_s * 1e-3) * 1e-9, "peak": hbm, "unit": "GB/s",
+                           "frac": by_k3 / (ms_s * 1e-3) * 1e-9 / hbm, "bytes_per_launch": by_k3}}
+    del e
+    return out
+
+
 def run_ours(a):
     # exactly ONE line on stdout: libraries (NCCL banner ...) get stderr, the JSON line gets the real stdout
     sys.stdout.flush()
@@ -342,6 +394,14 @@ def run_ours(a):
                "sweep_algorithmic_tflops": world * a.N * (4.0 * D * P + 6.0 * D * q + q ** 3 + 2.0 * q * q)
                * a.steps / (ms * 1e-3) * 1e-12 / world}
 
+    # ---- FP32 variant (tcgen05 / TMEM / TMA) on the same shard, N = 1 only: whole sweeps + its kernels
+    f32v = None
+    if world == 1 and a.mode == "B" and a.q in (16, 32) and a.D % 32 == 0 and not a.no_f32:
+        try:
+            f32v = bench_f32(torch, a, dev, eng, _cabi, lib, time_calls)
+        except Exception as ex:  # pragma: no cover
+            f32v = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -354,6 +414,8 @@ def run_ours(a):
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": a.N * a.D * 8, "d2h_bytes_per_step": 8,
                         "steps": e2e_steps},
                 "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}
+        if f32v is not None:
+            line["f32_variant"] = f32v
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(a)
         sys.stdout.flush()
@@ -376,6 +438,7 @@ def main():
     ap.add_argument("--mode", default="B", choices=["A", "B"])
     ap.add_argument("--algo", default="auto", choices=["auto", "generic", "dmma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-f32", action="store_true", help="skip the FP32-variant leg")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -34,18 +34,22 @@ __host__ __device__ constexpr int kb_sw(int r, int c) { return r * 8 + ((((c >> 
 __host__ __device__ constexpr int kb_boff(int i, int j) { return (kb_tri(i) + j) * 64; }
 
 template <int Q> struct KBC;
-template <> struct KBC<8>  { static constexpr int WARPS = 8,  OCC = 3; static constexpr bool ZS = true; };
-template <> struct KBC<16> { static constexpr int WARPS = 8,  OCC = 2; static constexpr bool ZS = true; };
-template <> struct KBC<32> { static constexpr int WARPS = 10, OCC = 2; static constexpr bool ZS = true; };
-template <> struct KBC<64> { static constexpr int WARPS = 11, OCC = 1; static constexpr bool ZS = false; };
+// MPW: matrices per warp, processed as interleaved instruction streams (the 8 x 8 diagonal blocks are a chain of
+// 8 dependent pivots each; a second matrix fills the latency)
+// (measured: MPW = 2 does not help -- the kernel is issue-bound, not latency-bound -- so MPW = 1 everywhere)
+template <> struct KBC<8>  { static constexpr int WARPS = 8,  OCC = 3, MPW = 1; static constexpr bool ZS = true; };
+template <> struct KBC<16> { static constexpr int WARPS = 8,  OCC = 2, MPW = 1; static constexpr bool ZS = true; };
+template <> struct KBC<32> { static constexpr int WARPS = 10, OCC = 2, MPW = 1; static constexpr bool ZS = true; };
+template <> struct KBC<64> { static constexpr int WARPS = 11, OCC = 1, MPW = 1; static constexpr bool ZS = false; };
 
 template <int Q> struct KB {
     static constexpr int NB = Q / 8, NBLK = kb_tri(NB);
     static constexpr int P = kb_tri(Q), PP = (P + 7) & ~7, OROW = PP + Q, LDG = kb_pitch(Q);
-    static constexpr int WARPS = KBC<Q>::WARPS, OCC = KBC<Q>::OCC;
+    static constexpr int WARPS = KBC<Q>::WARPS, OCC = KBC<Q>::OCC, MPW = KBC<Q>::MPW;
     static constexpr bool ZS = KBC<Q>::ZS;
     static constexpr int KW = OROW + PYVB_ZS_EXTRA;
-    static constexpr int WARP_D = NBLK * 64 + 2 * Q + (ZS ? OROW : 0) + 4;     // blocks | eta | z | column sums | scalars
+    static constexpr int MAT_D = NBLK * 64 + 2 * Q;                             // per matrix: blocks | eta | z
+    static constexpr int WARP_D = MPW * MAT_D + (ZS ? OROW : 0) + 4;            // ... | column sums | scalars
     static constexpr int TAB_B = ((P * 4) + 15) & ~15;                         // one uint32 table
     static constexpr int UNR = (P / 32 >= 16) ? 16 : (P + 31) / 32;            // global loads in flight per lane
     static constexpr size_t SMEM = (size_t)TAB_B + (size_t)WARPS * WARP_D * 8;
@@ -75,41 +79,56 @@ __device__ __forceinline__ void store_split3(__nv_bfloat16 *dst, size_t plane, f
     dst[2 * plane] = __float2bfloat16(r2);
 }
 
-// 8 x 8 diagonal block, accumulator layout (lane l: row l/4, columns 2(l%4), 2(l%4)+1).  In: the SPD block A
-// (lower triangle valid).  Out: X = chol(A)^-1 (lower triangular, exact zeros above the diagonal); lprod is
-// multiplied by prod_k 1/l_kk.  Right-looking factorisation and right-looking inversion fused in one sweep:
-// per pivot one broadcast, one rsqrt, and independent multiply-adds.
-__device__ __forceinline__ void diag_chol_inv(double c0, double c1, double &x0, double &x1, double &lprod) {
+// 8 x 8 diagonal blocks of MPW independent matrices, accumulator layout (lane l: row l/4, columns 2(l%4), 2(l%4)+1).
+// In: the SPD blocks A (lower triangle valid).  Out: X = chol(A)^-1 (lower triangular, exact zeros above the
+// diagonal); lprod[m] is multiplied by prod_k 1/l_kk.  Right-looking factorisation and right-looking inversion fused
+// in one sweep: per pivot one broadcast, one rsqrt, and independent multiply-adds; the MPW pivot chains interleave.
+template <int MPW>
+__device__ __forceinline__ void diag_chol_inv(double (&c0)[MPW], double (&c1)[MPW], double (&x0)[MPW], double (&x1)[MPW],
+                                              double (&lprod)[MPW]) {
     const int lane = threadIdx.x & 31;
     const int gid = lane >> 2, qd = lane & 3;
-    x0 = (gid == 2 * qd) ? 1.0 : 0.0;
-    x1 = (gid == 2 * qd + 1) ? 1.0 : 0.0;
+#pragma unroll
+    for (int m = 0; m < MPW; ++m) {
+        x0[m] = (gid == 2 * qd) ? 1.0 : 0.0;
+        x1[m] = (gid == 2 * qd + 1) ? 1.0 : 0.0;
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int kq = k >> 1;
-        const double ck = (k & 1) ? c1 : c0;
-        const double d = __shfl_sync(0xffffffffu, ck, k * 4 + kq);                 // pivot a_kk
-        const double rinv = rsqrt(d);
-        lprod *= rinv;
-        const double lik = __shfl_sync(0xffffffffu, ck, (lane & ~3) | kq) * rinv;   // l_(gid, k)   (gid >= k)
-        const double lj0 = __shfl_sync(0xffffffffu, ck, (2 * qd) * 4 + kq) * rinv;  // l_(2qd, k)
-        const double lj1 = __shfl_sync(0xffffffffu, ck, (2 * qd + 1) * 4 + kq) * rinv;
-        if (2 * qd > k) c0 = fma(-lik, lj0, c0);
-        if (2 * qd + 1 > k) c1 = fma(-lik, lj1, c1);
-        // row k of X is final once scaled by 1/l_kk; eliminate it from the rows below
-        if (gid == k) {
-            x0 *= rinv;
-            x1 *= rinv;
+        double rinv[MPW], lik[MPW];
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            const double ck = (k & 1) ? c1[m] : c0[m];
+            const double d = __shfl_sync(0xffffffffu, ck, k * 4 + kq);                    // pivot a_kk
+            rinv[m] = rsqrt(d);
+            lprod[m] *= rinv[m];
+            lik[m] = __shfl_sync(0xffffffffu, ck, (lane & ~3) | kq) * rinv[m];            // l_(gid, k)   (gid >= k)
+            const double lj0 = __shfl_sync(0xffffffffu, ck, (2 * qd) * 4 + kq) * rinv[m];  // l_(2qd, k)
+            const double lj1 = __shfl_sync(0xffffffffu, ck, (2 * qd + 1) * 4 + kq) * rinv[m];
+            if (2 * qd > k) c0[m] = fma(-lik[m], lj0, c0[m]);
+            if (2 * qd + 1 > k) c1[m] = fma(-lik[m], lj1, c1[m]);
         }
-        const double xk0 = __shfl_sync(0xffffffffu, x0, k * 4 + qd);
-        const double xk1 = __shfl_sync(0xffffffffu, x1, k * 4 + qd);
-        if (gid > k) {
-            x0 = fma(-lik, xk0, x0);
-            x1 = fma(-lik, xk1, x1);
+        // row k of X is final once scaled by 1/l_kk; eliminate it from the rows below
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            if (gid == k) {
+                x0[m] *= rinv[m];
+                x1[m] *= rinv[m];
+            }
+            const double xk0 = __shfl_sync(0xffffffffu, x0[m], k * 4 + qd);
+            const double xk1 = __shfl_sync(0xffffffffu, x1[m], k * 4 + qd);
+            if (gid > k) {
+                x0[m] = fma(-lik[m], xk0, x0[m]);
+                x1[m] = fma(-lik[m], xk1, x1[m]);
+            }
         }
     }
-    if (gid < 2 * qd) x0 = 0.0;
-    if (gid < 2 * qd + 1) x1 = 0.0;
+#pragma unroll
+    for (int m = 0; m < MPW; ++m) {
+        if (gid < 2 * qd) x0[m] = 0.0;
+        if (gid < 2 * qd + 1) x1[m] = 0.0;
+    }
 }
 
 template <int Q, bool F32>
@@ -120,15 +139,13 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
     using T = KB<Q>;
     using IO = KIO<Q, F32>;
     using io_t = typename IO::type;
-    constexpr int NB = T::NB;
+    constexpr int NB = T::NB, MPW = T::MPW;
     extern __shared__ __align__(16) unsigned char smem_kb[];
     // packed index p -> offset in the block storage (bits 0-11) | i (bits 12-17) | j (bits 18-23)
     uint32_t *tab = reinterpret_cast<uint32_t *>(smem_kb);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double *blk = reinterpret_cast<double *>(smem_kb + T::TAB_B) + (size_t)warp * T::WARP_D;
-    double *eta = blk + T::NBLK * 64;
-    double *zv = eta + Q;
-    double *csum = zv + Q;                                       // [OROW] when ZS
+    double *wbase = reinterpret_cast<double *>(smem_kb + T::TAB_B) + (size_t)warp * T::WARP_D;
+    double *csum = wbase + MPW * T::MAT_D;                       // [OROW] when ZS
     double *wsc = csum + (T::ZS ? T::OROW : 0);                  // [4]
 
     for (int p = tid; p < T::P; p += 32 * T::WARPS) {
@@ -146,89 +163,126 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
     const int oC = kb_sw(gid, 2 * qd);                           // accumulator pair    M[gid][2qd, 2qd+1]
     double s_qld = 0.0, s_ld = 0.0, s_n = 0.0;
 
+    // every warp walks over groups of MPW consecutive rows; the MPW matrices are independent instruction streams
     const long long nwarps = (long long)gridDim.x * T::WARPS;
-    for (long long n = (long long)blockIdx.x * T::WARPS + warp; n < N; n += nwarps) {
-        io_t *row = MZ + n * IO::PITCH;
-        // the row after this one: pull it into L2 now, it is read ~50k cycles from now
-        if (lane == 0 && n + nwarps < N)
-            prefetch_l2(row + nwarps * IO::PITCH, (uint32_t)((IO::USED * sizeof(io_t) + 15) & ~15u));
+    const long long ngroups = (N + MPW - 1) / MPW;
+    for (long long g = (long long)blockIdx.x * T::WARPS + warp; g < ngroups; g += nwarps) {
+        io_t *row[MPW];
+        long long nrow[MPW];
+        bool valid[MPW];
+        double *blk[MPW], *eta[MPW], *zv[MPW];
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            nrow[m] = g * MPW + m;
+            valid[m] = nrow[m] < N;
+            if (!valid[m]) nrow[m] = N - 1;                      // tail: redo the last row, store nothing
+            row[m] = MZ + nrow[m] * IO::PITCH;
+            blk[m] = wbase + m * T::MAT_D;
+            eta[m] = blk[m] + T::NBLK * 64;
+            zv[m] = eta[m] + Q;
+        }
+        // the group after this one: pull it into L2 now, it is read tens of thousands of cycles from now
+        if (lane == 0 && (g + nwarps) * MPW + MPW <= N)
+            prefetch_l2(MZ + (g + nwarps) * MPW * IO::PITCH, (uint32_t)(MPW * IO::PITCH * sizeof(io_t)));
         // ---- unpack [qprec packed | eta] into the block storage (coalesced global reads, UNR in flight)
-        {
-            const double e0 = (lane < Q) ? (double)row[IO::ZOFF + lane] : 0.0;
-            const double e1 = (Q > 32) ? (double)row[IO::ZOFF + 32 + (lane & 31)] : 0.0;
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            const double e0 = (lane < Q) ? (double)row[m][IO::ZOFF + lane] : 0.0;
+            const double e1 = (Q > 32) ? (double)row[m][IO::ZOFF + 32 + (lane & 31)] : 0.0;
 #pragma unroll 1
             for (int base = 0; base < T::P; base += 32 * T::UNR) {
                 double v[T::UNR];
 #pragma unroll
                 for (int u = 0; u < T::UNR; ++u) {
                     const int p = base + 32 * u + lane;
-                    v[u] = (p < T::P) ? (double)row[IO::POFF + p] : 0.0;
+                    v[u] = (p < T::P) ? (double)row[m][IO::POFF + p] : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < T::UNR; ++u) {
                     const int p = base + 32 * u + lane;
-                    if (p < T::P) blk[tab[p] & 0xfff] = v[u];
+                    if (p < T::P) blk[m][tab[p] & 0xfff] = v[u];
                 }
             }
-            if (lane < Q) eta[lane] = e0;
-            if (Q > 32) eta[32 + lane] = e1;
+            if (lane < Q) eta[m][lane] = e0;
+            if (Q > 32) eta[m][32 + lane] = e1;
         }
         __syncwarp();
 
         // ---- 1. left-looking block Cholesky; diagonal blocks are replaced by their inverses X_jj
-        double mant = 1.0;            // prod_k 1/l_kk = mant * 2^esum, renormalised after every diagonal block
-        int esum = 0;
-        bool ok = true;
+        double mant[MPW];             // prod_k 1/l_kk = mant * 2^esum, renormalised after every diagonal block
+        int esum[MPW];
+        bool ok[MPW];
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            mant[m] = 1.0;
+            esum[m] = 0;
+            ok[m] = true;
+        }
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
-            double acc[NB][2];
+            double acc[MPW][NB][2];
 #pragma unroll
-            for (int ib = 0; ib < NB; ++ib) acc[ib][0] = acc[ib][1] = 0.0;
+            for (int m = 0; m < MPW; ++m) {
 #pragma unroll
-            for (int kb = 0; kb < jb; ++kb) {
-                const double *Bj = blk + kb_boff(jb, kb);
-                const double b0 = Bj[oA0], b1 = Bj[oA1];
+                for (int ib = 0; ib < NB; ++ib) acc[m][ib][0] = acc[m][ib][1] = 0.0;
+#pragma unroll
+                for (int kb = 0; kb < jb; ++kb) {
+                    const double *Bj = blk[m] + kb_boff(jb, kb);
+                    const double b0 = Bj[oA0], b1 = Bj[oA1];
+#pragma unroll
+                    for (int ib = jb; ib < NB; ++ib) {
+                        const double *Ai = blk[m] + kb_boff(ib, kb);
+                        dmma884(acc[m][ib][0], acc[m][ib][1], Ai[oA0], b0);
+                        dmma884(acc[m][ib][0], acc[m][ib][1], Ai[oA1], b1);
+                    }
+                }
 #pragma unroll
                 for (int ib = jb; ib < NB; ++ib) {
-                    const double *Ai = blk + kb_boff(ib, kb);
-                    dmma884(acc[ib][0], acc[ib][1], Ai[oA0], b0);
-                    dmma884(acc[ib][0], acc[ib][1], Ai[oA1], b1);
+                    const double2 a = *reinterpret_cast<const double2 *>(blk[m] + kb_boff(ib, jb) + oC);
+                    acc[m][ib][0] = a.x - acc[m][ib][0];
+                    acc[m][ib][1] = a.y - acc[m][ib][1];
                 }
             }
+            double d0[MPW], d1[MPW], x0[MPW], x1[MPW];
 #pragma unroll
-            for (int ib = jb; ib < NB; ++ib) {
-                const double2 a = *reinterpret_cast<const double2 *>(blk + kb_boff(ib, jb) + oC);
-                acc[ib][0] = a.x - acc[ib][0];
-                acc[ib][1] = a.y - acc[ib][1];
+            for (int m = 0; m < MPW; ++m) {
+                d0[m] = acc[m][jb][0];
+                d1[m] = acc[m][jb][1];
             }
-            double x0, x1;
-            diag_chol_inv(acc[jb][0], acc[jb][1], x0, x1, mant);
-            {
-                ok = ok && (mant - mant == 0.0);                 // NaN / inf <=> a pivot was <= 0
-                const long long bits = __double_as_longlong(mant);
-                esum += (int)((bits >> 52) & 0x7ff) - 1023;
-                mant = __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
-            }
-            *reinterpret_cast<double2 *>(blk + kb_boff(jb, jb) + oC) = make_double2(x0, x1);
+            diag_chol_inv<MPW>(d0, d1, x0, x1, mant);
 #pragma unroll
-            for (int ib = jb + 1; ib < NB; ++ib)
-                *reinterpret_cast<double2 *>(blk + kb_boff(ib, jb) + oC) = make_double2(acc[ib][0], acc[ib][1]);
+            for (int m = 0; m < MPW; ++m) {
+                ok[m] = ok[m] && (mant[m] - mant[m] == 0.0);     // NaN / inf <=> a pivot was <= 0
+                const long long bits = __double_as_longlong(mant[m]);
+                esum[m] += (int)((bits >> 52) & 0x7ff) - 1023;
+                mant[m] = __longlong_as_double((bits & 0x800fffffffffffffLL) | 0x3ff0000000000000LL);
+                *reinterpret_cast<double2 *>(blk[m] + kb_boff(jb, jb) + oC) = make_double2(x0[m], x1[m]);
+#pragma unroll
+                for (int ib = jb + 1; ib < NB; ++ib)
+                    *reinterpret_cast<double2 *>(blk[m] + kb_boff(ib, jb) + oC) = make_double2(acc[m][ib][0], acc[m][ib][1]);
+            }
             __syncwarp();
             if (jb + 1 < NB) {
                 // L_ij = C_ij X_jj^T
-                const double *Xj = blk + kb_boff(jb, jb);
-                const double xb0 = Xj[oA0], xb1 = Xj[oA1];
 #pragma unroll
-                for (int ib = jb + 1; ib < NB; ++ib) {
-                    const double *Ci = blk + kb_boff(ib, jb);
-                    acc[ib][0] = acc[ib][1] = 0.0;
-                    dmma884(acc[ib][0], acc[ib][1], Ci[oA0], xb0);
-                    dmma884(acc[ib][0], acc[ib][1], Ci[oA1], xb1);
+                for (int m = 0; m < MPW; ++m) {
+                    const double *Xj = blk[m] + kb_boff(jb, jb);
+                    const double xb0 = Xj[oA0], xb1 = Xj[oA1];
+#pragma unroll
+                    for (int ib = jb + 1; ib < NB; ++ib) {
+                        const double *Ci = blk[m] + kb_boff(ib, jb);
+                        acc[m][ib][0] = acc[m][ib][1] = 0.0;
+                        dmma884(acc[m][ib][0], acc[m][ib][1], Ci[oA0], xb0);
+                        dmma884(acc[m][ib][0], acc[m][ib][1], Ci[oA1], xb1);
+                    }
                 }
                 __syncwarp();
 #pragma unroll
-                for (int ib = jb + 1; ib < NB; ++ib)
-                    *reinterpret_cast<double2 *>(blk + kb_boff(ib, jb) + oC) = make_double2(acc[ib][0], acc[ib][1]);
+                for (int m = 0; m < MPW; ++m)
+#pragma unroll
+                    for (int ib = jb + 1; ib < NB; ++ib)
+                        *reinterpret_cast<double2 *>(blk[m] + kb_boff(ib, jb) + oC) =
+                            make_double2(acc[m][ib][0], acc[m][ib][1]);
                 __syncwarp();
             }
         }
@@ -236,106 +290,131 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
         // ---- 2. X = L^-1, one block row at a time:  X_ik = -X_ii * sum_{k <= j < i} L_ij X_jk
 #pragma unroll
         for (int ib = 1; ib < NB; ++ib) {
-            double acc[NB][2];
+            double acc[MPW][NB][2];
 #pragma unroll
-            for (int kb = 0; kb < NB; ++kb) acc[kb][0] = acc[kb][1] = 0.0;
+            for (int m = 0; m < MPW; ++m) {
 #pragma unroll
-            for (int jb = 0; jb < ib; ++jb) {
-                const double *Lij = blk + kb_boff(ib, jb);
-                const double a0 = Lij[oA0], a1 = Lij[oA1];
+                for (int kb = 0; kb < NB; ++kb) acc[m][kb][0] = acc[m][kb][1] = 0.0;
 #pragma unroll
-                for (int kb = 0; kb <= jb; ++kb) {
-                    const double *Xjk = blk + kb_boff(jb, kb);
-                    dmma884(acc[kb][0], acc[kb][1], a0, Xjk[oT0]);
-                    dmma884(acc[kb][0], acc[kb][1], a1, Xjk[oT1]);
+                for (int jb = 0; jb < ib; ++jb) {
+                    const double *Lij = blk[m] + kb_boff(ib, jb);
+                    const double a0 = Lij[oA0], a1 = Lij[oA1];
+#pragma unroll
+                    for (int kb = 0; kb <= jb; ++kb) {
+                        const double *Xjk = blk[m] + kb_boff(jb, kb);
+                        dmma884(acc[m][kb][0], acc[m][kb][1], a0, Xjk[oT0]);
+                        dmma884(acc[m][kb][0], acc[m][kb][1], a1, Xjk[oT1]);
+                    }
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int kb = 0; kb < ib; ++kb)
-                *reinterpret_cast<double2 *>(blk + kb_boff(ib, kb) + oC) = make_double2(acc[kb][0], acc[kb][1]);
-            __syncwarp();
-            const double *Xii = blk + kb_boff(ib, ib);
-            const double xa0 = Xii[oA0], xa1 = Xii[oA1];
+            for (int m = 0; m < MPW; ++m)
 #pragma unroll
-            for (int kb = 0; kb < ib; ++kb) {
-                const double *S = blk + kb_boff(ib, kb);
-                acc[kb][0] = acc[kb][1] = 0.0;
-                dmma884(acc[kb][0], acc[kb][1], xa0, S[oT0]);
-                dmma884(acc[kb][0], acc[kb][1], xa1, S[oT1]);
+                for (int kb = 0; kb < ib; ++kb)
+                    *reinterpret_cast<double2 *>(blk[m] + kb_boff(ib, kb) + oC) = make_double2(acc[m][kb][0], acc[m][kb][1]);
+            __syncwarp();
+#pragma unroll
+            for (int m = 0; m < MPW; ++m) {
+                const double *Xii = blk[m] + kb_boff(ib, ib);
+                const double xa0 = Xii[oA0], xa1 = Xii[oA1];
+#pragma unroll
+                for (int kb = 0; kb < ib; ++kb) {
+                    const double *S = blk[m] + kb_boff(ib, kb);
+                    acc[m][kb][0] = acc[m][kb][1] = 0.0;
+                    dmma884(acc[m][kb][0], acc[m][kb][1], xa0, S[oT0]);
+                    dmma884(acc[m][kb][0], acc[m][kb][1], xa1, S[oT1]);
+                }
             }
             __syncwarp();
 #pragma unroll
-            for (int kb = 0; kb < ib; ++kb)
-                *reinterpret_cast<double2 *>(blk + kb_boff(ib, kb) + oC) = make_double2(-acc[kb][0], -acc[kb][1]);
+            for (int m = 0; m < MPW; ++m)
+#pragma unroll
+                for (int kb = 0; kb < ib; ++kb)
+                    *reinterpret_cast<double2 *>(blk[m] + kb_boff(ib, kb) + oC) =
+                        make_double2(-acc[m][kb][0], -acc[m][kb][1]);
             __syncwarp();
         }
 
         // ---- 3. Sigma = X^T X (lower blocks, diagonal blocks come out full):  S_ij = sum_{k >= i} X_ki^T X_kj
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
-            double acc[NB][2];
+            double acc[MPW][NB][2];
 #pragma unroll
-            for (int j = 0; j < NB; ++j) acc[j][0] = acc[j][1] = 0.0;
+            for (int m = 0; m < MPW; ++m) {
 #pragma unroll
-            for (int k = i; k < NB; ++k) {
-                const double *Xki = blk + kb_boff(k, i);
-                const double a0 = Xki[oT0], a1 = Xki[oT1];
+                for (int j = 0; j < NB; ++j) acc[m][j][0] = acc[m][j][1] = 0.0;
 #pragma unroll
-                for (int j = 0; j <= i; ++j) {
-                    const double *Xkj = blk + kb_boff(k, j);
-                    dmma884(acc[j][0], acc[j][1], a0, Xkj[oT0]);
-                    dmma884(acc[j][0], acc[j][1], a1, Xkj[oT1]);
+                for (int k = i; k < NB; ++k) {
+                    const double *Xki = blk[m] + kb_boff(k, i);
+                    const double a0 = Xki[oT0], a1 = Xki[oT1];
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        const double *Xkj = blk[m] + kb_boff(k, j);
+                        dmma884(acc[m][j][0], acc[m][j][1], a0, Xkj[oT0]);
+                        dmma884(acc[m][j][0], acc[m][j][1], a1, Xkj[oT1]);
+                    }
                 }
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j <= i; ++j)
-                *reinterpret_cast<double2 *>(blk + kb_boff(i, j) + oC) = make_double2(acc[j][0], acc[j][1]);
+            for (int m = 0; m < MPW; ++m)
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                    *reinterpret_cast<double2 *>(blk[m] + kb_boff(i, j) + oC) = make_double2(acc[m][j][0], acc[m][j][1]);
         }
         __syncwarp();
 
         // ---- zbar = Sigma eta on the tensor cores: B = eta_j broadcast over the 8 columns, so every accumulator
         //      column holds the block row's part of z
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            double z0 = 0.0, z1 = 0.0;
+        for (int m = 0; m < MPW; ++m) {
 #pragma unroll
-            for (int j = 0; j < NB; ++j) {
-                const double *B = blk + (j <= i ? kb_boff(i, j) : kb_boff(j, i));
-                const double a0 = B[j <= i ? oA0 : oT0], a1 = B[j <= i ? oA1 : oT1];
-                dmma884(z0, z1, a0, eta[j * 8 + qd]);
-                dmma884(z0, z1, a1, eta[j * 8 + qd + 4]);
+            for (int i = 0; i < NB; ++i) {
+                double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const double *B = blk[m] + (j <= i ? kb_boff(i, j) : kb_boff(j, i));
+                    const double a0 = B[j <= i ? oA0 : oT0], a1 = B[j <= i ? oA1 : oT1];
+                    dmma884(z0, z1, a0, eta[m][j * 8 + qd]);
+                    dmma884(z0, z1, a1, eta[m][j * 8 + qd + 4]);
+                }
+                if (qd == 0) zv[m][i * 8 + gid] = z0;
             }
-            if (qd == 0) zv[i * 8 + gid] = z0;
         }
         __syncwarp();
-        const double ldsum = ok ? -fma((double)esum, 0.69314718055994530942, log(mant)) : __longlong_as_double(0x7ff8000000000000LL);
 
         // ---- outputs: [<zz^T> packed | pad (left as it is: zeros) | zbar], optional Sigma, log-det
-        double *sg = (Sig != nullptr) ? (Sig + n * T::P) : nullptr;
+#pragma unroll
+        for (int m = 0; m < MPW; ++m) {
+            const double ldsum = ok[m] ? -fma((double)esum[m], 0.69314718055994530942, log(mant[m]))
+                                       : __longlong_as_double(0x7ff8000000000000LL);
+            if (!valid[m]) continue;                             // warp-uniform
+            const long long n = nrow[m];
+            double *sg = (Sig != nullptr) ? (Sig + n * T::P) : nullptr;
 #pragma unroll 4
-        for (int p = lane; p < T::P; p += 32) {
-            const uint32_t t = tab[p];
-            const double s = blk[t & 0xfff];
-            const double m = fma(zv[(t >> 12) & 63], zv[t >> 18], s);
-            row[IO::POFF + p] = (io_t)m;
-            if (F32) store_split3(MP + n * IO::PITCH + IO::POFF + p, (size_t)N * IO::PITCH, (float)m);
-            if (sg) sg[p] = s;
-            if (T::ZS) csum[p] += m;
-        }
-        for (int c = lane; c < Q; c += 32) {
-            const double z = zv[c];
-            row[IO::ZOFF + c] = (io_t)z;
-            if (F32) store_split3(MP + n * IO::PITCH + IO::ZOFF + c, (size_t)N * IO::PITCH, (float)z);
-            if (T::ZS) csum[T::PP + c] += z;
-        }
-        if (lane == 0) {
-            logdet[n] = ldsum;
-            s_qld += 0.5 / ldsum;
-            s_ld += ldsum;
-            s_n += 1.0;
-            if (!(ldsum - ldsum == 0.0)) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);   // NaN / inf <=> a pivot was <= 0
+            for (int p = lane; p < T::P; p += 32) {
+                const uint32_t t = tab[p];
+                const double s = blk[m][t & 0xfff];
+                const double mm = fma(zv[m][(t >> 12) & 63], zv[m][t >> 18], s);
+                row[m][IO::POFF + p] = (io_t)mm;
+                if (F32) store_split3(MP + n * IO::PITCH + IO::POFF + p, (size_t)N * IO::PITCH, (float)mm);
+                if (sg) sg[p] = s;
+                if (T::ZS) csum[p] += mm;
+            }
+            for (int c = lane; c < Q; c += 32) {
+                const double z = zv[m][c];
+                row[m][IO::ZOFF + c] = (io_t)z;
+                if (F32) store_split3(MP + n * IO::PITCH + IO::ZOFF + c, (size_t)N * IO::PITCH, (float)z);
+                if (T::ZS) csum[T::PP + c] += z;
+            }
+            if (lane == 0) {
+                logdet[n] = ldsum;
+                s_qld += 0.5 / ldsum;
+                s_ld += ldsum;
+                s_n += 1.0;
+                if (!(ldsum - ldsum == 0.0)) atomicAdd(&gl[PYVB_GL_NONPD], 1.0);   // NaN / inf <=> a pivot was <= 0
+            }
         }
         __syncwarp();
     }
@@ -349,7 +428,7 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
     }
     __syncthreads();
     double *out = zsums + (size_t)blockIdx.x * T::KW;
-    const double *w0 = reinterpret_cast<const double *>(smem_kb + T::TAB_B) + T::NBLK * 64 + 2 * Q;   // csum of warp 0
+    const double *w0 = reinterpret_cast<const double *>(smem_kb + T::TAB_B) + MPW * T::MAT_D;   // csum of warp 0
     for (int c = tid; c < T::KW; c += 32 * T::WARPS) {
         double a = 0.0;
         for (int w = 0; w < T::WARPS; ++w) a += w0[(size_t)w * T::WARP_D + c];   // [csum OROW | scalars 4] is contiguous
@@ -374,15 +453,15 @@ cudaError_t launch_blocked_q(long long N, void *MZ, double *Sig, double *logdet,
 }  // namespace
 
 int zsolve_blocked_blocks(long long N, int q) {
-    int warps = 8, occ = 2;
+    int warps = 8, occ = 2, mpw = 1;
     switch (q) {
-        case 8: warps = KB<8>::WARPS; occ = KB<8>::OCC; break;
-        case 16: warps = KB<16>::WARPS; occ = KB<16>::OCC; break;
-        case 32: warps = KB<32>::WARPS; occ = KB<32>::OCC; break;
-        case 64: warps = KB<64>::WARPS; occ = KB<64>::OCC; break;
+        case 8: warps = KB<8>::WARPS; occ = KB<8>::OCC; mpw = KB<8>::MPW; break;
+        case 16: warps = KB<16>::WARPS; occ = KB<16>::OCC; mpw = KB<16>::MPW; break;
+        case 32: warps = KB<32>::WARPS; occ = KB<32>::OCC; mpw = KB<32>::MPW; break;
+        case 64: warps = KB<64>::WARPS; occ = KB<64>::OCC; mpw = KB<64>::MPW; break;
         default: return 0;
     }
-    long long b = (N + warps - 1) / warps;
+    long long b = (N + (long long)mpw * warps - 1) / ((long long)mpw * warps);
     if (b > 148LL * occ) b = 148LL * occ;
     if (b < 1) b = 1;
     return (int)b;
