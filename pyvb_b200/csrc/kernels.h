@@ -57,6 +57,14 @@ int zsolve_blocked_blocks(long long N, int q);
 int zsolve_blocked_kw(int q);
 cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl,
                                   double *zsums, cudaStream_t st);
+int k2_impl(int q);   // 0 register-resident, 1 blocked tensor-core, 2 thread per matrix (PYVB_K2 overrides)
+// thread-per-matrix K2 (kernels_k2t.cu): q in {8, 16}
+int zsolve_tpm_blocks(long long N, int q);
+int zsolve_tpm_kw(int q);
+cudaError_t launch_zsolve_tpm(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
+                              cudaStream_t st);
+cudaError_t launch_zsolve_tpm_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
+                                  double *zsums, cudaStream_t st);
 cudaError_t launch_zsolve_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
                               double *zsums, cudaStream_t st);
 int stats_dmma_nchunks(long long N, int D, int q);

@@ -620,24 +620,31 @@ static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double 
     return cudaGetLastError();
 }
 
-// Which batched solve runs for this q: the blocked tensor-core kernel (kernels_k2.cu) or the register-resident
-// one above.  q = 64 only exists blocked; PYVB_K2=blocked / PYVB_K2=reg overrides the default for the others.
-static bool k2_blocked(int q) {
+// Which batched solve runs for this q: 0 = register-resident (lane per matrix row, above), 1 = blocked tensor-core
+// kernel (kernels_k2.cu), 2 = thread per matrix (kernels_k2t.cu).  q = 64 only exists blocked.  PYVB_K2 = reg /
+// blocked / tpm overrides the default (measured per 1M rows, FP64: q = 16: 1.62 / 2.0 / see DESIGN ms; q = 32: 9.0 / 5.8).
+int k2_impl(int q) {
     const char *e = getenv("PYVB_K2");               // read per call: tests flip it
-    const int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 2 : 0;
-    if (q == 64) return true;
-    if (mode == 1) return true;
-    if (mode == 2) return false;
-    return q >= 32;                                  // measured: q = 32 6.4 ms vs 9.0 ms per 1M rows; q <= 16 the other way
+    int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : -1;
+    if (q == 64) return 1;
+    if (mode == 2 && q > 16) mode = -1;
+    if (mode >= 0) return mode;
+    return q >= 32 ? 1 : 2;
 }
 
 void zsolve_partials(long long N, int q, int &nblk, int &kw) {
     long long b = 0, r = 0;
     nblk = kw = 0;
     if (N <= 0) return;
-    if (k2_blocked(q)) {
+    const int impl = k2_impl(q);
+    if (impl == 1) {
         kw = zsolve_blocked_kw(q);
         nblk = kw > 0 ? zsolve_blocked_blocks(N, q) : 0;
+        return;
+    }
+    if (impl == 2) {
+        kw = zsolve_tpm_kw(q);
+        nblk = zsolve_tpm_blocks(N, q);
         return;
     }
     switch (q) {
@@ -684,7 +691,9 @@ cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long l
 cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
                           cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    if (k2_blocked(q)) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st);
+    const int impl = k2_impl(q);
+    if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st);
+    if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st);
     switch (q) {
         case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);
         case 16: return launch_zsolve_q<16>(N, MZ, Sig, logdet, gl, zsums, st);
