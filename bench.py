@@ -381,7 +381,10 @@ def run_ours(a):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath)).get("zstep_dram_bytes_per_launch")
+            # measured DRAM bytes per row of K1 (ncu --set full at N = 151,552 rows) scaled to this launch's rows
+            tj = json.load(open(tpath))
+            traffic = tj.get("zstep_dmma%d_dram_bytes_per_row" % a.q)
+            traffic = traffic * a.N if traffic is not None else None
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "kernel": kname,
