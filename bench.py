@@ -27,8 +27,8 @@ UNIT = "rows*iters/s"
 
 
 def workload_name(a):
-    return "VB-PCA missing data N=%d (per GPU) D=%d q=%d %d%% missing FP64 mode=%s" % (
-        a.N, a.D, a.q, int(round(a.missing * 100)), a.mode)
+    return "VB-PCA missing data N=%d (per GPU) D=%d q=%d %d%% missing FP64 mode=%s%s" % (
+        a.N, a.D, a.q, int(round(a.missing * 100)), a.mode, " ARD" if getattr(a, "ard", False) else "")
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -279,7 +279,7 @@ def run_ours(a):
 
     X = make_data(torch, a.N, a.D, a.q, a.missing, 1234 + rank, dev)
     eng = PlateEngine(X, a.q, mode=a.mode, algo=a.algo, keep_sigma=False, distributed=(world > 1),
-                      row_offset=rank * a.N, device=dev)
+                      row_offset=rank * a.N, device=dev, ard=a.ard)
     del X
     eng.init_random(seed=4321, rank=rank)
     if os.environ.get("PYVB_NOCOMM"):          # diagnosis only: time the sweeps without the exchange
@@ -442,6 +442,7 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "generic", "dmma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-f32", action="store_true", help="skip the FP32-variant leg")
+    ap.add_argument("--ard", action="store_true", help="ARD Gamma precisions per latent column (config 4)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

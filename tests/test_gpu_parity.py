@@ -100,14 +100,17 @@ def test_generic_vs_oracle(eng, shape, mode):
     e.check()
 
 
-def test_ard_modeB_vs_oracle(eng):
-    N, D, q = 400, 24, 5
+@pytest.mark.parametrize("shape,algo", [((400, 24, 5), "generic"), ((600, 64, 64), "dmma"), ((900, 128, 16), "dmma")])
+def test_ard_modeB_vs_oracle(eng, shape, algo):
+    """ARD Gamma precisions per latent column (BASELINE config 4 is this at D = 512, q = 64): Gamma(d, a0, b0) as the
+    precision parent of every W column, /root/reference/src/pyvb/nodes/nodes_todo.py:113-138."""
+    N, D, q = shape
     X = synth_pca(N, D, q, 0.25, seed=9)
     init = rand_init(N, D, q, seed=2)
     init["al_qb"] = np.linspace(0.5, 1.5, q)
     o = PlateOracle(X, q, mode="B", ard=True)
     o.load_state(init)
-    e = eng(X, q, mode="B", ard=True, algo="generic")
+    e = eng(X, q, mode="B", ard=True, algo=algo)
     e.set_state(init)
     for it in range(5):
         ref, got = o.iterate(), e.iterate()
