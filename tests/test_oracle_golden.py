@@ -80,3 +80,21 @@ def test_modeB_elbo_monotone_late():
     tr = o.learn(30)
     assert np.all(np.isfinite(tr))
     assert np.all(np.diff(tr[10:]) > -1e-6 * abs(tr[-1]))
+
+
+@pytest.mark.parametrize("name", ["lds_a.npz", "lds_b.npz", "lds_c.npz"])
+def test_lds_oracle_matches_literal_reference(name):
+    """The LDS restatement (oracle/lds_oracle.py) against the literal reference's smoother, iteration by iteration
+    (fixtures: oracle/gen_golden_lds.py running examples/Linear_Dynamic_System.py:47-76)."""
+    from oracle.lds_oracle import LDSOracle
+    g = load_golden(name)
+    q = int(g["q"])
+    o = LDSOracle(g["Y"], q)
+    o.load_state({k: g["init_" + k] for k in LDSOracle.KEYS})
+    for it in range(int(g["niters"])):
+        o.iterate()
+        for k in LDSOracle.KEYS:
+            ref = g["it%d_%s" % (it, k)]
+            got = getattr(o, k)[0]
+            err = np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1e-300)
+            assert err < 1e-11, (name, it, k, err)
