@@ -234,6 +234,20 @@ int pyvb_stats_f32(long long N, long long nalloc, int D, int q, const void *plan
                    void *ws, size_t ws_bytes, double *xcache, const double *zsums, const pyvb_peers *peers /* host */,
                    void *stream);
 
+/* ---- VB smoother of a linear dynamic system, batched over B independent sequences (BASELINE config 5) ----
+ * Replaces the sweep of examples/Linear_Dynamic_System.py:69-76 for every sequence: all X_t.update() forwards, all
+ * backwards (nodes/gaussian.py:102-123 + nodes/node.py:203-227), the columns of A and C (nodes/nodes_todo.py:43-62),
+ * Q.update(), R.update() (DiagonalGamma, nodes/nodes_todo.py:187-190) -- `niters` whole iterations in one launch,
+ * one warp per sequence, the sequence resident in shared memory.  q, d <= 8; 3 <= T <= pyvb_lds_max_len().
+ *   Y [B][T][d] observations;  X [B][T][q] state means (in/out);  Xcov3 [B][3][q][q] out: the posterior covariances
+ *   of X_0, X_1..X_{T-2}, X_{T-1} (they do not depend on t otherwise);  A, Avar [B][q][q] (row k, column i: mean and
+ *   variance of A[k][i]);  C, Cvar [B][d][q];  Qa, Qb [B][q];  Ra, Rb [B][d]  (all in/out).
+ *   status: device double, incremented for every sequence with a non-positive-definite posterior precision. */
+int pyvb_lds_max_len(void);
+int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A, double *Avar,
+                         double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb, double alpha0,
+                         double a0, double b0, int niters, double *status, void *stream);
+
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
  * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.
  * bench.py times it with CUDA events to obtain the FP64 tensor roofline of the box it runs on. */

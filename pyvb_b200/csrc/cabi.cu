@@ -301,6 +301,23 @@ int pyvb_stats_f32(long long N, long long nalloc, int D, int q, const void *plan
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
 }
 
+int pyvb_lds_max_len(void) {
+    int T = 16;
+    while (lds_smem_bytes(T + 1) <= 227 * 1024) ++T;
+    return T;
+}
+
+int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A, double *Avar,
+                         double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb, double alpha0,
+                         double a0, double b0, int niters, double *status, void *stream) {
+    ARG(B >= 0 && q >= 1 && q <= 8 && d >= 1 && d <= 8 && niters >= 0, "B, q (<= 8), d (<= 8), niters");
+    ARG(T >= 3 && T <= pyvb_lds_max_len(), "T (3 .. pyvb_lds_max_len())");
+    ARG(Y && X && Xcov3 && A && Avar && C && Cvar && Qa && Qb && Ra && Rb && status, "null pointer");
+    cudaError_t e = launch_lds_iterate(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb, alpha0, a0, b0, niters,
+                                       status, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "lds_iterate");
+}
+
 int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch, void *stream) {
     ARG(blocks >= 1 && iters >= 1 && scratch, "blocks, iters, scratch");
     cudaError_t e = launch_bench_dmma(blocks, iters, scratch, (cudaStream_t)stream);

@@ -89,6 +89,12 @@ void zsolve_partials_f32(long long N, int q, int &nblk, int &kw);
 cudaError_t launch_stats_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *MP, double *ws,
                              int nchunks, cudaStream_t st);
 
+// ---- LDS smoother, batched over sequences (kernels_lds.cu) ----
+size_t lds_smem_bytes(int T);
+cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
+                               double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
+                               double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st);
+
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
 
 }  // namespace pyvb

@@ -1,0 +1,291 @@
+// VB smoother of a linear dynamic system, batched over independent sequences (BASELINE config 5): one WARP per
+// sequence, the whole sequence resident in shared memory, whole VB iterations inside one launch.
+//
+// Reference: examples/Linear_Dynamic_System.py:47-76 -- per iteration all X_t forwards, all X_t backwards, the A
+// columns, the C columns, Q, R -- i.e. per node
+//   X_t   Gaussian.update (nodes/gaussian.py:102-123) with Multiplication.pass_up_m1_m2 (nodes/node.py:203-227):
+//         prec_t = Qbar (I at t = 0) + <A^T Qbar A> [t < T-1] + <C^T Rbar C>,
+//         mean_t = prec_t^-1 (Qbar A x_{t-1} + A^T Qbar x_{t+1} + C^T Rbar y_t)
+//   A_i, C_i   hstack.pass_up_m1_m2 (nodes/nodes_todo.py:43-62), Gauss-Seidel over the columns
+//   Q, R  DiagonalGamma.update (nodes/nodes_todo.py:187-190)
+// The precisions do not depend on the states: three distinct q x q matrices per sequence and iteration (t = 0,
+// interior, t = T-1).  They are factored and inverted with the warp-cooperative 8 x 8 Cholesky of the batched solve
+// (chol8.cuh), the smoother gain K_s = Sigma_s [Qbar A | A^T Qbar | C^T Rbar] (8 x 24) is spread over the lanes
+// (lane = row i, quarter p: 6 coefficients), and one Gauss-Seidel step is 6 FMAs + two shuffle reductions per lane.
+// State and observation dimensions are padded to 8 inside the kernel (q, d <= 8).
+#include "chol8.cuh"
+#include "common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace pyvb {
+
+namespace {
+
+constexpr int LW = 4;                       // warps (sequences) per CTA
+
+// per-warp shared memory (doubles): xs [(T + 2)][8] (one zero row before and after), ys [T][8], then the small arrays
+__host__ __device__ inline size_t lds_warp_doubles(int T) { return (size_t)(T + 2) * 8 + (size_t)T * 8 + 64 * 13; }
+
+__global__ void __launch_bounds__(32 * LW)
+lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, double *__restrict__ X,
+                   double *__restrict__ Xcov3, double *__restrict__ A, double *__restrict__ Avar, double *__restrict__ C,
+                   double *__restrict__ Cvar, double *__restrict__ Qa, double *__restrict__ Qb, double *__restrict__ Ra,
+                   double *__restrict__ Rb, double alpha0, double a0, double b0, int niters, double *status) {
+    extern __shared__ __align__(16) double smem_l[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, qd = lane & 3;
+    double *base = smem_l + (size_t)warp * lds_warp_doubles(T);
+    double *xs = base + 8;                                  // xs[t * 8 + i], t = -1 .. T valid (zero rows at the ends)
+    double *ys = base + (size_t)(T + 2) * 8;
+    double *pA = ys + (size_t)T * 8;                        // [k][i]
+    double *pAv = pA + 64, *pC = pAv + 64, *pCv = pC + 64;
+    double *Sg = pCv + 64;                                  // [3][64]: Sigma_0, Sigma_interior, Sigma_{T-1}
+    double *tmp = Sg + 192;                                 // [64]
+    double *sSA = tmp + 64, *sSC = sSA + 64, *sXX1 = sSC + 64, *sYX = sXX1 + 64;
+    double *qbar = sYX + 64, *rbar = qbar + 8, *yy = rbar + 8, *xx0 = yy + 8;   // [8] each
+
+    for (int b = blockIdx.x * LW + warp; b < B; b += gridDim.x * LW) {
+        // ---- load the sequence and its parameters (padded to 8 x 8)
+        for (int i = lane; i < (T + 2) * 8; i += 32) base[i] = 0.0;
+        for (int i = lane; i < T * 8; i += 32) ys[i] = 0.0;
+        for (int i = lane; i < 64 * 4; i += 32) pA[i] = 0.0;
+        __syncwarp();
+        const double *Yb = Y + (size_t)b * T * d;
+        double *Xb = X + (size_t)b * T * q;
+        for (int i = lane; i < T * d; i += 32) ys[(i / d) * 8 + (i % d)] = Yb[i];
+        for (int i = lane; i < T * q; i += 32) xs[(i / q) * 8 + (i % q)] = Xb[i];
+        for (int i = lane; i < q * q; i += 32) {
+            pA[(i / q) * 8 + (i % q)] = A[(size_t)b * q * q + i];
+            pAv[(i / q) * 8 + (i % q)] = Avar[(size_t)b * q * q + i];
+        }
+        for (int i = lane; i < d * q; i += 32) {
+            pC[(i / q) * 8 + (i % q)] = C[(size_t)b * d * q + i];
+            pCv[(i / q) * 8 + (i % q)] = Cvar[(size_t)b * d * q + i];
+        }
+        double qb_l = (lane < q) ? Qb[(size_t)b * q + lane] : 1.0;            // lane k: Q row k; lane 8 + k: R row k
+        double qa_l = (lane < q) ? Qa[(size_t)b * q + lane] : 1.0;
+        if (lane >= 8 && lane < 8 + d) {
+            qb_l = Rb[(size_t)b * d + lane - 8];
+            qa_l = Ra[(size_t)b * d + lane - 8];
+        }
+        bool ok = true;
+        __syncwarp();
+
+        for (int iter = 0; iter < niters; ++iter) {
+            // ---- expected precisions; padded state dimensions get unit precision (decoupled)
+            if (lane < 8) qbar[lane] = (lane < q) ? qa_l / qb_l : 1.0;
+            if (lane >= 8 && lane < 16) rbar[lane - 8] = (lane - 8 < d) ? qa_l / qb_l : 0.0;
+            __syncwarp();
+            // ---- the three posterior precisions in the accumulator layout (lane: row gid, columns 2qd, 2qd + 1)
+            double c0[3], c1[3], x0[3], x1[3], lp[3] = {1.0, 1.0, 1.0};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = gid, j = 2 * qd + e;
+                double aqa = 0.0, crc = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    aqa = fma(qbar[k] * pA[k * 8 + i], pA[k * 8 + j], aqa);
+                    crc = fma(rbar[k] * pC[k * 8 + i], pC[k * 8 + j], crc);
+                    if (i == j) {
+                        aqa = fma(qbar[k], pAv[k * 8 + i], aqa);
+                        crc = fma(rbar[k], pCv[k * 8 + i], crc);
+                    }
+                }
+                const double eye = (i == j) ? 1.0 : 0.0, qd_ = (i == j) ? qbar[i] : 0.0;
+                const double p0 = eye + aqa + crc, pi = qd_ + aqa + crc, pT = qd_ + crc;
+                if (e == 0) { c0[0] = p0; c0[1] = pi; c0[2] = pT; } else { c1[0] = p0; c1[1] = pi; c1[2] = pT; }
+            }
+            diag_chol_inv<3>(c0, c1, x0, x1, lp);
+            ok = ok && (lp[0] - lp[0] == 0.0) && (lp[1] - lp[1] == 0.0) && (lp[2] - lp[2] == 0.0);
+            // Sigma_s = X_s^T X_s
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                tmp[gid * 8 + 2 * qd] = x0[s];
+                tmp[gid * 8 + 2 * qd + 1] = x1[s];
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int i = gid, j = 2 * qd + e;
+                    double sg = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) sg = fma(tmp[k * 8 + i], tmp[k * 8 + j], sg);
+                    Sg[s * 64 + i * 8 + j] = sg;
+                }
+                __syncwarp();
+            }
+            // ---- smoother gains: lane (row i = gid, quarter p = qd) holds K_s[i][6p .. 6p+5],
+            //      inputs v = [x_{t-1} (8) | x_{t+1} (8) | y_t (8)]
+            double kc[3][6];
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const int c = qd * 6 + m;
+                double k0 = 0.0, k1 = 0.0, k2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    double mjc;
+                    if (c < 8) mjc = qbar[j] * pA[j * 8 + c];                        // (Qbar A)[j][c]
+                    else if (c < 16) mjc = pA[(c - 8) * 8 + j] * qbar[c - 8];        // (A^T Qbar)[j][c-8]
+                    else mjc = pC[(c - 16) * 8 + j] * rbar[c - 16];                  // (C^T Rbar)[j][c-16]
+                    k0 = fma(Sg[gid * 8 + j], mjc, k0);
+                    k1 = fma(Sg[64 + gid * 8 + j], mjc, k1);
+                    k2 = fma(Sg[128 + gid * 8 + j], mjc, k2);
+                }
+                kc[0][m] = (c < 8) ? 0.0 : k0;                                      // t = 0: no x_{t-1} term
+                kc[1][m] = k1;
+                kc[2][m] = (c >= 8 && c < 16) ? 0.0 : k2;                           // t = T-1: no x_{t+1} term
+            }
+            // offsets of this lane's six inputs relative to row t: x rows t-1 / t+1 live in xs, y in ys
+            const double *src[6];
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const int c = qd * 6 + m;
+                src[m] = (c < 8) ? (xs + c - 8) : (c < 16) ? (xs + c) : (ys + c - 16);
+            }
+            auto step = [&](int t, const double (&kk)[6]) {
+                double a = 0.0, bsum = 0.0;
+#pragma unroll
+                for (int m = 0; m < 6; m += 2) {
+                    a = fma(kk[m], src[m][t * 8], a);
+                    bsum = fma(kk[m + 1], src[m + 1][t * 8], bsum);
+                }
+                a += bsum;
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                if (qd == 0) xs[t * 8 + gid] = a;                   // row t is not an input of step t
+                __syncwarp();
+            };
+            step(0, kc[0]);
+            for (int t = 1; t < T - 1; ++t) step(t, kc[1]);
+            step(T - 1, kc[2]);
+            step(T - 1, kc[2]);
+            for (int t = T - 2; t >= 1; --t) step(t, kc[1]);
+            step(0, kc[0]);
+
+            // ---- sufficient statistics of the sequence; lane owns entries (gid, 2qd), (gid, 2qd + 1)
+            double sxx0 = 0.0, sxx1 = 0.0, sx10 = 0.0, sx11 = 0.0, syx0 = 0.0, syx1 = 0.0, syy = 0.0;
+            double xp0 = 0.0, xp1 = 0.0;                            // x_{t-1}[2qd], x_{t-1}[2qd+1]
+            for (int t = 0; t < T; ++t) {
+                const double xg = xs[t * 8 + gid], yg = ys[t * 8 + gid];
+                const double2 xj = *reinterpret_cast<const double2 *>(xs + t * 8 + 2 * qd);
+                sxx0 = fma(xg, xj.x, sxx0);
+                sxx1 = fma(xg, xj.y, sxx1);
+                sx10 = fma(xg, xp0, sx10);                          // t = 0: x_{-1} = 0
+                sx11 = fma(xg, xp1, sx11);
+                syx0 = fma(yg, xj.x, syx0);
+                syx1 = fma(yg, xj.y, syx1);
+                syy = fma(yg, yg, syy);
+                xp0 = xj.x;
+                xp1 = xj.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int i = gid, j = 2 * qd + e;
+                const double sxx = e ? sxx1 : sxx0;
+                const double sc = sxx + Sg[i * 8 + j] + (double)(T - 2) * Sg[64 + i * 8 + j] + Sg[128 + i * 8 + j];
+                sSC[i * 8 + j] = sc;
+                sSA[i * 8 + j] = sc - (xs[(T - 1) * 8 + i] * xs[(T - 1) * 8 + j] + Sg[128 + i * 8 + j]);
+                sXX1[i * 8 + j] = e ? sx11 : sx10;
+                sYX[i * 8 + j] = e ? syx1 : syx0;
+            }
+            if (qd == 0) {
+                yy[gid] = syy;
+                xx0[gid] = xs[gid] * xs[gid] + Sg[gid * 8 + gid];   // <x_0 x_0^T>_kk
+            }
+            __syncwarp();
+
+            // ---- parameters: lane k < 8 owns row k of A (and Q_k), lane 8 + k row k of C (and R_k)
+            if (lane < 16) {
+                const bool isA = lane < 8;
+                const int k = isA ? lane : lane - 8;
+                const bool live = isA ? (k < q) : (k < d);
+                double *pm = isA ? pA : pC, *pv = isA ? pAv : pCv;
+                const double *S = isA ? sSA : sSC, *cross = isA ? sXX1 : sYX;
+                const double lam = isA ? qbar[k] : rbar[k];
+                if (live) {
+                    double a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] = pm[k * 8 + j];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < q) {
+                            const double prec = alpha0 + lam * S[i * 8 + i];
+                            double m2 = cross[k * 8 + i];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                if (j != i) m2 = fma(-S[i * 8 + j], a[j], m2);
+                            a[i] = lam * m2 / prec;
+                            pv[k * 8 + i] = 1.0 / prec;
+                        }
+                    }
+                    double quad = 0.0, lin = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        pm[k * 8 + i] = a[i];
+                        lin = fma(a[i], cross[k * 8 + i], lin);
+                        quad = fma(pv[k * 8 + i], S[i * 8 + i], quad);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) quad = fma(a[i] * a[j], S[i * 8 + j], quad);
+                    }
+                    if (isA) {
+                        qb_l = b0 + 0.5 * (sSC[k * 8 + k] - xx0[k]) + 0.5 * quad - lin;
+                        qa_l = a0 + 0.5 * (double)(T - 1);
+                    } else {
+                        qb_l = b0 + 0.5 * yy[k] + 0.5 * quad - lin;
+                        qa_l = a0 + 0.5 * (double)T;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- write back
+        for (int i = lane; i < T * q; i += 32) Xb[i] = xs[(i / q) * 8 + (i % q)];
+        for (int i = lane; i < q * q; i += 32) {
+            A[(size_t)b * q * q + i] = pA[(i / q) * 8 + (i % q)];
+            Avar[(size_t)b * q * q + i] = pAv[(i / q) * 8 + (i % q)];
+        }
+        for (int i = lane; i < d * q; i += 32) {
+            C[(size_t)b * d * q + i] = pC[(i / q) * 8 + (i % q)];
+            Cvar[(size_t)b * d * q + i] = pCv[(i / q) * 8 + (i % q)];
+        }
+        for (int i = lane; i < 3 * q * q; i += 32) {
+            const int s = i / (q * q), r = i % (q * q);
+            Xcov3[(size_t)b * 3 * q * q + i] = Sg[s * 64 + (r / q) * 8 + (r % q)];
+        }
+        if (lane < q) {
+            Qa[(size_t)b * q + lane] = qa_l;
+            Qb[(size_t)b * q + lane] = qb_l;
+        }
+        if (lane >= 8 && lane < 8 + d) {
+            Ra[(size_t)b * d + lane - 8] = qa_l;
+            Rb[(size_t)b * d + lane - 8] = qb_l;
+        }
+        if (lane == 0 && !ok) atomicAdd(status, 1.0);              // a posterior precision was not positive definite
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+size_t lds_smem_bytes(int T) { return (size_t)LW * lds_warp_doubles(T) * sizeof(double); }
+
+cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
+                               double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
+                               double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st) {
+    if (B <= 0 || niters <= 0) return cudaSuccess;
+    const size_t smem = lds_smem_bytes(T);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(lds_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = (int)((227 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    long long blocks = ((long long)B + LW - 1) / LW;
+    if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
+    lds_iterate_kernel<<<(unsigned)blocks, 32 * LW, smem, st>>>(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb,
+                                                               alpha0, a0, b0, niters, status);
+    return cudaGetLastError();
+}
+
+}  // namespace pyvb
