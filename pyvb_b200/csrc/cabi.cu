@@ -303,7 +303,7 @@ int pyvb_stats_f32(long long N, long long nalloc, int D, int q, const void *plan
 
 int pyvb_lds_max_len(void) {
     int T = 16;
-    while (lds_smem_bytes(T + 1) <= 227 * 1024) ++T;
+    while (lds_smem_bytes(T + 1, 8) <= 227 * 1024) ++T;
     return T;
 }
 

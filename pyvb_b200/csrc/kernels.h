@@ -90,7 +90,7 @@ cudaError_t launch_stats_f32(long long N, long long nalloc, int D, int q, const 
                              int nchunks, cudaStream_t st);
 
 // ---- LDS smoother, batched over sequences (kernels_lds.cu) ----
-size_t lds_smem_bytes(int T);
+size_t lds_smem_bytes(int T, int d);
 cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
                                double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
                                double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st);

@@ -24,8 +24,11 @@ namespace {
 
 constexpr int LW = 4;                       // warps (sequences) per CTA
 
-// per-warp shared memory (doubles): xs [(T + 2)][8] (one zero row before and after), ys [T][8], then the small arrays
-__host__ __device__ inline size_t lds_warp_doubles(int T) { return (size_t)(T + 2) * 8 + (size_t)T * 8 + 64 * 13; }
+// per-warp shared memory (doubles): xs [(T + 2)][8] (one zero row before and after), ys [T][d] (+ 8: the padded
+// columns of the last row are read with zero coefficients), then the small arrays
+__host__ __device__ inline size_t lds_warp_doubles(int T, int d) {
+    return (size_t)(T + 2) * 8 + (((size_t)T * d + 8 + 1) & ~(size_t)1) + 64 * 13;
+}
 
 __global__ void __launch_bounds__(32 * LW)
 lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, double *__restrict__ X,
@@ -35,10 +38,10 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
     extern __shared__ __align__(16) double smem_l[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, qd = lane & 3;
-    double *base = smem_l + (size_t)warp * lds_warp_doubles(T);
+    double *base = smem_l + (size_t)warp * lds_warp_doubles(T, d);
     double *xs = base + 8;                                  // xs[t * 8 + i], t = -1 .. T valid (zero rows at the ends)
     double *ys = base + (size_t)(T + 2) * 8;
-    double *pA = ys + (size_t)T * 8;                        // [k][i]
+    double *pA = ys + (((size_t)T * d + 8 + 1) & ~(size_t)1);   // [k][i]
     double *pAv = pA + 64, *pC = pAv + 64, *pCv = pC + 64;
     double *Sg = pCv + 64;                                  // [3][64]: Sigma_0, Sigma_interior, Sigma_{T-1}
     double *tmp = Sg + 192;                                 // [64]
@@ -48,12 +51,12 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
     for (int b = blockIdx.x * LW + warp; b < B; b += gridDim.x * LW) {
         // ---- load the sequence and its parameters (padded to 8 x 8)
         for (int i = lane; i < (T + 2) * 8; i += 32) base[i] = 0.0;
-        for (int i = lane; i < T * 8; i += 32) ys[i] = 0.0;
+        for (int i = lane; i < T * d + 8; i += 32) ys[i] = 0.0;
         for (int i = lane; i < 64 * 4; i += 32) pA[i] = 0.0;
         __syncwarp();
         const double *Yb = Y + (size_t)b * T * d;
         double *Xb = X + (size_t)b * T * q;
-        for (int i = lane; i < T * d; i += 32) ys[(i / d) * 8 + (i % d)] = Yb[i];
+        for (int i = lane; i < T * d; i += 32) ys[i] = Yb[i];
         for (int i = lane; i < T * q; i += 32) xs[(i / q) * 8 + (i % q)] = Xb[i];
         for (int i = lane; i < q * q; i += 32) {
             pA[(i / q) * 8 + (i % q)] = A[(size_t)b * q * q + i];
@@ -137,17 +140,19 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
             }
             // offsets of this lane's six inputs relative to row t: x rows t-1 / t+1 live in xs, y in ys
             const double *src[6];
+            int str[6];                                             // row pitch of the input: 8 (states) or d (observations)
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 const int c = qd * 6 + m;
                 src[m] = (c < 8) ? (xs + c - 8) : (c < 16) ? (xs + c) : (ys + c - 16);
+                str[m] = (c < 16) ? 8 : d;
             }
             auto step = [&](int t, const double (&kk)[6]) {
                 double a = 0.0, bsum = 0.0;
 #pragma unroll
                 for (int m = 0; m < 6; m += 2) {
-                    a = fma(kk[m], src[m][t * 8], a);
-                    bsum = fma(kk[m + 1], src[m + 1][t * 8], bsum);
+                    a = fma(kk[m], src[m][t * str[m]], a);           // (padded observation columns: zero gain, finite data)
+                    bsum = fma(kk[m + 1], src[m + 1][t * str[m + 1]], bsum);
                 }
                 a += bsum;
                 a += __shfl_xor_sync(0xffffffffu, a, 1);
@@ -166,7 +171,7 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
             double sxx0 = 0.0, sxx1 = 0.0, sx10 = 0.0, sx11 = 0.0, syx0 = 0.0, syx1 = 0.0, syy = 0.0;
             double xp0 = 0.0, xp1 = 0.0;                            // x_{t-1}[2qd], x_{t-1}[2qd+1]
             for (int t = 0; t < T; ++t) {
-                const double xg = xs[t * 8 + gid], yg = ys[t * 8 + gid];
+                const double xg = xs[t * 8 + gid], yg = (gid < d) ? ys[t * d + gid] : 0.0;
                 const double2 xj = *reinterpret_cast<const double2 *>(xs + t * 8 + 2 * qd);
                 sxx0 = fma(xg, xj.x, sxx0);
                 sxx1 = fma(xg, xj.y, sxx1);
@@ -268,13 +273,13 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
 
 }  // namespace
 
-size_t lds_smem_bytes(int T) { return (size_t)LW * lds_warp_doubles(T) * sizeof(double); }
+size_t lds_smem_bytes(int T, int d) { return (size_t)LW * lds_warp_doubles(T, d) * sizeof(double); }
 
 cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
                                double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
                                double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st) {
     if (B <= 0 || niters <= 0) return cudaSuccess;
-    const size_t smem = lds_smem_bytes(T);
+    const size_t smem = lds_smem_bytes(T, d);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(lds_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
