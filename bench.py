@@ -33,14 +33,15 @@ def workload_name(a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """Polls NVML (clocks, power, throttle reasons) every ~20 ms from a thread while the timed region runs.
-    (Polling every 4 ms slowed the sweeps of a multi-GPU run by 0.28 ms each -- NVML queries disturb the peer
-    traffic of the exchange kernel; tools/comm_probe.sh.)"""
+    """Polls NVML (clocks, power, throttle reasons) from a thread while the timed region runs: about four samples
+    across the region (the interval comes from the warm-up's step time, 20 ms at least).  Every NVML poll stalls the
+    sweeps of a multi-GPU run by ~0.9 ms (the queries disturb the peer traffic of the exchange kernel: polling every
+    4 ms cost 0.28 ms per 7 ms sweep, tools/comm_probe.sh), so the samples are kept few."""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                "hw_power_brake": 0x80, "sync_boost": 0x10}
 
-    def __init__(self, index):
-        self.rows, self.ok, self._stop = [], False, False
+    def __init__(self, index, interval=0.02):
+        self.rows, self.ok, self._stop, self.interval = [], False, False, float(interval)
         try:
             import pynvml
             self.nv = pynvml
@@ -67,7 +68,7 @@ class ClockSampler(object):
                                   nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, rs))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(self.interval)
 
     def stop(self, t0, t1):
         if not self.ok:
@@ -290,10 +291,16 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
     for _ in range(max(a.warmup, 3)):
         eng.iterate_async()
+    w1.record()
     sync()
-    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("PYVB_NOSAMPLER")) else None
+    est_region_s = w0.elapsed_time(w1) / max(a.warmup, 3) * a.steps * 1e-3
+    sampler = (ClockSampler(local, interval=max(0.02, est_region_s / 4.0))
+               if (rank == 0 and not os.environ.get("PYVB_NOSAMPLER")) else None)
+    time.sleep(0.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
