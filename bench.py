@@ -33,10 +33,10 @@ def workload_name(a):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    """Polls NVML (clocks, power, throttle reasons) from a thread while the timed region runs: about four samples
-    across the region (the interval comes from the warm-up's step time, 20 ms at least).  Every NVML poll stalls the
-    sweeps of a multi-GPU run by ~0.9 ms (the queries disturb the peer traffic of the exchange kernel: polling every
-    4 ms cost 0.28 ms per 7 ms sweep, tools/comm_probe.sh), so the samples are kept few."""
+    """Polls NVML (clocks, power, throttle reasons) every 20 ms from a thread; the samples that fall inside the timed
+    region are reported.  It is created BEFORE the barrier that precedes the timed region: nvmlInit takes ~0.1 s, and
+    when only rank 0 paid it after the barrier every other rank's first exchange waited for rank 0 inside ITS timed
+    region (0.3-9 ms per sweep of apparent multi-GPU overhead, tools/comm_probe.sh)."""
     REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                "hw_power_brake": 0x80, "sync_boost": 0x10}
 
@@ -60,12 +60,18 @@ class ClockSampler(object):
         nv = self.nv
         while not self._stop:
             try:
-                try:
-                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.rows.append((time.time(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0, rs))
+                fields = os.environ.get("PYVB_SAMPLER_FIELDS", "crp")      # diagnosis: which query disturbs
+                rs, clk, pw = 0, 0, 0.0
+                if "r" in fields:
+                    try:
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                if "c" in fields:
+                    clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                if "p" in fields:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.rows.append((time.time(), clk, pw, rs))
             except Exception:
                 pass
             time.sleep(self.interval)
@@ -291,16 +297,10 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record()
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get("PYVB_NOSAMPLER")) else None
     for _ in range(max(a.warmup, 3)):
         eng.iterate_async()
-    w1.record()
     sync()
-    est_region_s = w0.elapsed_time(w1) / max(a.warmup, 3) * a.steps * 1e-3
-    sampler = (ClockSampler(local, interval=max(0.02, est_region_s / 4.0))
-               if (rank == 0 and not os.environ.get("PYVB_NOSAMPLER")) else None)
-    time.sleep(0.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
     e0.record()
