@@ -59,6 +59,7 @@ int pyvb_algo_supported(int algo, int D, int q) {
 
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo) {
     const StatLayout L(D, q);
+    if (N <= 0) return align256((L.len + PYVB_NSCAL) * sizeof(double));
     if (algo == PYVB_ALGO_F32) return align256((size_t)stats_f32_nchunks(N, D, q) * L.len * sizeof(double));
     int nch = stats_generic_nchunks(N);
     if (pick_algo(algo, D, q) == PYVB_ALGO_DMMA) {
@@ -128,10 +129,10 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
                    const double *P0, const double *h0, double *gl, double *Zbar, long long ldz, double *M2,
                    long long ldm, double *Sig, double *logdet, double *zsums, int algo, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    if (N == 0) return PYVB_OK;                      // an empty row block (e.g. an empty shard): nothing to update
     ARG(X && Gw && P0 && h0 && gl && Zbar && M2 && logdet, "null pointer");
     ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
     ARG(ldg >= gw_woff(q) + q + 1, "ldg");
-    if (N == 0) return PYVB_OK;
     const int a = pick_algo(algo, D, q);
     cudaError_t e;
     if (a == PYVB_ALGO_DMMA) {
@@ -154,6 +155,7 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
 int pyvb_zsolve_f64(long long N, int q, double *MZ, long long ldmz, double *Sig, double *logdet, double *gl,
                     double *zsums, void *stream) {
     ARG(N >= 0 && (q == 8 || q == 16 || q == 32 || q == 64), "N, q (8, 16, 32 or 64)");
+    if (N == 0) return PYVB_OK;
     ARG(MZ && logdet && gl, "null pointer");
     ARG(ldmz == pyvb_mz_pitch(q), "ldmz must equal pyvb_mz_pitch(q)");
     cudaError_t e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, (cudaStream_t)stream);
@@ -166,7 +168,18 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
                    int xcache_valid, const double *zsums, int zsums_valid, const pyvb_peers *peers, int algo,
                    void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
-    ARG(X && Zbar && M2 && logdet && stats && ws, "null pointer");
+    ARG(stats && ws, "null pointer");
+    if (N == 0) {
+        // an empty shard contributes zeros, but still takes part in the exchange
+        ARG(ws_bytes >= (StatLayout(D, q).len + PYVB_NSCAL) * sizeof(double), "workspace too small");
+        cudaError_t e0 = cudaMemsetAsync(ws, 0, (StatLayout(D, q).len + PYVB_NSCAL) * sizeof(double), (cudaStream_t)stream);
+        if (e0 == cudaSuccess)
+            e0 = launch_stats_reduce(D, q, (const double *)ws, 1, (const double *)ws + StatLayout(D, q).len, 1, stats,
+                                     NULL, 0, NULL, 0, 0, peers ? peers->bufs : NULL, peers ? peers->world : 1,
+                                     peers ? peers->rank : 0, peers ? peers->epoch : 0ULL, (cudaStream_t)stream);
+        return e0 == cudaSuccess ? PYVB_OK : cuda_fail(e0, "stats (empty shard)");
+    }
+    ARG(X && Zbar && M2 && logdet, "null pointer");
     ARG(ldx >= D && ldz >= q && ldm >= q * (q + 1) / 2, "ldx, ldz, ldm");
     ARG((Xorig == NULL) || (V != NULL && qldX != NULL), "mode A needs V and qldX with Xorig");
     ARG(ws_bytes >= pyvb_stats_workspace_bytes(N, D, q, algo), "workspace too small");
@@ -235,6 +248,7 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
                     const double *mu, const double *Zbar, long long ldz, const double *gl, double *Xhat, double *V,
                     double *qldX, void *stream) {
     ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    if (N == 0) return PYVB_OK;
     ARG(Xorig && Wbar && mu && Zbar && gl && Xhat && V && qldX, "null pointer");
     ARG(ldx >= D && ldz >= q, "ldx, ldz");
     cudaError_t e =
@@ -248,7 +262,9 @@ int pyvb_f32_poff(int q) { return f32_poff(q); }
 int pyvb_f32_supported(int D, int q) { return f32_supported(D, q) ? 1 : 0; }
 
 int pyvb_prepare_x_f32(long long N, int D, const double *X, long long ldx, void *planes, void *stream) {
-    ARG(N >= 0 && D >= 1 && X && planes && ldx >= D, "N, D, X, planes, ldx");
+    ARG(N >= 0 && D >= 1 && ldx >= D, "N, D, ldx");
+    if (N == 0) return PYVB_OK;
+    ARG(X && planes, "null pointer");
     cudaError_t e = launch_prepare_x_f32(N, D, X, ldx, planes, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "prepare_x_f32");
 }
@@ -273,6 +289,7 @@ int pyvb_zstep_f32(long long N, long long nalloc, int D, int q, const void *plan
                    const double *P0, const double *h0, double *gl, float *MZ32, void *MP, double *Sig, double *logdet,
                    double *zsums, void *stream) {
     ARG(N >= 0 && nalloc >= N && f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
+    if (N == 0) return PYVB_OK;
     ARG(planes && GT && WT && P0 && h0 && gl && MZ32 && MP && logdet, "null pointer");
     cudaError_t e = launch_zstep_f32(N, nalloc, D, q, planes, GT, WT, P0, h0, gl, MZ32, (cudaStream_t)stream);
     if (e == cudaSuccess) e = launch_zsolve_f32(N, q, MZ32, MP, Sig, logdet, gl, zsums, (cudaStream_t)stream);
@@ -283,7 +300,17 @@ int pyvb_stats_f32(long long N, long long nalloc, int D, int q, const void *plan
                    void *ws, size_t ws_bytes, double *xcache, const double *zsums, const pyvb_peers *peers,
                    void *stream) {
     ARG(N >= 0 && nalloc >= N && f32_supported(D, q), "the FP32 path needs q in {16, 32, 64} and D % 32 == 0");
-    ARG(planes && MP && stats && ws && xcache && zsums, "null pointer (xcache and zsums are required)");
+    ARG(stats && ws, "null pointer");
+    if (N == 0) {
+        ARG(ws_bytes >= (StatLayout(D, q).len + PYVB_NSCAL) * sizeof(double), "workspace too small");
+        cudaError_t e0 = cudaMemsetAsync(ws, 0, (StatLayout(D, q).len + PYVB_NSCAL) * sizeof(double), (cudaStream_t)stream);
+        if (e0 == cudaSuccess)
+            e0 = launch_stats_reduce(D, q, (const double *)ws, 1, (const double *)ws + StatLayout(D, q).len, 1, stats,
+                                     NULL, 0, NULL, 0, 0, peers ? peers->bufs : NULL, peers ? peers->world : 1,
+                                     peers ? peers->rank : 0, peers ? peers->epoch : 0ULL, (cudaStream_t)stream);
+        return e0 == cudaSuccess ? PYVB_OK : cuda_fail(e0, "stats_f32 (empty shard)");
+    }
+    ARG(planes && MP && xcache && zsums, "null pointer (xcache and zsums are required)");
     ARG(ws_bytes >= pyvb_stats_workspace_bytes(N, D, q, PYVB_ALGO_F32), "workspace too small");
     ARG(peers == NULL || (peers->bufs != NULL && peers->world >= 1 && peers->rank >= 0 && peers->rank < peers->world &&
                           peers->world <= 256 && peers->epoch >= 1),
@@ -312,6 +339,7 @@ int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X,
                          double a0, double b0, int niters, double *status, void *stream) {
     ARG(B >= 0 && q >= 1 && q <= 8 && d >= 1 && d <= 8 && niters >= 0, "B, q (<= 8), d (<= 8), niters");
     ARG(T >= 3 && T <= pyvb_lds_max_len(), "T (3 .. pyvb_lds_max_len())");
+    if (B == 0) return PYVB_OK;
     ARG(Y && X && Xcov3 && A && Avar && C && Cvar && Qa && Qb && Ra && Rb && status, "null pointer");
     cudaError_t e = launch_lds_iterate(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb, alpha0, a0, b0, niters,
                                        status, (cudaStream_t)stream);

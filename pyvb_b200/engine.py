@@ -374,7 +374,7 @@ class PlateEngine(object):
         if self._stats_fresh:
             return
         if self.f32:
-            if not self._zsums_valid:
+            if not self._zsums_valid and self.N > 0:
                 self._zsums_from_state()
             rc = self.lib.pyvb_stats_f32(self.N, self.N, self.D, self.q, self.planes.data_ptr(), self.MP.data_ptr(),
                                          self.stats.data_ptr(), self.ws.data_ptr(), self.ws_bytes,

@@ -53,3 +53,11 @@ def test_lds_batch_matches_oracle(shape):
     for k in KEYS:
         assert np.array_equal(st2[k], st[k]), k
     e.check()
+
+
+def test_lds_empty_batch_is_a_noop():
+    from pyvb_b200 import LDSEngine
+    e = LDSEngine(np.zeros((0, 10, 3)), 2, device="cuda:0")
+    e.iterate(2)
+    e.check()
+    assert e.get_state()["X"].shape == (0, 10, 2)

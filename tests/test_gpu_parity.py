@@ -238,3 +238,17 @@ def test_iterate_from_host_equals_resident_sweep(eng):
     sa, sb = a.get_state(), b.get_state()
     for k in ("Wbar", "mu", "Zbar", "Sig"):
         assert tensor_rel(sb[k], sa[k]) < 1e-12, k
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_empty_row_block_sweeps_on_the_priors(eng, precision):
+    """An empty shard (N = 0 rows) is legal: the sweep runs on the priors alone and stays finite (it still takes
+    part in the exchange when rows are sharded)."""
+    D, q = 32, 16
+    e = eng(np.zeros((0, D)), q, mode="B", precision=precision)
+    e.init_random(seed=3)
+    vals = [e.iterate() for _ in range(3)]
+    assert np.all(np.isfinite(vals))
+    st = e.get_state()
+    assert np.all(np.isfinite(st["Wbar"])) and np.allclose(st["Wbar"], 0.0)      # no data: W at its prior mean
+    e.check()
