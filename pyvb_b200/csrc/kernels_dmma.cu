@@ -93,6 +93,8 @@ static cudaError_t make_map(CUtensorMap *m, const void *base, uint64_t inner, ui
 // NCT > 1: the output columns are split into NCT column tiles, one CTA each (q = 64: 268 column groups do not
 // fit one CTA's accumulators); consecutive CTAs share the X tile through L2
 template <int Q> struct ZC;
+// (measured and rejected for q = 16: KC = 8 with 6 stages, 4 stages, one 8-warp CTA per SM, a dedicated producer
+//  warp -- all within 1 % of this configuration; what did help was making the kernel persistent)
 template <> struct ZC<8>  { static constexpr int WM = 4, WN = 1, RGW = 4, KC = 16, ST = 3, OCC = 2, NCT = 1; };
 template <> struct ZC<16> { static constexpr int WM = 4, WN = 1, RGW = 2, KC = 16, ST = 3, OCC = 2, NCT = 1; };
 template <> struct ZC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 1; };
@@ -122,7 +124,7 @@ template <int Q> struct ZT {
     static constexpr int GS_B = KC * GP * 8;
     static constexpr int OROW = NGT * 8;        // doubles per output row (segment) [packed | pad | eta]
     static constexpr int SROW = c_srow(OROW);   // staging pitch
-    static constexpr int MAIN_B = (c_max(ST * (XT_B + GS_B), R * SROW * 8) + 15) & ~15;
+    static constexpr int MAIN_B = (ST * (XT_B + GS_B) + 15) & ~15;
     static constexpr size_t SMEM = 1024 + (size_t)MAIN_B + (size_t)(P + Q) * 8 + 2 * ST * 8;
     static_assert(XT_B % 1024 == 0, "swizzled tiles must stay 1024-byte aligned");
 };
@@ -259,11 +261,15 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
 }
 
 // ------------------------------------------------------------------ Z step, part 1 (K1): tensor-core contraction
+// Persistent: every CTA walks over (row tile, column tile) pairs; the TMA pipeline runs CONTINUOUSLY across the
+// tiles (the copies of the next tile are in flight while the current one finishes), and the accumulators leave
+// straight from registers with 16-byte stores (8 rows x 64 contiguous bytes per warp instruction), so there is no
+// staging buffer, no per-tile prologue and no pipeline drain between tiles.
 template <int Q>
 __global__ void __launch_bounds__(ZT<Q>::NTHR, ZC<Q>::OCC)
 zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, const double *__restrict__ Gw,
                   const double *__restrict__ P0, const double *__restrict__ h0, const double *__restrict__ gl,
-                  double *__restrict__ MZ) {
+                  double *__restrict__ MZ, long long ntiles) {
     using T = ZT<Q>;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
@@ -271,19 +277,16 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char *xs_base = smem;                              // ST swizzled X tiles
     unsigned char *gs_base = smem + T::ST * T::XT_B;            // ST Gw chunks
-    double *stg = reinterpret_cast<double *>(smem);             // epilogue staging aliases the pipeline buffers
     double *p0v = reinterpret_cast<double *>(smem + T::MAIN_B);
     double *h0s = p0v + T::P;
     uint64_t *full = reinterpret_cast<uint64_t *>(h0s + Q);
     uint64_t *empty = full + T::ST;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ct = T::TILED ? (int)(blockIdx.x % T::NCT) : 0;          // column tile
-    const long long row0 = (long long)(blockIdx.x / T::NCT) * T::R;
-    const int cgb = ct * T::NGT;                                        // first column group of the tile
-    const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;    // groups in this tile
-    const bool need_mu = cgb + ngt > T::NGO;                            // the tile has eta columns
     const int nk = D / T::KC;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; column tile fastest (neighbours share the X tile in L2)
+    const long long my_tiles = (ntiles > (long long)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_it = my_tiles * nk;                   // pipeline steps of this CTA
 
     for (int p = tid; p < T::P; p += T::NTHR) {
         int i, j;
@@ -301,10 +304,21 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     }
     __syncthreads();
 
-    // ===================== producer role (warp 0, one lane): two TMA copies per stage =====================
-    auto produce = [&](int kc) {
-        const int s = kc % T::ST;
-        const uint32_t ph = (uint32_t)((kc / T::ST) & 1);
+    // ===================== producer role (warp 0, one lane): pipeline step `it` = chunk it % nk of tile it / nk =====
+    // (the producer keeps its own (tile, chunk, stage, parity) counters: no divisions on the critical path)
+    long long p_tile = blockIdx.x, p_it = 0;
+    int p_kc = 0, p_s = 0;
+    uint32_t p_ph = 0;
+    auto produce = [&]() {
+        const int s = p_s;
+        const uint32_t ph = p_ph;
+        const long long tile = p_tile;
+        const int kc = p_kc;
+        const int ct = T::TILED ? (int)((unsigned long long)tile % (unsigned)T::NCT) : 0;
+        const long long row0 = (T::TILED ? (long long)((unsigned long long)tile / (unsigned)T::NCT) : tile) * T::R;
+        const int cgb = ct * T::NGT;
+        const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;
+        const bool need_mu = cgb + ngt > T::NGO;
         mbar_wait(&empty[s], ph ^ 1);
         if (!T::TILED) {
             if (lane == 0) {
@@ -327,30 +341,45 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
             }
         }
         __syncwarp();
+        ++p_it;
+        if (++p_kc == nk) {
+            p_kc = 0;
+            p_tile += gridDim.x;
+        }
+        if (++p_s == T::ST) {
+            p_s = 0;
+            p_ph ^= 1;
+        }
     };
     if (warp == 0)
-        for (int kc = 0; kc < T::ST - 1 && kc < nk; ++kc) produce(kc);
+        while (p_it < T::ST - 1 && p_it < total_it) produce();
 
     // ===================== DMMA main loop =====================
     const int wm = warp / T::WN, wn = warp % T::WN;
     const int gid = lane >> 2, qd = lane & 3;
     const int prow = row_perm<T::KC>(gid);                 // tile row (within a group of 8) of MMA row gid
     const int lg0 = wn * T::NGW;                            // first group of this warp inside the tile
-    const int cg0 = cgb + lg0;
-    const int ncg = (ngt - lg0 < T::NGW) ? (ngt - lg0) : T::NGW;
-    double acc[T::RGW][T::NGW][2];
+    const double tau = gl[PYVB_GL_TAU];
+    int xo[T::KC / 4];                                      // swizzled byte offsets of this lane's X element
 #pragma unroll
-    for (int rg = 0; rg < T::RGW; ++rg)
+    for (int kk = 0; kk < T::KC / 4; ++kk) xo[kk] = xt_off<T::KC>(wm * T::RGW * 8 + prow, kk * 4 + qd);
+    int s = 0;
+    uint32_t ph = 0;
+    for (long long tl = 0; tl < my_tiles; ++tl) {
+        const long long tile = (long long)blockIdx.x + tl * gridDim.x;
+        const int ct = T::TILED ? (int)((unsigned long long)tile % (unsigned)T::NCT) : 0;
+        const long long row0 = (T::TILED ? (long long)((unsigned long long)tile / (unsigned)T::NCT) : tile) * T::R;
+        const int cgb = ct * T::NGT;
+        const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;
+        const int cg0 = cgb + lg0;
+        const int ncg = (ngt - lg0 < T::NGW) ? (ngt - lg0) : T::NGW;
+        double acc[T::RGW][T::NGW][2];
 #pragma unroll
-        for (int j = 0; j < T::NGW; ++j) acc[rg][j][0] = acc[rg][j][1] = 0.0;
-    {
-        int xo[T::KC / 4];                                  // swizzled byte offsets of this lane's X element
+        for (int rg = 0; rg < T::RGW; ++rg)
 #pragma unroll
-        for (int kk = 0; kk < T::KC / 4; ++kk) xo[kk] = xt_off<T::KC>(wm * T::RGW * 8 + prow, kk * 4 + qd);
-        int s = 0;
-        uint32_t ph = 0;
+            for (int j = 0; j < T::NGW; ++j) acc[rg][j][0] = acc[rg][j][1] = 0.0;
         for (int kc = 0; kc < nk; ++kc) {
-            if (warp == 0 && kc + T::ST - 1 < nk) produce(kc + T::ST - 1);
+            if (warp == 0 && p_it < total_it) produce();       // keeps the pipeline ST - 1 steps ahead
             mbar_wait(&full[s], ph);
             const unsigned char *xs = xs_base + s * T::XT_B;
             const double *gs = reinterpret_cast<const double *>(gs_base + s * T::GS_B) + qd * T::GP;
@@ -385,37 +414,29 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
                 ph ^= 1;
             }
         }
-    }
-
-    // ===================== epilogue: qprec = P0 + tau*acc, eta = h0 + tau*acc -> staging -> MZ rows ==========
-    __syncthreads();                                       // all warps are done with the pipeline buffers
-    const double tau = gl[PYVB_GL_TAU];
+        // ---- epilogue of the tile: qprec = P0 + tau*acc, eta = h0 + tau*acc, registers -> MZ rows
 #pragma unroll
-    for (int rg = 0; rg < T::RGW; ++rg) {
-        double *srow = stg + (size_t)(wm * T::RGW * 8 + rg * 8 + prow) * T::SROW;
+        for (int rg = 0; rg < T::RGW; ++rg) {
+            const long long row = row0 + wm * T::RGW * 8 + rg * 8 + prow;
+            if (row >= N) continue;
+            double *orow = MZ + row * T::LDG;
 #pragma unroll
-        for (int j = 0; j < T::NGW; ++j) {
-            if (T::WN > 1 && j >= ncg) continue;
-            const int cg = cg0 + j;
-            const int c = cg * 8 + 2 * qd;
-            double2 v;
-            if (cg < T::NGO) {   // packed qprec columns; the pad columns [P, PP) come out as exact zeros (Gw pad = 0)
-                v.x = (c < T::P) ? fma(tau, acc[rg][j][0], p0v[c]) : 0.0;
-                v.y = (c + 1 < T::P) ? fma(tau, acc[rg][j][1], p0v[c + 1]) : 0.0;
-            } else {
-                v.x = fma(tau, acc[rg][j][0], h0s[c - T::PP]);
-                v.y = fma(tau, acc[rg][j][1], h0s[c + 1 - T::PP]);
+            for (int j = 0; j < T::NGW; ++j) {
+                if (T::WN > 1 && j >= ncg) continue;
+                const int cg = cg0 + j;
+                const int c = cg * 8 + 2 * qd;
+                double2 v;
+                if (cg < T::NGO) {   // packed qprec columns; the pad columns [P, PP) come out as exact zeros
+                    v.x = (c < T::P) ? fma(tau, acc[rg][j][0], p0v[c]) : 0.0;
+                    v.y = (c + 1 < T::P) ? fma(tau, acc[rg][j][1], p0v[c + 1]) : 0.0;
+                } else {
+                    v.x = fma(tau, acc[rg][j][0], h0s[c - T::PP]);
+                    v.y = fma(tau, acc[rg][j][1], h0s[c + 1 - T::PP]);
+                }
+                *reinterpret_cast<double2 *>(orow + c) = v;
             }
-            *reinterpret_cast<double2 *>(srow + (lg0 + j) * 8 + 2 * qd) = v;
         }
     }
-    fence_async_smem();
-    __syncthreads();
-    for (int r = tid; r < T::R; r += T::NTHR)
-        if (row0 + r < N)
-            bulk_s2g(MZ + (row0 + r) * T::LDG + cgb * 8, stg + (size_t)r * T::SROW, (uint32_t)(ngt * 64));
-    bulk_commit();
-    bulk_wait_read_all();
 }
 
 // ------------------------------------------------------------------ Z step, part 2 (K2): batched q x q solve
@@ -667,8 +688,9 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
-    const long long blocks = ((N + T::R - 1) / T::R) * T::NCT;
-    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ);
+    const long long ntiles = ((N + T::R - 1) / T::R) * T::NCT;
+    const long long blocks = ntiles < 148LL * ZC<Q>::OCC ? ntiles : 148LL * ZC<Q>::OCC;
+    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
     e = cudaGetLastError();
     if (e != cudaSuccess || k1_only) return e;
     return launch_zsolve(N, Q, MZ, Sig, logdet, gl, zsums, st);
