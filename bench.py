@@ -420,7 +420,7 @@ def run_ours(a):
                            "l2": "inputs larger than L2 (X shard %.2f GB per GPU)" % (a.N * a.D * 8 / 1e9),
                            "parallelism": "rows sharded over %d GPU(s), one all-reduce of %d doubles per sweep"
                                           % (world, eng.L.len)},
-                "clocks": clocks, "gpu_launches": 9 * a.steps,   # wupdate, pack_gw, zstep K1, zsolve K2, stats GEMM, mzsums, rowscalars, reduce, global
+                "clocks": clocks, "gpu_launches": 7 * a.steps,   # per sweep: wupdate, pack_gw, zstep K1, zsolve K2, stats GEMM, reduce(+exchange), global
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": a.N * a.D * 8, "d2h_bytes_per_step": 8,
                         "steps": e2e_steps},
                 "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}
