@@ -200,6 +200,25 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
                     const double *mu, const double *Zbar, long long ldz, const double *gl,
                     double *Xhat, double *V, double *qldX, void *stream);
 
+/* ---- exact mask contraction on the INT8 tensor cores (tcgen05.mma kind::i8) ----
+ * Same reference arithmetic as pyvb_zstep_f64 (nodes/node.py:203-227 + nodes/gaussian.py:112-123) and the same result
+ * to FP64 rounding: the 0/1 mask is exact in int8 and every column of G is split into seven balanced base-256 digit
+ * planes of a 2^-54 fixed-point representation (relative to the column maximum), so mask @ G is a sum of exact
+ * integer GEMMs recombined in FP64.  The eta columns (X real) stay on the FP64 tensor cores.  Mode B only.
+ * q in {16, 32, 64}, D % 64 == 0, D small enough for the resident mask block (pyvb_i8_supported).
+ *   mask   [N][D] int8, 1 = observed: pyvb_prepare_mask_i8 (once per data set)
+ *   GI     pyvb_i8_digits_bytes(D, q) bytes, gscale pyvb_i8_ncols(q) doubles: per-sweep scratch (filled by the call)
+ *   MZ     the interleaved rows of the DMMA path (ldmz = pyvb_mz_pitch(q)); Gw as for pyvb_zstep_f64 (DMMA pitch)
+ * k1_only != 0 leaves [qprec packed | eta] in the rows (measurement). */
+int pyvb_i8_supported(int D, int q);
+size_t pyvb_i8_digits_bytes(int D, int q);
+int pyvb_i8_ncols(int q);
+int pyvb_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, void *stream);
+int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx, const void *mask, const double *Wbar,
+                      const double *Wvar, const double *Gw, int ldg, const double *P0, const double *h0, double *gl,
+                      double *MZ, long long ldmz, void *GI, double *gscale, double *Sig, double *logdet, double *zsums,
+                      int k1_only, void *stream);
+
 /* ---- FP32 variant of the Z-step contraction (tcgen05 tensor cores, TMEM accumulators, TMA-staged bf16 x 3 splits) ----
  * Same reference arithmetic as pyvb_zstep_f64's K1 (nodes/node.py:203-227).  q in {16, 32, 64}, D % 32 == 0.
  *   planes  bf16 [3][N][D]    mask | x_h | x_m  (x = x_h + x_m to 16 bits; zeros where not observed); static over sweeps

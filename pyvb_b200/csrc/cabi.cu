@@ -256,6 +256,37 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "impute");
 }
 
+int pyvb_i8_supported(int D, int q) { return (i8_supported(D, q) && dmma_supported(D, q)) ? 1 : 0; }
+size_t pyvb_i8_digits_bytes(int D, int q) { return i8_digits_bytes(D, q); }
+int pyvb_i8_ncols(int q) { return i8_ncols(q); }
+
+int pyvb_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, void *stream) {
+    ARG(N >= 0 && D >= 4 && (D % 4) == 0 && ldx >= D && (ldx % 2) == 0, "N, D (% 4), ldx (even)");
+    if (N == 0) return PYVB_OK;
+    ARG(X && mask, "null pointer");
+    cudaError_t e = launch_prepare_mask_i8(N, D, X, ldx, mask, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "prepare_mask_i8");
+}
+
+int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx, const void *mask, const double *Wbar,
+                      const double *Wvar, const double *Gw, int ldg, const double *P0, const double *h0, double *gl,
+                      double *MZ, long long ldmz, void *GI, double *gscale, double *Sig, double *logdet, double *zsums,
+                      int k1_only, void *stream) {
+    ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    if (!pyvb_i8_supported(D, q))
+        return fail(PYVB_ENOSUP, "%s", "the INT8 path needs q in {16, 32, 64}, D % 64 == 0 and a mask block that fits shared memory");
+    if (N == 0) return PYVB_OK;
+    ARG(X && mask && Wbar && Wvar && Gw && P0 && h0 && gl && MZ && GI && gscale && logdet, "null pointer");
+    ARG(ldx >= D && (ldx % 2) == 0, "ldx");
+    ARG(ldg == pyvb_gw_pitch(q) && ldmz == pyvb_mz_pitch(q), "ldg / ldmz must equal pyvb_gw_pitch(q) / pyvb_mz_pitch(q)");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, st);
+    if (e == cudaSuccess) e = launch_zstep_i8(N, D, q, mask, GI, P0, gscale, gl, MZ, (int)ldmz, st);
+    if (e == cudaSuccess) e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, P0, h0, gl, MZ, st);
+    if (e == cudaSuccess && !k1_only) e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, st);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_i8");
+}
+
 int pyvb_f32_pitch(int q) { return f32_ncp(q); }
 int pyvb_f32_zoff(int q) { return f32_zoff(q); }
 int pyvb_f32_poff(int q) { return f32_poff(q); }

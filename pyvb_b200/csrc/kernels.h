@@ -48,6 +48,8 @@ bool dmma_supported(int D, int q);
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                               int ldg, const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
                               double *logdet, double *zsums, int k1_only, cudaStream_t st);
+cudaError_t launch_zstep_eta_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
+                                  const double *P0, const double *h0, double *gl, double *MZ, cudaStream_t st);
 cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
                           cudaStream_t st);
 // K2 leaves nblk partials of kw doubles each in zsums (0, 0: no fast K2 for this q)
@@ -88,6 +90,16 @@ int stats_f32_nchunks(long long N, int D, int q);
 void zsolve_partials_f32(long long N, int q, int &nblk, int &kw);
 cudaError_t launch_stats_f32(long long N, long long nalloc, int D, int q, const void *planes, const void *MP, double *ws,
                              int nchunks, cudaStream_t st);
+
+// ---- exact mask contraction on the INT8 tensor cores (kernels_i8.cu) ----
+bool i8_supported(int D, int q);
+size_t i8_digits_bytes(int D, int q);          // bytes of the digit planes of G
+int i8_ncols(int q);                           // packed columns rounded up to 32 (length of gscale)
+cudaError_t launch_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, cudaStream_t st);
+cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wvar, void *GI, double *gscale,
+                             cudaStream_t st);
+cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const void *GI, const double *P0,
+                            const double *gscale, const double *gl, double *MZ, int ldmz, cudaStream_t st);
 
 // ---- LDS smoother, batched over sequences (kernels_lds.cu) ----
 size_t lds_smem_bytes(int T, int d);

@@ -106,12 +106,16 @@ __host__ __device__ constexpr int c_pitch4(int need) {      // smallest pitch >=
     return p;
 }
 
-template <int Q> struct ZT {
+// ETA = true: only the eta column groups [NGO, NG) (the O.(X - mu) @ <W> part); all warps line up along the rows.
+// Used together with the int8 mask contraction (kernels_i8.cu), which produces the qprec columns.
+template <int Q, bool ETA = false> struct ZT {
     using C = ZC<Q>;
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, NGO = PP / 8, NGE = Q / 8, NG = NGO + NGE;
-    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST, NCT = C::NCT;
-    static constexpr bool TILED = NCT > 1;
-    static constexpr int NGT = (NG + NCT - 1) / NCT;   // column groups per column tile
+    static constexpr int WM = ETA ? C::WM * C::WN : C::WM, WN = ETA ? 1 : C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST;
+    static constexpr int NCT = ETA ? 1 : C::NCT;
+    static constexpr bool TILED = ETA || NCT > 1;
+    static constexpr int CG0 = ETA ? NGO : 0;          // first column group this kernel computes
+    static constexpr int NGT = ETA ? NGE : (NG + NCT - 1) / NCT;   // column groups per column tile
     static constexpr int NGW = (NGT + WN - 1) / WN;
     static constexpr int R = WM * RGW * 8;
     static constexpr int NCW = WM * WN;
@@ -265,12 +269,12 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
 // tiles (the copies of the next tile are in flight while the current one finishes), and the accumulators leave
 // straight from registers with 16-byte stores (8 rows x 64 contiguous bytes per warp instruction), so there is no
 // staging buffer, no per-tile prologue and no pipeline drain between tiles.
-template <int Q>
-__global__ void __launch_bounds__(ZT<Q>::NTHR, ZC<Q>::OCC)
+template <int Q, bool ETA>
+__global__ void __launch_bounds__(ZT<Q, ETA>::NTHR, ZC<Q>::OCC)
 zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, const double *__restrict__ Gw,
                   const double *__restrict__ P0, const double *__restrict__ h0, const double *__restrict__ gl,
                   double *__restrict__ MZ, long long ntiles) {
-    using T = ZT<Q>;
+    using T = ZT<Q, ETA>;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
     // shared address space so that fragment loads compile to LDS, not generic LD
@@ -314,9 +318,9 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         const uint32_t ph = p_ph;
         const long long tile = p_tile;
         const int kc = p_kc;
-        const int ct = T::TILED ? (int)((unsigned long long)tile % (unsigned)T::NCT) : 0;
-        const long long row0 = (T::TILED ? (long long)((unsigned long long)tile / (unsigned)T::NCT) : tile) * T::R;
-        const int cgb = ct * T::NGT;
+        const int ct = T::NCT > 1 ? (int)((unsigned long long)tile % (unsigned)T::NCT) : 0;
+        const long long row0 = (T::NCT > 1 ? (long long)((unsigned long long)tile / (unsigned)T::NCT) : tile) * T::R;
+        const int cgb = T::CG0 + ct * T::NGT;
         const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;
         const bool need_mu = cgb + ngt > T::NGO;
         mbar_wait(&empty[s], ph ^ 1);
@@ -367,9 +371,9 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
     uint32_t ph = 0;
     for (long long tl = 0; tl < my_tiles; ++tl) {
         const long long tile = (long long)blockIdx.x + tl * gridDim.x;
-        const int ct = T::TILED ? (int)((unsigned long long)tile % (unsigned)T::NCT) : 0;
-        const long long row0 = (T::TILED ? (long long)((unsigned long long)tile / (unsigned)T::NCT) : tile) * T::R;
-        const int cgb = ct * T::NGT;
+        const int ct = T::NCT > 1 ? (int)((unsigned long long)tile % (unsigned)T::NCT) : 0;
+        const long long row0 = (T::NCT > 1 ? (long long)((unsigned long long)tile / (unsigned)T::NCT) : tile) * T::R;
+        const int cgb = T::CG0 + ct * T::NGT;
         const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;
         const int cg0 = cgb + lg0;
         const int ncg = (ngt - lg0 < T::NGW) ? (ngt - lg0) : T::NGW;
@@ -677,6 +681,34 @@ void zsolve_partials(long long N, int q, int &nblk, int &kw) {
     nblk = (int)b;
 }
 
+template <int Q, bool ETA>
+static cudaError_t launch_k1_q(long long N, int D, const double *X, long long ldx, const double *Gw, const double *P0,
+                               const double *h0, double *gl, double *MZ, cudaStream_t st) {
+    using T = ZT<Q, ETA>;
+    CUtensorMap tmX;
+    cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, T::KC, T::R,
+                             T::KC == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(zstep_dmma_kernel<Q, ETA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    if (e != cudaSuccess) return e;
+    const long long ntiles = ((N + T::R - 1) / T::R) * T::NCT;
+    const long long blocks = ntiles < 148LL * ZC<Q>::OCC ? ntiles : 148LL * ZC<Q>::OCC;
+    zstep_dmma_kernel<Q, ETA><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
+    return cudaGetLastError();
+}
+
+// the eta columns alone (see ZT<Q, true>): MZ rows get [.. | eta] with the qprec columns left untouched
+cudaError_t launch_zstep_eta_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
+                                  const double *P0, const double *h0, double *gl, double *MZ, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    switch (q) {
+        case 16: return launch_k1_q<16, true>(N, D, X, ldx, Gw, P0, h0, gl, MZ, st);
+        case 32: return launch_k1_q<32, true>(N, D, X, ldx, Gw, P0, h0, gl, MZ, st);
+        case 64: return launch_k1_q<64, true>(N, D, X, ldx, Gw, P0, h0, gl, MZ, st);
+    }
+    return cudaErrorNotSupported;
+}
+
 template <int Q>
 static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long ldx, const double *Gw,
                                   const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
@@ -686,11 +718,11 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, T::KC, T::R,
                              T::KC == 16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(zstep_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    e = cudaFuncSetAttribute(zstep_dmma_kernel<Q, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     const long long ntiles = ((N + T::R - 1) / T::R) * T::NCT;
     const long long blocks = ntiles < 148LL * ZC<Q>::OCC ? ntiles : 148LL * ZC<Q>::OCC;
-    zstep_dmma_kernel<Q><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
+    zstep_dmma_kernel<Q, false><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
     e = cudaGetLastError();
     if (e != cudaSuccess || k1_only) return e;
     return launch_zsolve(N, Q, MZ, Sig, logdet, gl, zsums, st);

@@ -69,6 +69,13 @@ class PlateEngine(object):
         self.f32 = (precision == "f32")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.mode, self.q, self.ard = mode, int(q), bool(ard)
+        # algo "i8": the mask contraction of the Z step on the INT8 tensor cores (exact, kernels_i8.cu); the rest as "dmma".
+        # "auto" picks it when the shape allows (PYVB_I8=0 keeps the all-DMMA path)
+        self.use_i8 = (algo == "i8")
+        if algo == "i8":
+            algo = "dmma"
+        elif algo == "auto" and mode == "B" and precision == "f64" and os.environ.get("PYVB_I8", "0") != "0":
+            self.use_i8 = None                                  # decided below, once D is known
         self.algo = _ALGOS[algo] if isinstance(algo, str) else int(algo)
         self.distributed = bool(distributed)
         self.row_offset = int(row_offset)
@@ -117,6 +124,16 @@ class PlateEngine(object):
             self.qldX = None
             n_eff_local = n_obs_local
         del obs
+        i8_ok = bool(self.lib.pyvb_i8_supported(D, q)) and mode == "B" and not self.f32
+        if self.use_i8 is None:
+            self.use_i8 = i8_ok
+        elif self.use_i8 and not i8_ok:
+            raise ValueError("algo='i8' needs mode B, FP64, q in (16, 32, 64), D % 64 == 0 and D <= ~1280")
+        if self.use_i8:
+            self.mask8 = torch.empty(N, D, dtype=torch.int8, device=dev)
+            self.GI = torch.empty(int(self.lib.pyvb_i8_digits_bytes(D, q)), dtype=torch.int8, device=dev)
+            self.gscale = torch.empty(int(self.lib.pyvb_i8_ncols(q)), dtype=f64, device=dev)
+        self._mask_valid = False
         n_eff = self._allreduce_scalar(float(n_eff_local))
         self.n_rows_total = int(self._allreduce_scalar(float(N)))
 
@@ -317,6 +334,7 @@ class PlateEngine(object):
         assert self.mode == "B" and not self.f32
         self.X.copy_(X, non_blocking=True)
         self._xcache_valid = False
+        self._mask_valid = False
         self._stats_fresh = False
 
     def get_state(self):
@@ -431,6 +449,22 @@ class PlateEngine(object):
             return
         full = (lo == 0 and hi == self.N and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA))
         self._zsums_valid = False
+        if self.use_i8:
+            if not self._mask_valid:                        # the int8 mask follows X (static in mode B)
+                rc = self.lib.pyvb_prepare_mask_i8(hi - lo, D, self.X.data_ptr() + lo * D * 8, D,
+                                                   self.mask8.data_ptr() + lo * D, self._stream())
+                _cabi.check(rc, "pyvb_prepare_mask_i8")
+                self._mask_valid = (lo == 0 and hi == self.N)
+            rc = self.lib.pyvb_zstep_i8_f64(hi - lo, D, q, self.X.data_ptr() + lo * D * 8, D,
+                                            self.mask8.data_ptr() + lo * D, self.Wbar.data_ptr(), self.Wvar.data_ptr(),
+                                            self.Gw.data_ptr(), self.ldg, self.P0.data_ptr(), self.h0.data_ptr(),
+                                            self.gl.data_ptr(), self.MZ.data_ptr() + lo * self.ldmz * 8, self.ldmz,
+                                            self.GI.data_ptr(), self.gscale.data_ptr(), sig,
+                                            self.logdet.data_ptr() + lo * 8, self.zsums.data_ptr() if full else 0,
+                                            0, self._stream())
+            _cabi.check(rc, "pyvb_zstep_i8_f64")
+            self._zsums_valid = full
+            return
         rc = self.lib.pyvb_zstep_f64(hi - lo, D, q, self.X.data_ptr() + lo * D * 8, D, self.Gw.data_ptr(),
                                      self.ldg, self.P0.data_ptr(), self.h0.data_ptr(), self.gl.data_ptr(),
                                      self.Zbar.data_ptr() + lo * self.ldmz * 8, self.ldmz,
@@ -526,6 +560,7 @@ class PlateEngine(object):
         self.update_W()
         self._ensure_gw()
         self._xcache_valid = False
+        self._mask_valid = False
         step = (N + nchunks - 1) // nchunks
         step = (step + 63) // 64 * 64
         for lo in range(0, N, step):

@@ -1,0 +1,111 @@
+"""GPU parity of the INT8 tensor-core mask contraction (kernels_i8.cu, pyvb_zstep_i8_f64): the same FP64 results as
+the DMMA path and the oracle, through the C-ABI.  The digit split is exact by construction (integer GEMMs), so the
+tolerance is the one of the other FP64 kernels: 1e-11 kernel against kernel, 1e-9 against the oracle per sweep."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import tensor_rel
+from oracle.plate_oracle import PlateOracle, synth_pca
+from test_gpu_parity import rand_init, _cmp_state, TOL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pyvb_b200 import PlateEngine
+    return PlateEngine
+
+
+I8_SHAPES = [(5000, 256, 16), (64, 64, 16), (1, 64, 16), (777, 128, 32), (2100, 192, 32), (333, 64, 64), (1500, 128, 64),
+             (19000, 1024, 32)]
+
+
+@pytest.mark.parametrize("shape", I8_SHAPES)
+def test_i8_zstep_matches_dmma(eng, shape):
+    """kernel-level: the MZ rows, Sigma and log-dets of one Z step, INT8 mask contraction against the all-DMMA path."""
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.3, seed=N + q)
+    if N > 10:
+        X[2, :] = np.nan            # an all-missing row
+        X[5, :] = 1.0               # a fully observed row
+    init = rand_init(N, D, q, seed=7)
+    init["Wbar"][:, 0] *= 1e3       # columns of G on very different scales (per-column fixed-point scale)
+    init["Wbar"][:, 1] *= 1e-4
+    ed, ei = eng(X, q, mode="B", algo="dmma"), eng(X, q, mode="B", algo="i8")
+    assert ei.use_i8 and not ed.use_i8
+    for e in (ed, ei):
+        e.set_state(init)
+        e.update_Z()
+        e._ensure_stats()
+    sd, si = ed.get_state(), ei.get_state()
+    for k in ("Zbar", "Sig"):
+        assert tensor_rel(si[k], sd[k]) < 1e-11, (shape, k)
+    assert tensor_rel(ei.M2.contiguous().cpu().numpy(), ed.M2.contiguous().cpu().numpy()) < 1e-11
+    ld, li = ed.logdet.cpu().numpy(), ei.logdet.cpu().numpy()
+    assert np.max(np.abs(ld - li)) < 1e-11 * max(1.0, np.max(np.abs(ld)))
+    assert tensor_rel(ei.stats.cpu().numpy()[:ei.L.scal], ed.stats.cpu().numpy()[:ed.L.scal]) < 1e-11
+    ei.check()
+
+
+@pytest.mark.parametrize("shape", [(600, 64, 16), (300, 128, 32)])
+def test_i8_qprec_is_exact_to_rounding(eng, shape):
+    """The qprec columns alone (k1_only), against a float128-free exact check: every G entry is rounded to
+    scale * 2^-55, the integer sums are exact, so |qprec_i8 - qprec_exact| <= tau * n_obs * scale_c * 2^-55 + 1 ulp."""
+    from pyvb_b200 import _cabi
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.4, seed=3)
+    init = rand_init(N, D, q, seed=5)
+    e = eng(X, q, mode="B", algo="i8")
+    e.set_state(init)
+    e._ensure_gw()
+    lib = e.lib
+    _cabi.check(lib.pyvb_prepare_mask_i8(N, D, e.X.data_ptr(), D, e.mask8.data_ptr(), e._stream()), "mask")
+    rc = lib.pyvb_zstep_i8_f64(N, D, q, e.X.data_ptr(), D, e.mask8.data_ptr(), e.Wbar.data_ptr(), e.Wvar.data_ptr(),
+                               e.Gw.data_ptr(), e.ldg, e.P0.data_ptr(), e.h0.data_ptr(), e.gl.data_ptr(),
+                               e.MZ.data_ptr(), e.ldmz, e.GI.data_ptr(), e.gscale.data_ptr(), 0, e.logdet.data_ptr(), 0,
+                               1, e._stream())
+    _cabi.check(rc, "zstep_i8 k1")
+    torch.cuda.synchronize()
+    P = q * (q + 1) // 2
+    got = e.MZ[:, :P].cpu().numpy()
+    eta = e.MZ[:, e.zoff:e.zoff + q].cpu().numpy()
+    O = (~np.isnan(X))
+    ii, jj = np.tril_indices(q)
+    W, Wv = init["Wbar"], init["Wvar"]
+    G = W[:, ii] * W[:, jj] + np.where(ii == jj, Wv[:, ii], 0.0)                  # D x P
+    tau = e.get_state()["tau"]
+    ref = np.eye(q)[ii, jj][None, :] + tau * (O.astype(np.longdouble) @ G.astype(np.longdouble)).astype(np.float64)
+    scale = np.abs(G).max(0)
+    bound = tau * O.sum(1)[:, None] * scale[None, :] * 2.0 ** -55 + 4 * np.finfo(np.float64).eps * np.abs(ref)
+    assert np.all(np.abs(got - ref) <= bound), float(np.max(np.abs(got - ref) / bound))
+    X0 = np.where(O, X - init["mu"][None, :], 0.0)
+    assert tensor_rel(eta, tau * (X0 @ W)) < 1e-12
+    assert np.array_equal(e.mask8.cpu().numpy().astype(bool), O)
+
+
+@pytest.mark.parametrize("shape", [(3000, 256, 16), (1200, 64, 32), (700, 128, 64)])
+def test_i8_iterations_match_oracle(eng, shape):
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.25, seed=N)
+    init = rand_init(N, D, q, seed=11)
+    o = PlateOracle(X, q, mode="B")
+    o.load_state(init)
+    e = eng(X, q, mode="B", algo="i8")
+    e.set_state(init)
+    for it in range(5):
+        ref, got = o.iterate(), e.iterate()
+        st = e.get_state()
+        _cmp_state(st, o.state(), ("Wbar", "Wvar", "mu", "muvar", "Zbar", "Sig"), (shape, it))
+        assert abs(st["qb"] - o.qb) <= TOL * abs(o.qb)
+        assert abs(got - ref) <= TOL * abs(ref), (shape, it, got, ref)
+    e.check()
+
+
+def test_i8_rejects_unsupported_shape(eng):
+    X = synth_pca(40, 48, 16, 0.1, seed=1)
+    with pytest.raises(ValueError):
+        eng(X, 16, mode="B", algo="i8")
