@@ -219,6 +219,25 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
                       double *MZ, long long ldmz, void *GI, double *gscale, double *Sig, double *logdet, double *zsums,
                       int k1_only, void *stream);
 
+/* Statistics with the mask-type sums T1 = O^T vec<zz^T>, Bst = O^T Zbar (nodes/nodes_todo.py:50-61) on the INT8 tensor
+ * cores: the MZ columns are rewritten as seven balanced base-256 digit planes (fixed point, 2^-54 of the column maximum),
+ * the products with the 0/1 mask are exact integer GEMMs, recombined in FP64 per row chunk.  Ast = (O.X)^T Zbar stays on
+ * the FP64 tensor cores.  Mode B, interleaved MZ rows, q in {16, 32, 64}, D % 16 == 0.  Requires what pyvb_stats_f64
+ * treats as optional: xcache (valid: the X-only sums of an earlier pyvb_stats_f64 call).  zsums: the K2 partials of the
+ * Z step that produced these rows, or NULL (then logdet [N] is read and the MZ column sums take one more pass).
+ *   maskT  [D][pyvb_stats_i8_npad(N)] int8: pyvb_prepare_maskt_i8 (once per data set)
+ *   ZI     pyvb_stats_i8_digits_bytes(N, q) bytes, scratch pyvb_stats_i8_scratch_len(q) doubles: per-call scratch
+ *   ws     pyvb_stats_i8_workspace_bytes(N, D, q) */
+int pyvb_stats_i8_supported(int D, int q);
+long long pyvb_stats_i8_npad(long long N);
+size_t pyvb_stats_i8_digits_bytes(long long N, int q);
+size_t pyvb_stats_i8_scratch_len(int q);
+size_t pyvb_stats_i8_workspace_bytes(long long N, int D, int q);
+int pyvb_prepare_maskt_i8(long long N, int D, const double *X, long long ldx, void *maskT, void *stream);
+int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx, const void *maskT, const double *MZ,
+                      long long ldmz, const double *logdet, void *ZI, double *scratch, double *stats, void *ws,
+                      size_t ws_bytes, const double *xcache, const double *zsums, const pyvb_peers *peers, void *stream);
+
 /* ---- FP32 variant of the Z-step contraction (tcgen05 tensor cores, TMEM accumulators, TMA-staged bf16 x 3 splits) ----
  * Same reference arithmetic as pyvb_zstep_f64's K1 (nodes/node.py:203-227).  q in {16, 32, 64}, D % 32 == 0.
  *   planes  bf16 [3][N][D]    mask | x_h | x_m  (x = x_h + x_m to 16 bits; zeros where not observed); static over sweeps

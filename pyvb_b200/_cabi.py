@@ -46,6 +46,14 @@ SIGNATURES = {
     "pyvb_prepare_mask_i8": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp]),
     "pyvb_zstep_i8_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
                                   c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
+    "pyvb_stats_i8_supported": (c_int, [c_int, c_int]),
+    "pyvb_stats_i8_npad": (c_ll, [c_ll]),
+    "pyvb_stats_i8_digits_bytes": (c_sz, [c_ll, c_int]),
+    "pyvb_stats_i8_scratch_len": (c_sz, [c_int]),
+    "pyvb_stats_i8_workspace_bytes": (c_sz, [c_ll, c_int, c_int]),
+    "pyvb_prepare_maskt_i8": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp]),
+    "pyvb_stats_i8_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz,
+                                  c_dp, c_dp, ctypes.POINTER(Peers), c_dp]),
     "pyvb_f32_pitch": (c_int, [c_int]),
     "pyvb_f32_zoff": (c_int, [c_int]),
     "pyvb_f32_poff": (c_int, [c_int]),

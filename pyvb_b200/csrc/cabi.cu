@@ -287,6 +287,70 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_i8");
 }
 
+int pyvb_stats_i8_supported(int D, int q) { return (stats_i8_supported(D, q) && dmma_supported(D, q)) ? 1 : 0; }
+long long pyvb_stats_i8_npad(long long N) { return stats_i8_npad(N); }
+size_t pyvb_stats_i8_digits_bytes(long long N, int q) { return stats_i8_digits_bytes(N, q); }
+size_t pyvb_stats_i8_scratch_len(int q) { return stats_i8_scratch_len(q, pyvb_mz_pitch(q)); }
+size_t pyvb_stats_i8_workspace_bytes(long long N, int D, int q) {
+    const StatLayout L(D, q);
+    if (N <= 0) return align256((L.len + PYVB_NSCAL) * sizeof(double));
+    return align256((size_t)stats_i8_nchunks(N, D, q) * L.len * sizeof(double)) +
+           align256((size_t)rowscalars_nblk(N) * PYVB_NSCAL * sizeof(double));
+}
+
+int pyvb_prepare_maskt_i8(long long N, int D, const double *X, long long ldx, void *maskT, void *stream) {
+    ARG(N >= 0 && D >= 1 && ldx >= D, "N, D, ldx");
+    if (N == 0) return PYVB_OK;
+    ARG(X && maskT, "null pointer");
+    cudaError_t e = launch_prepare_maskT_i8(N, D, X, ldx, maskT, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "prepare_maskT_i8");
+}
+
+int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx, const void *maskT, const double *MZ,
+                      long long ldmz, const double *logdet, void *ZI, double *scratch, double *stats, void *ws,
+                      size_t ws_bytes, const double *xcache, const double *zsums, const pyvb_peers *peers, void *stream) {
+    ARG(N >= 0 && D >= 1 && q >= 1 && q <= PYVB_QMAX, "N, D, q");
+    if (!pyvb_stats_i8_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "the INT8 statistics need q in {16, 32, 64}, D % 16 == 0");
+    ARG(stats && ws, "null pointer");
+    ARG(peers == NULL || (peers->bufs != NULL && peers->world >= 1 && peers->rank >= 0 && peers->rank < peers->world &&
+                          peers->world <= 256 && peers->epoch >= 1),
+        "peers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const StatLayout L(D, q);
+    if (N == 0) {
+        ARG(ws_bytes >= (L.len + PYVB_NSCAL) * sizeof(double), "workspace too small");
+        cudaError_t e0 = cudaMemsetAsync(ws, 0, (L.len + PYVB_NSCAL) * sizeof(double), st);
+        if (e0 == cudaSuccess)
+            e0 = launch_stats_reduce(D, q, (const double *)ws, 1, (const double *)ws + L.len, 1, stats, NULL, 0, NULL, 0, 0,
+                                     peers ? peers->bufs : NULL, peers ? peers->world : 1, peers ? peers->rank : 0,
+                                     peers ? peers->epoch : 0ULL, st);
+        return e0 == cudaSuccess ? PYVB_OK : cuda_fail(e0, "stats_i8 (empty shard)");
+    }
+    ARG(X && maskT && MZ && ZI && scratch && xcache, "null pointer (xcache is required)");
+    ARG(zsums || logdet, "zsums or logdet");
+    ARG(ldx >= D && (ldx % 2) == 0 && ldmz == pyvb_mz_pitch(q), "ldx, ldmz");
+    ARG(ws_bytes >= pyvb_stats_i8_workspace_bytes(N, D, q), "workspace too small");
+    int nzblk = 0, zkw = 0;
+    if (zsums) zsolve_partials(N, q, nzblk, zkw);
+    const int nch = stats_i8_nchunks(N, D, q);
+    cudaError_t e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch, st);
+    if (e == cudaSuccess) e = launch_stats_x_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st);
+    double *ws_sc = NULL;
+    const int nblk = rowscalars_nblk(N);
+    if (e == cudaSuccess && nzblk == 0) {        // no K2 partials (q = 64): the MZ column sums and the per-row scalars take a pass
+        ARG(logdet, "logdet is needed without zsums");
+        ws_sc = (double *)((char *)ws + align256((size_t)nch * L.len * sizeof(double)));
+        e = launch_mzsums(N, D, q, MZ + gw_woff(q), ldmz, MZ, ldmz, (double *)ws, nch, st);
+        if (e == cudaSuccess) e = launch_rowscalars(N, D, X, ldx, NULL, NULL, NULL, logdet, ws_sc, nblk, 1, st);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "stats_i8");
+    e = launch_stats_reduce(D, q, (const double *)ws, nch, ws_sc, nblk, stats, const_cast<double *>(xcache), 1,
+                            nzblk > 0 ? zsums : NULL, nzblk, zkw,
+                            peers ? peers->bufs : NULL, peers ? peers->world : 1, peers ? peers->rank : 0,
+                            peers ? peers->epoch : 0ULL, st);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");
+}
+
 int pyvb_f32_pitch(int q) { return f32_ncp(q); }
 int pyvb_f32_zoff(int q) { return f32_zoff(q); }
 int pyvb_f32_poff(int q) { return f32_poff(q); }

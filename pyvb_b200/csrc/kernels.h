@@ -101,6 +101,19 @@ cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wva
 cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const void *GI, const double *P0,
                             const double *gscale, const double *gl, double *MZ, int ldmz, cudaStream_t st);
 
+// K3-i8: mask-type statistics (T1, Bst) on the INT8 tensor cores + Ast on the FP64 tensor cores
+bool stats_i8_supported(int D, int q);
+int stats_i8_ncols(int q);
+long long stats_i8_npad(long long N);                       // rows of maskT / ZI rounded up to 128
+size_t stats_i8_digits_bytes(long long N, int q);           // bytes of ZI
+size_t stats_i8_scratch_len(int q, int ldmz);               // doubles: partial column maxima + zscale
+int stats_i8_nchunks(long long N, int D, int q);
+cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long long ldx, void *maskT, cudaStream_t st);
+cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,
+                            double *scratch, double *ws, int nchunks, cudaStream_t st);
+cudaError_t launch_stats_x_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
+                                double *ws_main, int nchunks, cudaStream_t st);
+
 // ---- LDS smoother, batched over sequences (kernels_lds.cu) ----
 size_t lds_smem_bytes(int T, int d);
 cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,

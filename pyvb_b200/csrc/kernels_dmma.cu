@@ -763,11 +763,15 @@ template <> struct SC<16> { static constexpr int WM = 8, WN = 1, RGW = 2, KC = 1
 template <> struct SC<32> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 1; };
 template <> struct SC<64> { static constexpr int WM = 2, WN = 4, RGW = 2, KC = 8,  ST = 3, OCC = 1, NCT = 4; };
 
-template <int Q> struct STT {
+// XO = true: only the X-type statistics Ast = (O.X)^T Zbar (the mask-type ones come from the INT8 kernel, kernels_i8.cu):
+// all warps line up along the data dimensions, the MZ tile is just the zbar columns (+ the 4 pad columns that follow
+// them, which keeps the shared-memory pitch = 4 (mod 8): conflict-free B fragments)
+template <int Q, bool XO = false> struct STT {
     using C = SC<Q>;
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7;
-    static constexpr int NGO = (PP + Q) / 8, NGX = Q / 8, NG = NGO + NGX;   // O-type: [<zz^T> | pad | zbar]; X-type: zbar
-    static constexpr int WM = C::WM, WN = C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST, NCT = C::NCT;
+    static constexpr int NGO = XO ? 0 : (PP + Q) / 8, NGX = Q / 8, NG = NGO + NGX;   // O-type: [<zz^T> | pad | zbar]; X-type: zbar
+    static constexpr int WM = XO ? C::WM * C::WN : C::WM, WN = XO ? 1 : C::WN, RGW = C::RGW, KC = C::KC, ST = XO ? 4 : C::ST;
+    static constexpr int NCT = XO ? 1 : C::NCT;
     static constexpr bool TILED = NCT > 1;      // output columns split over NCT CTAs (q = 64)
     static constexpr int NGT = (NG + NCT - 1) / NCT;
     static constexpr int NGW = (NGT + WN - 1) / WN;
@@ -776,8 +780,8 @@ template <int Q> struct STT {
     static constexpr int NCW = WM * WN;
     static constexpr int NTHR = NCW * 32;       // warp 0 doubles as the producer
     static constexpr int VP = c_gw_pitch(Q);    // pitch of the MZ rows in global memory
-    static constexpr int VPS = TILED ? c_pitch4(NGT * 8) : VP;   // ... and of the (column tile of the) rows in shared memory
-    static constexpr bool BTILE = VP <= 256;    // MZ tile through one tensor copy (box dims are limited to 256)
+    static constexpr int VPS = XO ? Q + 4 : (TILED ? c_pitch4(NGT * 8) : VP);   // ... and of the (column tile of the) rows in shared memory
+    static constexpr bool BTILE = XO || VP <= 256;    // MZ tile through one tensor copy (box dims are limited to 256)
     static constexpr int SUB_B = KC * 128;
     static constexpr int AS_B = NSUB * SUB_B, VS_B = KC * VPS * 8;
     static constexpr size_t SMEM = 1024 + (size_t)ST * (AS_B + VS_B) + 2 * ST * 8;
@@ -786,11 +790,11 @@ template <int Q> struct STT {
 
 // grid.x = number of d tiles, grid.y = row chunks.  Partial sums go to ws[chunk][stat layout]; a second
 // kernel adds the chunks in a fixed order (deterministic).
-template <int Q>
-__global__ void __launch_bounds__(STT<Q>::NTHR, SC<Q>::OCC)
+template <int Q, bool XO>
+__global__ void __launch_bounds__(STT<Q, XO>::NTHR, SC<Q>::OCC)
 stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV, long long N, int D,
                   const double *__restrict__ MZ, double *__restrict__ ws, long long rows_per_chunk) {
-    using T = STT<Q>;
+    using T = STT<Q, XO>;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
     // shared address space so that fragment loads compile to LDS, not generic LD
@@ -918,7 +922,7 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         const int cg = cg0 + j;
                         const bool otype = cg < T::NGO;
                         // X-type groups re-use the zbar columns of the tile
-                        const int col = (otype ? cg * 8 : (T::PP + (cg - T::NGO) * 8)) - cgb * 8;
+                        const int col = XO ? cg * 8 : ((otype ? cg * 8 : (T::PP + (cg - T::NGO) * 8)) - cgb * 8);
                         const double b = vs[kk * 4 * T::VPS + col];
 #pragma unroll
                         for (int rg = 0; rg < T::RGW; ++rg)
@@ -986,28 +990,43 @@ int stats_dmma_nchunks(long long N, int D, int q) {
     return (int)c;
 }
 
-template <int Q>
+template <int Q, bool XO = false>
 static cudaError_t launch_stats_q(long long N, int D, const double *X, long long ldx, const double *MZ, double *ws,
                                   int nchunks, cudaStream_t st) {
-    using T = STT<Q>;
+    using T = STT<Q, XO>;
     CUtensorMap tmX, tmV;
     cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, 16, T::KC, CU_TENSOR_MAP_SWIZZLE_128B);
     if (e != cudaSuccess) return e;
-    if (T::BTILE) {
+    if (XO) {   // the zbar columns [PP, PP + Q) and the 4 pad columns behind them
+        e = make_map(&tmV, MZ + T::PP, (uint64_t)(Q + 4), (uint64_t)N, (uint64_t)T::VP, Q + 4, T::KC, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (e != cudaSuccess) return e;
+    } else if (T::BTILE) {
         e = make_map(&tmV, MZ, (uint64_t)T::VP, (uint64_t)N, (uint64_t)T::VP, T::VP, T::KC, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (e != cudaSuccess) return e;
     } else {
         tmV = tmX;   // unused
     }
-    e = cudaFuncSetAttribute(stats_dmma_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+    e = cudaFuncSetAttribute(stats_dmma_kernel<Q, XO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     long long rpc = (N + nchunks - 1) / nchunks;
     rpc = ((rpc + T::KC - 1) / T::KC) * T::KC;                 // chunk boundaries on pipeline-step boundaries
     if (rpc < T::KC) rpc = T::KC;
     const int ndt = ((D + T::DT - 1) / T::DT) * T::NCT;
     dim3 grid((unsigned)ndt, (unsigned)nchunks);
-    stats_dmma_kernel<Q><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc);
+    stats_dmma_kernel<Q, XO><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc);
     return cudaGetLastError();
+}
+
+// Ast alone, `nchunks` row chunks of `rpc` rows (a multiple of 64: the INT8 kernel's chunks) into ws[chunk][stat layout]
+cudaError_t launch_stats_x_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
+                                double *ws_main, int nchunks, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    switch (q) {
+        case 16: return launch_stats_q<16, true>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+        case 32: return launch_stats_q<32, true>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+        case 64: return launch_stats_q<64, true>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+    }
+    return cudaErrorNotSupported;
 }
 
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,

@@ -170,7 +170,7 @@ struct I8Geom {
 size_t i8_smem_bytes(int D, int q) {
     const I8Geom g(q);
     const int nk = D / BKB;
-    return 1024 + (size_t)nk * A_B + (size_t)ST * B_B + (size_t)(g.PP + g.NC8) * 8 + (size_t)(2 * nk + 2 * ST + 4) * 8 + 16;
+    return 1024 + (size_t)nk * A_B + (size_t)ST * B_B + (size_t)(2 * g.NC8) * 8 + (size_t)(2 * nk + 2 * ST + 4) * 8 + 16;
 }
 
 // ------------------------------------------------------------------ K1-i8: qprec columns of the MZ rows
@@ -184,8 +184,8 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int nk = D / BKB;
     unsigned char *a_base = smem;                                              // [nk][128 x 64 B] resident mask block
     unsigned char *b_base = smem + (size_t)nk * A_B;                           // [ST][224 x 64 B] digit tiles
-    double *p0v = reinterpret_cast<double *>(b_base + ST * B_B);               // [PP]: packed P0, zero pad
-    double *fcol = p0v + G.PP;                                                 // [NC8]: tau * scale_c * 2^-54
+    double *p0v = reinterpret_cast<double *>(b_base + ST * B_B);               // [NC8]: packed P0, zero pad
+    double *fcol = p0v + G.NC8;                                                // [NC8]: tau * scale_c * 2^-54
     uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nk]
     uint64_t *aempty = afull + nk;                                             // [nk]
     uint64_t *full = aempty + nk;                                              // [ST]
@@ -197,7 +197,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double tau = gl[PYVB_GL_TAU];
 
-    for (int p = tid; p < G.PP; p += NTHR) {
+    for (int p = tid; p < G.NC8; p += NTHR) {
         double v = 0.0;
         if (p < G.P) {
             int i, j;
@@ -285,7 +285,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int half = (warp - 2) >> 2;                      // which 16 of the tile's 32 columns
         int tl = 0;
         for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-            const long long row = (long long)rb * BM + wq * 32 + lane;
+            const long long rowbase = (long long)rb * BM + wq * 32;
             for (int ct = 0; ct < G.NCT; ++ct, ++tl) {
                 const int c0 = ct * CT + half * 16;
                 const int buf = tl & 1;
@@ -301,29 +301,329 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[buf]);       // the accumulator buffer is free again
-                if (row < N) {
-                    double *orow = MZ + row * ldmz + c0;
+                // lane = row: 16 outputs (8 column pairs) per lane
+                double o[16];
 #pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        if (c0 + ch * 8 < G.PP) {               // PP is a multiple of 8: a chunk is entirely in or out
+                for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-                            for (int k = 0; k < 8; k += 2) {
-                                int d0[NPL], d1[NPL];
+                    for (int k = 0; k < 8; ++k) {
+                        int dg[NPL];
 #pragma unroll
-                                for (int p = 0; p < NPL; ++p) {
-                                    d0[p] = (int)a[ch][p][k];
-                                    d1[p] = (int)a[ch][p][k + 1];
-                                }
-                                const int c = c0 + ch * 8 + k;
-                                double2 o;
-                                o.x = fma(fcol[c], combine7(d0), p0v[c]);
-                                o.y = fma(fcol[c + 1], combine7(d1), p0v[c + 1]);
-                                *reinterpret_cast<double2 *>(orow + ch * 8 + k) = o;
-                            }
+                        for (int p = 0; p < NPL; ++p) dg[p] = (int)a[ch][p][k];
+                        const int c = c0 + ch * 8 + k;
+                        o[ch * 8 + k] = fma(fcol[c], combine7(dg), p0v[c]);
+                    }
+                // 8 x 8 transposition of the column pairs inside every group of 8 lanes (three butterfly stages): lane
+                // (g, k) ends up with pair k of the rows 8g .. 8g+7, so that one store instruction covers 4 rows x 128
+                // contiguous bytes instead of 32 rows x 16 bytes (32 cache lines per instruction made the stores,
+                // not the MMAs, the bottleneck)
+#pragma unroll
+                for (int m = 1; m < 8; m <<= 1) {
+                    const bool up = (lane & m) != 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k & m) continue;
+                        const int lo = 2 * k, hi = 2 * (k | m);
+                        const double s0 = up ? o[lo] : o[hi], s1 = up ? o[lo + 1] : o[hi + 1];
+                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, m), r1 = __shfl_xor_sync(0xffffffffu, s1, m);
+                        if (up) {
+                            o[lo] = r0;
+                            o[lo + 1] = r1;
+                        } else {
+                            o[hi] = r0;
+                            o[hi + 1] = r1;
                         }
                     }
                 }
+                const int col = c0 + 2 * (lane & 7);
+                if (col < G.PP) {                               // PP is even: a pair is entirely in or out
+                    const long long r0 = rowbase + 8 * (lane >> 3);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (r0 + j < N)
+                            *reinterpret_cast<double2 *>(MZ + (r0 + j) * ldmz + col) = make_double2(o[2 * j], o[2 * j + 1]);
+                }
             }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+
+// =====================================================================================================================
+// K3-i8: the mask-type sufficient statistics  T1 = O^T vec<zz^T>,  Bst = O^T Zbar  (hstack, nodes/nodes_todo.py:50-61)
+// on the INT8 tensor cores.  Same idea as K1-i8 with the roles turned: the contraction index is the ROW n, so both
+// operands are needed "n contiguous":
+//   maskT [D][npad]                      int8, the transposed mask (static, prepared once per data set)
+//   ZI    [ct][plane][c % 32][npad]      int8, the seven balanced base-256 digit planes of the MZ columns
+//                                        c in [0, P + q) = [<zz^T> packed | zbar], rewritten after every Z step with one
+//                                        fixed-point scale per column, zscale_c = max_n |MZ[n][c]| (colmax pass)
+// Work item = (block of 128 data dimensions, column tile of 32, row chunk): one TMEM accumulator (224 columns) summed
+// over the whole chunk, then recombined to FP64 and written to the chunk's partial-sum buffer (the deterministic
+// second stage, stats_reduce_kernel, adds the chunks).  Items are dealt round-robin to 148 persistent CTAs, chunk-major,
+// so that the CTAs running at the same time share their operand tiles through L2.
+constexpr int SST = 6;                                   // stages of the K3-i8 ring (22 KB each)
+constexpr int CM_BLOCKS = 148 * 4;                       // partial column maxima
+
+// column maxima of |MZ| over a block of rows: pm[blk][ldmz].  Warp per row, lane l owns the columns l, l + 32, ...
+// (KPL of them, in registers): every row is KPL independent coalesced loads.
+template <int KPL>
+__global__ void __launch_bounds__(256)
+colmax_kernel(long long N, int ldmz, const double *__restrict__ MZ, double *__restrict__ pm, long long rows_per_blk) {
+    extern __shared__ double cm_sh[];                       // [ldmz]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long r0 = (long long)blockIdx.x * rows_per_blk;
+    long long r1 = r0 + rows_per_blk;
+    if (r1 > N) r1 = N;
+    double m[KPL];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) m[k] = 0.0;
+#pragma unroll 2
+    for (long long n = r0 + warp; n < r1; n += 8) {
+        const double *row = MZ + n * ldmz;
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) {
+            const int c = lane + 32 * k;
+            if (c < ldmz) m[k] = fmax(m[k], fabs(row[c]));
+        }
+    }
+    for (int w = 0; w < 8; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                const int c = lane + 32 * k;
+                if (c < ldmz) cm_sh[c] = (w == 0) ? m[k] : fmax(cm_sh[c], m[k]);
+            }
+        }
+        __syncthreads();
+    }
+    for (int c = threadIdx.x; c < ldmz; c += 256) pm[(size_t)blockIdx.x * ldmz + c] = cm_sh[c];
+}
+__global__ void __launch_bounds__(256)
+colmax_reduce_kernel(int ncols, int nvalid, int ldmz, const double *__restrict__ pm, int nblk, double *__restrict__ zscale) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= ncols) return;
+    double m = 0.0;
+    if (c < nvalid)
+        for (int b = 0; b < nblk; ++b) m = fmax(m, pm[(size_t)b * ldmz + c]);
+    zscale[c] = (m > 0.0 && m < 1e300) ? m : 1.0;           // NaN / inf rows (non-PD) poison only themselves downstream
+}
+
+// MZ rows -> digit planes, transposed: CTA = 128 rows x 32 columns
+__global__ void __launch_bounds__(256)
+digitize_kernel(long long N, long long npad, int ldmz, int nvalid, const double *__restrict__ MZ,
+                const double *__restrict__ zscale, signed char *__restrict__ ZI) {
+    constexpr int PITCH = 132;                              // bytes per (plane, column) row in shared memory: 33 words
+    __shared__ __align__(16) signed char sh[NPL * CT * PITCH];
+    const int ct = blockIdx.y;
+    const long long n0 = (long long)blockIdx.x * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = ct * CT + lane;
+    const bool cv = c < nvalid;
+    const double inv = cv ? 18014398509481984.0 / zscale[c] : 0.0;    // 2^54 / scale
+#pragma unroll 4
+    for (int r = warp; r < 128; r += 8) {
+        const long long n = n0 + r;
+        double x = 0.0;
+        if (cv && n < N) x = MZ[n * ldmz + c];
+        double t = x * inv;
+        t = (fabs(t) <= 18014398509481984.0) ? t : 0.0;      // NaN / inf (a non-PD row, reported separately) -> 0
+        long long v = __double2ll_rn(t);
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+            const long long dg = ((v + 128) & 255) - 128;
+            sh[(p * CT + lane) * PITCH + r] = (signed char)dg;
+            v = (v - dg) >> 8;
+        }
+    }
+    __syncthreads();
+    // rows (plane, column) of 128 bytes -> ZI[ct][plane][column][n0 .. n0 + 128): one warp writes one 128-byte row
+    const int nrem = (N - n0 < 128) ? (int)(N - n0) : 128;
+    for (int row = warp; row < NPL * CT; row += 8) {
+        signed char *dst = ZI + ((size_t)ct * NPL * CT + row) * npad + n0;
+        const int w = *reinterpret_cast<const int *>(&sh[row * PITCH + lane * 4]);
+        if (lane * 4 + 3 < nrem) {
+            *reinterpret_cast<int *>(dst + lane * 4) = w;
+        } else {
+            for (int b = 0; b < 4; ++b)
+                if (lane * 4 + b < nrem) dst[lane * 4 + b] = (signed char)(w >> (8 * b));
+        }
+    }
+}
+
+// X [N][ldx] -> maskT [D][npad] (1 = observed); CTA = 128 rows x 32 data dimensions
+__global__ void __launch_bounds__(256)
+prepare_maskT_kernel(long long N, int D, long long npad, const double *__restrict__ X, long long ldx,
+                     signed char *__restrict__ maskT) {
+    constexpr int PITCH = 132;
+    __shared__ __align__(16) signed char sh[32 * PITCH];
+    const int d0 = blockIdx.y * 32;
+    const long long n0 = (long long)blockIdx.x * 128;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = d0 + lane;
+    for (int r = warp; r < 128; r += 8) {
+        const long long n = n0 + r;
+        signed char m = 0;
+        if (d < D && n < N) {
+            const double x = X[n * ldx + d];
+            m = (x == x) ? 1 : 0;
+        }
+        sh[lane * PITCH + r] = m;
+    }
+    __syncthreads();
+    const int nrem = (N - n0 < 128) ? (int)(N - n0) : 128;
+    for (int row = warp; row < 32; row += 8) {
+        if (d0 + row >= D) break;
+        signed char *dst = maskT + (size_t)(d0 + row) * npad + n0;
+        const int w = *reinterpret_cast<const int *>(&sh[row * PITCH + lane * 4]);
+        if (lane * 4 + 3 < nrem) {
+            *reinterpret_cast<int *>(dst + lane * 4) = w;
+        } else {
+            for (int b = 0; b < 4; ++b)
+                if (lane * 4 + b < nrem) dst[lane * 4 + b] = (signed char)(w >> (8 * b));
+        }
+    }
+}
+
+size_t si8_smem_bytes(int q) {
+    return 1024 + (size_t)SST * (A_B + B_B) + (size_t)((i_tri(q) + q + 31) & ~31) * 8 + (size_t)(2 * SST + 4) * 8 + 16;
+}
+
+__global__ void __launch_bounds__(NTHR, 1)
+stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long N, int D, int q,
+                const double *__restrict__ zscale, double *__restrict__ ws, long long rows_per_chunk, int nchunks, int ndb,
+                int nct) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    const int P = i_tri(q), NCZ = (P + q + 31) & ~31;
+    unsigned char *st_base = smem;                                             // [SST][A 8 KB | B 14 KB]
+    double *fcol = reinterpret_cast<double *>(smem + (size_t)SST * (A_B + B_B));   // [NCZ]: zscale_c * 2^-54
+    uint64_t *full = reinterpret_cast<uint64_t *>(fcol + NCZ);
+    uint64_t *empty = full + SST;
+    uint64_t *tfull = empty + SST;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tbase = reinterpret_cast<uint32_t *>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nitems = ndb * nct * nchunks;
+    for (int c = tid; c < NCZ; c += NTHR) fcol[c] = zscale[c] * 5.5511151231257827e-17;   // 2^-54
+    if (tid == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < SST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 8);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tbase, 512);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tbase;
+
+    // item -> (chunk, dblk, ct), chunk-major; K steps of the chunk
+    auto item_geom = [&](int item, int &chunk, int &db, int &ct, long long &r0, int &nsteps) {
+        chunk = item / (ndb * nct);
+        const int rem = item - chunk * (ndb * nct);
+        db = rem / nct;
+        ct = rem - db * nct;
+        r0 = (long long)chunk * rows_per_chunk;
+        long long r1 = r0 + rows_per_chunk;
+        if (r1 > N) r1 = N;
+        nsteps = (r1 > r0) ? (int)((r1 - r0 + BKB - 1) / BKB) : 0;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                int chunk, db, ct, nsteps;
+                long long r0;
+                item_geom(item, chunk, db, ct, r0, nsteps);
+                for (int k = 0; k < nsteps; ++k, ++it) {
+                    const int s = it % SST;
+                    umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / SST) & 1) ^ 1));
+                    unsigned char *st = st_base + (size_t)s * (A_B + B_B);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
+                    const int n = (int)(r0 + (long long)k * BKB);
+                    tma_load_3d_i8(st, &tmA, n, db * BM, 0, &full[s]);             // 128 data dimensions x 64 rows
+                    tma_load_3d_i8(st + A_B, &tmB, n, 0, ct, &full[s]);            // 7 planes x 32 columns x 64 rows
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
+            int it = 0, tl = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tl) {
+                int chunk, db, ct, nsteps;
+                long long r0;
+                item_geom(item, chunk, db, ct, r0, nsteps);
+                const int buf = tl & 1;
+                umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));
+                umma::fence_after_sync();
+                const uint32_t dacc = tmem + (uint32_t)(buf * 256);
+                for (int k = 0; k < nsteps; ++k, ++it) {
+                    const int s = it % SST;
+                    umma::mbar_wait_bounded(&full[s], (uint32_t)((it / SST) & 1));
+                    umma::fence_after_sync();
+                    const uint32_t a0 = smem_u32(st_base + (size_t)s * (A_B + B_B));
+#pragma unroll
+                    for (int ks = 0; ks < BKB / 32; ++ks)
+                        umma::mma_i8(dacc, umma::desc_kmajor_sw64(a0, ks), umma::desc_kmajor_sw64(a0 + A_B, ks), idesc,
+                                     (k | ks) ? 1u : 0u);
+                    umma::mma_commit(&empty[s]);
+                }
+                umma::mma_commit(&tfull[buf]);
+            }
+        }
+    } else {
+        const StatLayout L(D, q);
+        const int wq = warp & 3, half = (warp - 2) >> 2;
+        int tl = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tl) {
+            int chunk, db, ct, nsteps;
+            long long r0;
+            item_geom(item, chunk, db, ct, r0, nsteps);
+            const int buf = tl & 1;
+            const int d = db * BM + wq * 32 + lane;
+            const int c0 = ct * CT + half * 16;
+            double *out = ws + (size_t)chunk * L.len;
+            umma::mbar_wait_bounded(&tfull[buf], (uint32_t)((tl >> 1) & 1));
+            umma::fence_after_sync();
+            const uint32_t taddr = tmem + (uint32_t)(buf * 256 + half * 16) + ((uint32_t)(wq * 32) << 16);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t a[NPL][8];
+                if (nsteps > 0) {                                  // an empty chunk contributes zeros (nothing was accumulated)
+#pragma unroll
+                    for (int p = 0; p < NPL; ++p) tmem_ld8(taddr + (uint32_t)(p * CT + ch * 8), a[p]);
+                    umma::tmem_ld_wait();
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    double v = 0.0;
+                    if (nsteps > 0) {
+#pragma unroll
+                        for (int p = NPL - 1; p >= 0; --p) v = fma(v, 256.0, i2d((int)a[p][k]));   // |a| <= 128 rows: exact steps
+                    }
+                    const int c = c0 + ch * 8 + k;
+                    if (d < D) {
+                        if (c < P) out[L.t1 + (size_t)d * P + c] = fcol[c] * v;
+                        else if (c < P + q) out[L.bst + (size_t)d * q + (c - P)] = fcol[c] * v;
+                    }
+                }
+            }
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[buf]);
         }
     }
     umma::fence_before_sync();
@@ -369,6 +669,90 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
     const long long nrb = (N + BM - 1) / BM;
     const int grid = (int)(nrb < 148 ? nrb : 148);
     zstep_i8_kernel<<<grid, NTHR, smem, st>>>(tmA, tmB, N, D, q, P0, gscale, gl, MZ, ldmz, (int)nrb);
+    return cudaGetLastError();
+}
+
+// ---- K3-i8 host side
+bool stats_i8_supported(int D, int q) { return (q == 16 || q == 32 || q == 64) && D >= 16 && (D % 16) == 0; }
+int stats_i8_ncols(int q) { return (i_tri(q) + q + 31) & ~31; }
+long long stats_i8_npad(long long N) { return (N + 127) / 128 * 128; }
+size_t stats_i8_digits_bytes(long long N, int q) { return (size_t)stats_i8_ncols(q) * NPL * (size_t)stats_i8_npad(N); }
+size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * ldmz + stats_i8_ncols(q); }
+
+static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
+// chunks: items = ndb * nct * nchunks a whole number of rounds over 148 CTAs, chunks of >= 32 K steps, <= 2^23 rows
+int stats_i8_nchunks(long long N, int D, int q) {
+    const long long per = (long long)((D + BM - 1) / BM) * (stats_i8_ncols(q) / CT);
+    const long long step = 148 / gcd_ll(148, per);
+    long long by_rows = N / (32LL * BKB);
+    if (by_rows < 1) by_rows = 1;
+    long long k = (6 * 148LL + per * step - 1) / (per * step);      // ~6 items per CTA
+    if (k < 1) k = 1;
+    long long c = k * step;
+    if (c > by_rows) c = (by_rows >= step) ? (by_rows / step) * step : by_rows;
+    const long long cmin = (N + (1LL << 23) - 1) >> 23;
+    if (c < cmin) c = cmin;
+    if (c > 1024) c = 1024;
+    return (int)c;
+}
+long long stats_i8_rows_per_chunk(long long N, int nchunks) {
+    long long rpc = (N + nchunks - 1) / nchunks;
+    rpc = (rpc + BKB - 1) / BKB * BKB;
+    return rpc < BKB ? BKB : rpc;
+}
+
+cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long long ldx, void *maskT, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)((D + 31) / 32));
+    prepare_maskT_kernel<<<grid, 256, 0, st>>>(N, D, stats_i8_npad(N), X, ldx, static_cast<signed char *>(maskT));
+    return cudaGetLastError();
+}
+
+// colmax -> zscale -> digit planes of the MZ rows -> T1, Bst partial sums of every row chunk in ws[chunk][stat layout]
+cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,
+                            double *scratch, double *ws, int nchunks, cudaStream_t st) {
+    if (N <= 0) return cudaSuccess;
+    const int P = i_tri(q), NCZ = stats_i8_ncols(q), nct = NCZ / CT, ndb = (D + BM - 1) / BM;
+    const long long npad = stats_i8_npad(N);
+    double *pm = scratch, *zscale = scratch + (size_t)CM_BLOCKS * ldmz;
+    int nblk = CM_BLOCKS;
+    long long rpb = (N + nblk - 1) / nblk;
+    if (rpb < 64) rpb = 64;
+    nblk = (int)((N + rpb - 1) / rpb);
+    const size_t cms = (size_t)ldmz * sizeof(double);
+    if (q == 16) colmax_kernel<5><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
+    else if (q == 32) colmax_kernel<18><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
+    else colmax_kernel<68><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
+    colmax_reduce_kernel<<<(NCZ + 255) / 256, 256, 0, st>>>(NCZ, P + q, ldmz, pm, nblk, zscale);
+    dim3 gd((unsigned)((N + 127) / 128), (unsigned)nct);
+    digitize_kernel<<<gd, 256, 0, st>>>(N, npad, ldmz, P + q, MZ, zscale, static_cast<signed char *>(ZI));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    CUtensorMap tmA, tmB;
+    {   // maskT [D][npad] with N valid columns; ZI [nct][224][npad] with N valid columns: reads past N are zero filled
+        EncodeTiledFn enc = get_encode_i8();
+        if (!enc) return cudaErrorNotSupported;
+        cuuint32_t es[3] = {1, 1, 1};
+        cuuint64_t da[3] = {(cuuint64_t)N, (cuuint64_t)D, 1}, sa[2] = {(cuuint64_t)npad, (cuuint64_t)npad * D};
+        cuuint32_t ba[3] = {BKB, BM, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(maskT), da, sa, ba, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+        cuuint64_t db[3] = {(cuuint64_t)N, (cuuint64_t)(NPL * CT), (cuuint64_t)nct};
+        cuuint64_t sb[2] = {(cuuint64_t)npad, (cuuint64_t)npad * NPL * CT};
+        cuuint32_t bb[3] = {BKB, NPL * CT, 1};
+        r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ZI, db, sb, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    const size_t smem = si8_smem_bytes(q);
+    e = cudaFuncSetAttribute(stats_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long nitems = (long long)ndb * nct * nchunks;
+    const int grid = (int)(nitems < 148 ? nitems : 148);
+    stats_i8_kernel<<<grid, NTHR, smem, st>>>(tmA, tmB, N, D, q, zscale, ws, stats_i8_rows_per_chunk(N, nchunks), nchunks,
+                                              ndb, nct);
     return cudaGetLastError();
 }
 

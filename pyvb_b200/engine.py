@@ -134,6 +134,10 @@ class PlateEngine(object):
             self.GI = torch.empty(int(self.lib.pyvb_i8_digits_bytes(D, q)), dtype=torch.int8, device=dev)
             self.gscale = torch.empty(int(self.lib.pyvb_i8_ncols(q)), dtype=f64, device=dev)
         self._mask_valid = False
+        # ... and the mask-type statistics (K3-i8): transposed mask + digit planes of the MZ rows
+        self.use_i8_stats = bool(self.use_i8 and self.lib.pyvb_stats_i8_supported(D, q)
+                                 and os.environ.get("PYVB_I8_STATS", "1") != "0")
+        self._maskT_valid = False
         n_eff = self._allreduce_scalar(float(n_eff_local))
         self.n_rows_total = int(self._allreduce_scalar(float(N)))
 
@@ -164,6 +168,16 @@ class PlateEngine(object):
         self.stats = torch.zeros(self.L.len, dtype=f64, device=dev)
         assert self.L.len == int(self.lib.pyvb_stats_len(D, q))
         self.ws_bytes = int(self.lib.pyvb_stats_workspace_bytes(N, D, q, ALGO_F32 if self.f32 else self.algo))
+        if self.use_i8_stats:
+            try:
+                self.npad = int(self.lib.pyvb_stats_i8_npad(N))
+                self.maskT = torch.empty(D, self.npad, dtype=torch.int8, device=dev)
+                self.ZI = torch.empty(int(self.lib.pyvb_stats_i8_digits_bytes(N, q)), dtype=torch.int8, device=dev)
+                self.i8_scratch = torch.empty(int(self.lib.pyvb_stats_i8_scratch_len(q)), dtype=f64, device=dev)
+                self.ws_bytes = max(self.ws_bytes, int(self.lib.pyvb_stats_i8_workspace_bytes(N, D, q)))
+            except torch.cuda.OutOfMemoryError:          # the digit planes are 7 bytes per MZ entry: DMMA statistics instead
+                self.maskT = self.ZI = self.i8_scratch = None
+                self.use_i8_stats = False
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=dev)
         if self.f32:
             self._xcache_valid = True
@@ -335,6 +349,7 @@ class PlateEngine(object):
         self.X.copy_(X, non_blocking=True)
         self._xcache_valid = False
         self._mask_valid = False
+        self._maskT_valid = False
         self._stats_fresh = False
 
     def get_state(self):
@@ -400,6 +415,24 @@ class PlateEngine(object):
                                          self.peers.next() if (self.peers is not None and self.distributed) else None,
                                          self._stream())
             _cabi.check(rc, "pyvb_stats_f32")
+            if self.distributed and self.peers is None:
+                allreduce_stats(self.stats)
+            self._stats_fresh = True
+            return
+        if self.use_i8_stats and self._xcache_valid and self.N > 0:
+            if not self._maskT_valid:
+                _cabi.check(self.lib.pyvb_prepare_maskt_i8(self.N, self.D, self.X.data_ptr(), self.D,
+                                                           self.maskT.data_ptr(), self._stream()), "pyvb_prepare_maskt_i8")
+                self._maskT_valid = True
+            rc = self.lib.pyvb_stats_i8_f64(self.N, self.D, self.q, self.X.data_ptr(), self.D, self.maskT.data_ptr(),
+                                            self.MZ.data_ptr(), self.ldmz, self.logdet.data_ptr(), self.ZI.data_ptr(),
+                                            self.i8_scratch.data_ptr(), self.stats.data_ptr(), self.ws.data_ptr(),
+                                            self.ws_bytes, self.xcache.data_ptr(),
+                                            self.zsums.data_ptr() if (self.zsums is not None and self._zsums_valid) else 0,
+                                            self.peers.next() if (self.peers is not None and self.distributed) else None,
+                                            self._stream())
+            _cabi.check(rc, "pyvb_stats_i8_f64")
+            self.i8_stats_calls = getattr(self, "i8_stats_calls", 0) + 1
             if self.distributed and self.peers is None:
                 allreduce_stats(self.stats)
             self._stats_fresh = True
@@ -561,6 +594,7 @@ class PlateEngine(object):
         self._ensure_gw()
         self._xcache_valid = False
         self._mask_valid = False
+        self._maskT_valid = False
         step = (N + nchunks - 1) // nchunks
         step = (step + 63) // 64 * 64
         for lo in range(0, N, step):

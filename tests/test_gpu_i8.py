@@ -39,15 +39,19 @@ def test_i8_zstep_matches_dmma(eng, shape):
     assert ei.use_i8 and not ed.use_i8
     for e in (ed, ei):
         e.set_state(init)
+        e._ensure_stats()           # fills the cache of the X-only sums (the INT8 statistics need it)
         e.update_Z()
         e._ensure_stats()
+    assert getattr(ei, "i8_stats_calls", 0) == 1 and ei.use_i8_stats
     sd, si = ed.get_state(), ei.get_state()
     for k in ("Zbar", "Sig"):
         assert tensor_rel(si[k], sd[k]) < 1e-11, (shape, k)
     assert tensor_rel(ei.M2.contiguous().cpu().numpy(), ed.M2.contiguous().cpu().numpy()) < 1e-11
     ld, li = ed.logdet.cpu().numpy(), ei.logdet.cpu().numpy()
     assert np.max(np.abs(ld - li)) < 1e-11 * max(1.0, np.max(np.abs(ld)))
-    assert tensor_rel(ei.stats.cpu().numpy()[:ei.L.scal], ed.stats.cpu().numpy()[:ed.L.scal]) < 1e-11
+    vd, vi = ed.L.views(ed.stats.cpu().numpy()), ei.L.views(ei.stats.cpu().numpy())
+    for k in ("T1", "Bst", "Ast", "cnt", "colx", "S", "zsum"):
+        assert tensor_rel(vi[k], vd[k]) < 1e-11, (shape, k, tensor_rel(vi[k], vd[k]))
     ei.check()
 
 
@@ -102,6 +106,7 @@ def test_i8_iterations_match_oracle(eng, shape):
         _cmp_state(st, o.state(), ("Wbar", "Wvar", "mu", "muvar", "Zbar", "Sig"), (shape, it))
         assert abs(st["qb"] - o.qb) <= TOL * abs(o.qb)
         assert abs(got - ref) <= TOL * abs(ref), (shape, it, got, ref)
+    assert getattr(e, "i8_stats_calls", 0) >= 4
     e.check()
 
 
