@@ -257,7 +257,10 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
 }
 
 int pyvb_i8_supported(int D, int q) { return (i8_supported(D, q) && dmma_supported(D, q)) ? 1 : 0; }
-size_t pyvb_i8_digits_bytes(int D, int q) { return i8_digits_bytes(D, q); }
+// digit planes of G, then (256-byte aligned) the compact [wbar | mu] array of the eta kernel
+size_t pyvb_i8_digits_bytes(int D, int q) {
+    return align256(i8_digits_bytes(D, q)) + align256((size_t)D * zstep_eta_pitch(q) * sizeof(double));
+}
 int pyvb_i8_ncols(int q) { return i8_ncols(q); }
 
 int pyvb_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, void *stream) {
@@ -282,7 +285,8 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, st);
     if (e == cudaSuccess) e = launch_zstep_i8(N, D, q, mask, GI, P0, gscale, gl, MZ, (int)ldmz, st);
-    if (e == cudaSuccess) e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, P0, h0, gl, MZ, st);
+    double *weta = (double *)((char *)GI + align256(i8_digits_bytes(D, q)));
+    if (e == cudaSuccess) e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, weta, P0, h0, gl, MZ, st);
     if (e == cudaSuccess && !k1_only) e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_i8");
 }

@@ -48,8 +48,10 @@ bool dmma_supported(int D, int q);
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                               int ldg, const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
                               double *logdet, double *zsums, int k1_only, cudaStream_t st);
+int zstep_eta_pitch(int q);
 cudaError_t launch_zstep_eta_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
-                                  const double *P0, const double *h0, double *gl, double *MZ, cudaStream_t st);
+                                  double *weta, const double *P0, const double *h0, double *gl, double *MZ,
+                                  cudaStream_t st);
 cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
                           cudaStream_t st);
 // K2 leaves nblk partials of kw doubles each in zsums (0, 0: no fast K2 for this q)

@@ -111,7 +111,10 @@ __host__ __device__ constexpr int c_pitch4(int need) {      // smallest pitch >=
 template <int Q, bool ETA = false> struct ZT {
     using C = ZC<Q>;
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, NGO = PP / 8, NGE = Q / 8, NG = NGO + NGE;
-    static constexpr int WM = ETA ? C::WM * C::WN : C::WM, WN = ETA ? 1 : C::WN, RGW = C::RGW, KC = C::KC, ST = C::ST;
+    // ETA: 2 x Q / 8 tensor-core instructions per 4 x 8 data entries -- the kernel streams X at HBM speed only with many
+    // small stages in flight (8 stages, 2 CTAs per SM: > 100 KB outstanding per SM)
+    static constexpr int WM = ETA ? C::WM * C::WN : C::WM, WN = ETA ? 1 : C::WN, RGW = C::RGW, KC = C::KC;
+    static constexpr int ST = ETA ? 8 : C::ST, OCC = ETA ? 2 : C::OCC;
     static constexpr int NCT = ETA ? 1 : C::NCT;
     static constexpr bool TILED = ETA || NCT > 1;
     static constexpr int CG0 = ETA ? NGO : 0;          // first column group this kernel computes
@@ -270,7 +273,7 @@ __device__ __forceinline__ void k2_solve(const double *const (&Arow)[MI], const 
 // straight from registers with 16-byte stores (8 rows x 64 contiguous bytes per warp instruction), so there is no
 // staging buffer, no per-tile prologue and no pipeline drain between tiles.
 template <int Q, bool ETA>
-__global__ void __launch_bounds__(ZT<Q, ETA>::NTHR, ZC<Q>::OCC)
+__global__ void __launch_bounds__(ZT<Q, ETA>::NTHR, ZT<Q, ETA>::OCC)
 zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, const double *__restrict__ Gw,
                   const double *__restrict__ P0, const double *__restrict__ h0, const double *__restrict__ gl,
                   double *__restrict__ MZ, long long ntiles) {
@@ -324,11 +327,12 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         const int ngt = (T::NG - cgb < T::NGT) ? (T::NG - cgb) : T::NGT;
         const bool need_mu = cgb + ngt > T::NGO;
         mbar_wait(&empty[s], ph ^ 1);
-        if (!T::TILED) {
+        if (!T::TILED || ETA) {
+            // ETA: Gw is the compact [wbar (Q) | mu | pad] array with row pitch GP (pack_weta_kernel): the chunk is one copy
             if (lane == 0) {
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::GS_B));
                 tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);   // rows past N: zero fill
-                bulk_g2s(gs_base + s * T::GS_B, Gw + (size_t)kc * T::KC * T::LDG, T::GS_B, &full[s]);
+                bulk_g2s(gs_base + s * T::GS_B, Gw + (size_t)kc * T::KC * (ETA ? T::GP : T::LDG), T::GS_B, &full[s]);
             }
         } else {
             // one Gw row segment per lane (+ the mu pair for the tile that holds the eta columns)
@@ -692,19 +696,33 @@ static cudaError_t launch_k1_q(long long N, int D, const double *X, long long ld
     e = cudaFuncSetAttribute(zstep_dmma_kernel<Q, ETA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     const long long ntiles = ((N + T::R - 1) / T::R) * T::NCT;
-    const long long blocks = ntiles < 148LL * ZC<Q>::OCC ? ntiles : 148LL * ZC<Q>::OCC;
+    const long long blocks = ntiles < 148LL * T::OCC ? ntiles : 148LL * T::OCC;
     zstep_dmma_kernel<Q, ETA><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
     return cudaGetLastError();
 }
 
-// the eta columns alone (see ZT<Q, true>): MZ rows get [.. | eta] with the qprec columns left untouched
+// compact copy of the [wbar | mu] columns of Gw: weta[d][0..q) = wbar_d, weta[d][q] = mu_d, zero pad to the pitch
+__global__ void __launch_bounds__(256)
+pack_weta_kernel(int D, int q, int ldg, int pp, int gp, const double *__restrict__ Gw, double *__restrict__ weta) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= D * gp) return;
+    const int d = e / gp, c = e - d * gp;
+    weta[e] = (c <= q) ? Gw[(size_t)d * ldg + pp + c] : 0.0;
+}
+int zstep_eta_pitch(int q) { return c_pitch4(q + 2); }
+
+// the eta columns alone (see ZT<Q, true>): MZ rows get [.. | eta] with the qprec columns left untouched.
+// weta: scratch of D * zstep_eta_pitch(q) doubles
 cudaError_t launch_zstep_eta_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
-                                  const double *P0, const double *h0, double *gl, double *MZ, cudaStream_t st) {
+                                  double *weta, const double *P0, const double *h0, double *gl, double *MZ,
+                                  cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
+    const int gp = zstep_eta_pitch(q);
+    pack_weta_kernel<<<(D * gp + 255) / 256, 256, 0, st>>>(D, q, c_gw_pitch(q), (c_tri(q) + 7) & ~7, gp, Gw, weta);
     switch (q) {
-        case 16: return launch_k1_q<16, true>(N, D, X, ldx, Gw, P0, h0, gl, MZ, st);
-        case 32: return launch_k1_q<32, true>(N, D, X, ldx, Gw, P0, h0, gl, MZ, st);
-        case 64: return launch_k1_q<64, true>(N, D, X, ldx, Gw, P0, h0, gl, MZ, st);
+        case 16: return launch_k1_q<16, true>(N, D, X, ldx, weta, P0, h0, gl, MZ, st);
+        case 32: return launch_k1_q<32, true>(N, D, X, ldx, weta, P0, h0, gl, MZ, st);
+        case 64: return launch_k1_q<64, true>(N, D, X, ldx, weta, P0, h0, gl, MZ, st);
     }
     return cudaErrorNotSupported;
 }

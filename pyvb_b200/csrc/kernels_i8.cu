@@ -401,14 +401,16 @@ colmax_kernel(long long N, int ldmz, const double *__restrict__ MZ, double *__re
     }
     for (int c = threadIdx.x; c < ldmz; c += 256) pm[(size_t)blockIdx.x * ldmz + c] = cm_sh[c];
 }
+// one warp per column: max over the row-block partials
 __global__ void __launch_bounds__(256)
 colmax_reduce_kernel(int ncols, int nvalid, int ldmz, const double *__restrict__ pm, int nblk, double *__restrict__ zscale) {
-    const int c = blockIdx.x * 256 + threadIdx.x;
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ncols) return;
     double m = 0.0;
     if (c < nvalid)
-        for (int b = 0; b < nblk; ++b) m = fmax(m, pm[(size_t)b * ldmz + c]);
-    zscale[c] = (m > 0.0 && m < 1e300) ? m : 1.0;           // NaN / inf rows (non-PD) poison only themselves downstream
+        for (int b = lane; b < nblk; b += 32) m = fmax(m, pm[(size_t)b * ldmz + c]);
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) zscale[c] = (m > 0.0 && m < 1e300) ? m : 1.0;   // NaN / inf rows (non-PD) are reported by K2, not here
 }
 
 // MZ rows -> digit planes, transposed: CTA = 128 rows x 32 columns
@@ -423,19 +425,30 @@ digitize_kernel(long long N, long long npad, int ldmz, int nvalid, const double 
     const int c = ct * CT + lane;
     const bool cv = c < nvalid;
     const double inv = cv ? 18014398509481984.0 / zscale[c] : 0.0;    // 2^54 / scale
-#pragma unroll 4
-    for (int r = warp; r < 128; r += 8) {
-        const long long n = n0 + r;
-        double x = 0.0;
-        if (cv && n < N) x = MZ[n * ldmz + c];
-        double t = x * inv;
-        t = (fabs(t) <= 18014398509481984.0) ? t : 0.0;      // NaN / inf (a non-PD row, reported separately) -> 0
-        long long v = __double2ll_rn(t);
+    // v + sum_t 128 256^t has the unsigned bytes (digit_t + 128); flipping bit 7 of every byte gives the signed digits.
+    // A warp takes 16 consecutive rows, four at a time: one 32-bit shared-memory store per plane and four rows.
+    constexpr unsigned long long BIAS = 0x0080808080808080ULL;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int r = warp * 16 + g * 4;
+        unsigned int lo[4], hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long n = n0 + r + k;
+            double x = 0.0;
+            if (cv && n < N) x = MZ[n * ldmz + c];
+            double t = x * inv;
+            t = (fabs(t) <= 18014398509481984.0) ? t : 0.0;  // NaN / inf (a non-PD row, reported separately) -> 0
+            const unsigned long long u = ((unsigned long long)__double2ll_rn(t) + BIAS) ^ BIAS;
+            lo[k] = (unsigned int)u;
+            hi[k] = (unsigned int)(u >> 32);
+        }
 #pragma unroll
         for (int p = 0; p < NPL; ++p) {
-            const long long dg = ((v + 128) & 255) - 128;
-            sh[(p * CT + lane) * PITCH + r] = (signed char)dg;
-            v = (v - dg) >> 8;
+            const unsigned int *w = (p < 4) ? lo : hi;
+            const unsigned int sel = (unsigned)(p & 3) | ((unsigned)(4 + (p & 3)) << 4);
+            const unsigned int w01 = __byte_perm(w[0], w[1], sel), w23 = __byte_perm(w[2], w[3], sel);
+            *reinterpret_cast<unsigned int *>(&sh[(p * CT + lane) * PITCH + r]) = __byte_perm(w01, w23, 0x5410);
         }
     }
     __syncthreads();
@@ -723,7 +736,7 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
     if (q == 16) colmax_kernel<5><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
     else if (q == 32) colmax_kernel<18><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
     else colmax_kernel<68><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-    colmax_reduce_kernel<<<(NCZ + 255) / 256, 256, 0, st>>>(NCZ, P + q, ldmz, pm, nblk, zscale);
+    colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, ldmz, pm, nblk, zscale);
     dim3 gd((unsigned)((N + 127) / 128), (unsigned)nct);
     digitize_kernel<<<gd, 256, 0, st>>>(N, npad, ldmz, P + q, MZ, zscale, static_cast<signed char *>(ZI));
     cudaError_t e = cudaGetLastError();
