@@ -349,8 +349,25 @@ def run_ours(a):
 
     eng._ensure_gw()
     ms_z = time_calls(lambda: eng.update_Z(), 5)
-    ms_k1 = ms_k2 = None
-    if lib.pyvb_algo_supported(2, a.D, a.q):
+    ms_k1 = ms_k2 = ms_k1_i8 = ms_k1_eta = None
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if eng.use_i8:
+        def k1_phase(ph):
+            _cabi.check(lib.pyvb_zstep_i8_f64(eng.N, eng.D, eng.q, eng.X.data_ptr(), eng.D, eng.mask8.data_ptr(),
+                                              eng.Wbar.data_ptr(), eng.Wvar.data_ptr(), eng.Gw.data_ptr(), eng.ldg,
+                                              eng.P0.data_ptr(), eng.h0.data_ptr(), eng.gl.data_ptr(), eng.MZ.data_ptr(),
+                                              eng.ldmz, eng.GI.data_ptr(), eng.gscale.data_ptr(), 0,
+                                              eng.logdet.data_ptr(), 0, ph, stream), "zstep_i8")
+        ms_k1_i8 = time_calls(lambda: k1_phase(2), 5)
+        ms_k1_eta = time_calls(lambda: k1_phase(3), 5)
+        ms_k1 = time_calls(lambda: k1_phase(1), 5)
+        def k2_only():
+            _cabi.check(lib.pyvb_zsolve_f64(eng.N, eng.q, eng.MZ.data_ptr(), eng.ldmz, 0, eng.logdet.data_ptr(),
+                                            eng.gl.data_ptr(), eng.zsums.data_ptr() if eng.zsums is not None else 0,
+                                            stream), "zsolve")
+        k1_phase(1); ms_k2 = time_calls(k2_only, 1)
+        eng.update_Z()                           # restore a consistent state
+    elif lib.pyvb_algo_supported(2, a.D, a.q):
         def k1_only():
             alg, eng.algo = eng.algo, 3          # PYVB_ALGO_DMMA_K1: contraction only
             eng.update_Z()
@@ -379,27 +396,62 @@ def run_ours(a):
     fl_k1 = a.N * (2.0 * D * P + 2.0 * D * q)                            # K1 (SURVEY 8d terms)
     fl_z = fl_k1 + a.N * (q ** 3 + 2.0 * q * q)                          # + K2
     fl_s = a.N * (2.0 * D * P + 4.0 * D * q)                              # K3
-    if ms_k1 is not None:
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    i8_kernels = None
+    if eng.use_i8:
+        # INT8 path: the FP64 tensor pipe is no longer the bound; every kernel of the sweep is a stream over HBM.
+        # Algorithmic bytes per launch: rows in / rows out, nothing counted twice.
+        ncz = (P + q + 31) // 32 * 32
+        by = {"zstep_i8 (INT8 mask contraction -> qprec)": (a.N * (1.0 * D + 8.0 * P), ms_k1_i8),
+              "zstep_dmma_kernel<ETA> (eta = O.(X-mu) @ W on the FP64 tensor cores)": (a.N * (8.0 * D + 8.0 * q), ms_k1_eta),
+              "zsolve (K2: batched q x q Cholesky / inverse / solve)": (a.N * (16.0 * (P + q) + 8.0), ms_k2),
+              "statistics (colmax + digitize + INT8 T1/Bst + DMMA Ast + reduce)":
+                  (a.N * (8.0 * (P + q) + 8.0 * (P + q) + 7.0 * ncz + 1.0 * D + 7.0 * ncz + 8.0 * D + 8.0 * q), ms_s)}
+        i8_kernels = {k: {"ms": v[1], "algorithmic_GB": v[0] * 1e-9, "GBps": v[0] / (v[1] * 1e-3) * 1e-9,
+                          "frac_of_hbm_peak": v[0] / (v[1] * 1e-3) * 1e-9 / hbm} for k, v in by.items()}
+    if eng.use_i8:
+        # dominant single kernel of the INT8-path sweep: the batched solve (K2), HBM bound
+        kname = "zsolve (K2: batched q x q Cholesky / inverse / solve, in place on the MZ rows)"
+        by_dom, ms_dom = a.N * (16.0 * (P + q) + 8.0), ms_k2
+        fl_dom = None
+    elif ms_k1 is not None:
         kname, fl_dom, ms_dom = "zstep_dmma_kernel (K1: mask @ vec(G) contraction on FP64 tensor cores)", fl_k1, ms_k1
     else:
         kname, fl_dom, ms_dom = "zstep (generic K1+K2)", fl_z, ms_z
-    ach = fl_dom / (ms_dom * 1e-3) * 1e-12
+    ach = fl_dom / (ms_dom * 1e-3) * 1e-12 if fl_dom is not None else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         try:
             # measured DRAM bytes per row of K1 (ncu --set full at N = 151,552 rows) scaled to this launch's rows
             tj = json.load(open(tpath))
-            traffic = tj.get("zstep_dmma%d_dram_bytes_per_row" % a.q)
+            traffic = tj.get(("zsolve%d_dram_bytes_per_row" if eng.use_i8 else "zstep_dmma%d_dram_bytes_per_row") % a.q)
             traffic = traffic * a.N if traffic is not None else None
         except Exception:
             traffic = None
-    roofline = {"bound": "tensor", "kernel": kname,
+    if eng.use_i8:
+        ach_b = by_dom / (ms_dom * 1e-3) * 1e-9
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": ach_b, "peak": hbm, "unit": "GB/s", "frac": ach_b / hbm,
+                    "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                    "bytes_per_launch": by_dom, "ms_per_launch": ms_dom,
+                    "fp64_tensor_peak_tflops": peak_tf,
+                    "sweep_fp64_equivalent_tflops": a.N * (4.0 * D * P + 6.0 * D * q + q ** 3 + 2.0 * q * q) * a.steps
+                    / (ms * 1e-3) * 1e-12,
+                    "note": "the mask contractions run as exact integer GEMMs on the INT8 tensor cores: the sweep's FP64-"
+                            "equivalent rate exceeds the FP64 tensor roof; every kernel is a stream over HBM (see kernels)"}
+    else:
+      roofline = {"bound": "tensor", "kernel": kname,
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
                 "peak_source": "FP64 DMMA.8x8x4 loop measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                "BASELINE.md section 4 asks for it to be measured on the box)",
                 "flops_per_launch": fl_dom, "ms_per_launch": ms_dom}
-    kernels = {"zstep_ms": ms_z, "zstep_k1_ms": ms_k1, "zsolve_k2_ms": ms_k2, "zstep_tflops": fl_z / (ms_z * 1e-3) * 1e-12,
+    kernels = {"zstep_ms": ms_z, "zstep_k1_ms": ms_k1, "zstep_k1_i8_ms": ms_k1_i8, "zstep_k1_eta_ms": ms_k1_eta,
+               "zsolve_k2_ms": ms_k2, "i8_path": i8_kernels, "zstep_tflops": fl_z / (ms_z * 1e-3) * 1e-12,
                "stats_ms": ms_s, "stats_tflops": fl_s / (ms_s * 1e-3) * 1e-12,
                "sweep_algorithmic_tflops": world * a.N * (4.0 * D * P + 6.0 * D * q + q ** 3 + 2.0 * q * q)
                * a.steps / (ms * 1e-3) * 1e-12 / world}
@@ -416,11 +468,14 @@ def run_ours(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "algo": a.algo, "rows_total": world * a.N,
+                "config": {"workload": workload_name(a), "algo": ("i8" if eng.use_i8 else a.algo), "rows_total": world * a.N,
                            "l2": "inputs larger than L2 (X shard %.2f GB per GPU)" % (a.N * a.D * 8 / 1e9),
                            "parallelism": "rows sharded over %d GPU(s), one all-reduce of %d doubles per sweep"
                                           % (world, eng.L.len)},
-                "clocks": clocks, "gpu_launches": 7 * a.steps,   # per sweep: wupdate, pack_gw, zstep K1, zsolve K2, stats GEMM, reduce(+exchange), global
+                # per sweep, all-DMMA path: wupdate, pack_gw, zstep K1, zsolve K2, stats GEMM, reduce(+exchange), global;
+                # INT8 path: wupdate, pack_gw, pack_g_i8, zstep_i8, pack_weta, eta, zsolve, colmax, colmax_reduce,
+                # digitize, stats_i8, stats_x, reduce(+exchange), global
+                "clocks": clocks, "gpu_launches": (14 if eng.use_i8 else 7) * a.steps,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": a.N * a.D * 8, "d2h_bytes_per_step": 8,
                         "steps": e2e_steps},
                 "roofline": roofline, "kernels": kernels, "elbo_last": elbo[-1] if elbo else None}
@@ -446,7 +501,7 @@ def main():
     ap.add_argument("--q", type=int, default=16)
     ap.add_argument("--missing", type=float, default=0.2)
     ap.add_argument("--mode", default="B", choices=["A", "B"])
-    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "dmma"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "dmma", "i8"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-f32", action="store_true", help="skip the FP32-variant leg")
     ap.add_argument("--ard", action="store_true", help="ARD Gamma precisions per latent column (config 4)")

@@ -209,7 +209,7 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
  *   mask   [N][D] int8, 1 = observed: pyvb_prepare_mask_i8 (once per data set)
  *   GI     pyvb_i8_digits_bytes(D, q) bytes, gscale pyvb_i8_ncols(q) doubles: per-sweep scratch (filled by the call)
  *   MZ     the interleaved rows of the DMMA path (ldmz = pyvb_mz_pitch(q)); Gw as for pyvb_zstep_f64 (DMMA pitch)
- * k1_only != 0 leaves [qprec packed | eta] in the rows (measurement). */
+ * k1_only (measurement): 1 leaves [qprec packed | eta] in the rows; 2 runs the INT8 part alone, 3 the eta part alone. */
 int pyvb_i8_supported(int D, int q);
 size_t pyvb_i8_digits_bytes(int D, int q);
 int pyvb_i8_ncols(int q);

@@ -283,10 +283,16 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     ARG(ldx >= D && (ldx % 2) == 0, "ldx");
     ARG(ldg == pyvb_gw_pitch(q) && ldmz == pyvb_mz_pitch(q), "ldg / ldmz must equal pyvb_gw_pitch(q) / pyvb_mz_pitch(q)");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, st);
-    if (e == cudaSuccess) e = launch_zstep_i8(N, D, q, mask, GI, P0, gscale, gl, MZ, (int)ldmz, st);
-    double *weta = (double *)((char *)GI + align256(i8_digits_bytes(D, q)));
-    if (e == cudaSuccess) e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, weta, P0, h0, gl, MZ, st);
+    // k1_only: 0 whole Z step, 1 contraction only (INT8 qprec + DMMA eta), 2 INT8 part only, 3 eta part only
+    cudaError_t e = cudaSuccess;
+    if (k1_only != 3) {
+        e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, st);
+        if (e == cudaSuccess) e = launch_zstep_i8(N, D, q, mask, GI, P0, gscale, gl, MZ, (int)ldmz, st);
+    }
+    if (e == cudaSuccess && k1_only != 2) {
+        double *weta = (double *)((char *)GI + align256(i8_digits_bytes(D, q)));
+        e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, weta, P0, h0, gl, MZ, st);
+    }
     if (e == cudaSuccess && !k1_only) e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_i8");
 }

@@ -74,7 +74,7 @@ class PlateEngine(object):
         self.use_i8 = (algo == "i8")
         if algo == "i8":
             algo = "dmma"
-        elif algo == "auto" and mode == "B" and precision == "f64" and os.environ.get("PYVB_I8", "0") != "0":
+        elif algo == "auto" and mode == "B" and precision == "f64" and os.environ.get("PYVB_I8", "1") != "0":
             self.use_i8 = None                                  # decided below, once D is known
         self.algo = _ALGOS[algo] if isinstance(algo, str) else int(algo)
         self.distributed = bool(distributed)
