@@ -225,12 +225,13 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
  * the FP64 tensor cores.  Mode B, interleaved MZ rows, q in {16, 32, 64}, D % 16 == 0.  Requires what pyvb_stats_f64
  * treats as optional: xcache (valid: the X-only sums of an earlier pyvb_stats_f64 call).  zsums: the K2 partials of the
  * Z step that produced these rows, or NULL (then logdet [N] is read and the MZ column sums take one more pass).
- *   maskT  [D][pyvb_stats_i8_npad(N)] int8: pyvb_prepare_maskt_i8 (once per data set)
+ *   maskT  pyvb_stats_i8_maskt_bytes(N, D) bytes, [n / 64][D][64] int8: pyvb_prepare_maskt_i8 (once per data set)
  *   ZI     pyvb_stats_i8_digits_bytes(N, q) bytes, scratch pyvb_stats_i8_scratch_len(q) doubles: per-call scratch
  *   ws     pyvb_stats_i8_workspace_bytes(N, D, q) */
 int pyvb_stats_i8_supported(int D, int q);
 long long pyvb_stats_i8_npad(long long N);
 size_t pyvb_stats_i8_digits_bytes(long long N, int q);
+size_t pyvb_stats_i8_maskt_bytes(long long N, int D);
 size_t pyvb_stats_i8_scratch_len(int q);
 size_t pyvb_stats_i8_workspace_bytes(long long N, int D, int q);
 int pyvb_prepare_maskt_i8(long long N, int D, const double *X, long long ldx, void *maskT, void *stream);

@@ -300,6 +300,7 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
 int pyvb_stats_i8_supported(int D, int q) { return (stats_i8_supported(D, q) && dmma_supported(D, q)) ? 1 : 0; }
 long long pyvb_stats_i8_npad(long long N) { return stats_i8_npad(N); }
 size_t pyvb_stats_i8_digits_bytes(long long N, int q) { return stats_i8_digits_bytes(N, q); }
+size_t pyvb_stats_i8_maskt_bytes(long long N, int D) { return stats_i8_maskt_bytes(N, D); }
 size_t pyvb_stats_i8_scratch_len(int q) { return stats_i8_scratch_len(q, pyvb_mz_pitch(q)); }
 size_t pyvb_stats_i8_workspace_bytes(long long N, int D, int q) {
     const StatLayout L(D, q);

@@ -108,6 +108,7 @@ bool stats_i8_supported(int D, int q);
 int stats_i8_ncols(int q);
 long long stats_i8_npad(long long N);                       // rows of maskT / ZI rounded up to 128
 size_t stats_i8_digits_bytes(long long N, int q);           // bytes of ZI
+size_t stats_i8_maskt_bytes(long long N, int D);            // bytes of maskT
 size_t stats_i8_scratch_len(int q, int ldmz);               // doubles: partial column maxima + zscale
 int stats_i8_nchunks(long long N, int D, int q);
 cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long long ldx, void *maskT, cudaStream_t st);

@@ -356,8 +356,10 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // K3-i8: the mask-type sufficient statistics  T1 = O^T vec<zz^T>,  Bst = O^T Zbar  (hstack, nodes/nodes_todo.py:50-61)
 // on the INT8 tensor cores.  Same idea as K1-i8 with the roles turned: the contraction index is the ROW n, so both
 // operands are needed "n contiguous":
-//   maskT [D][npad]                      int8, the transposed mask (static, prepared once per data set)
-//   ZI    [ct][plane][c % 32][npad]      int8, the seven balanced base-256 digit planes of the MZ columns
+//   maskT [n / 64][D][64]                int8, the transposed mask (static, prepared once per data set)
+//   ZI    [n / 64][ct][plane][c % 32][64] int8, the seven balanced base-256 digit planes of the MZ columns
+//                                        (tile-major: every TMA box is one contiguous 8 KB / 14 KB block -- with a
+//                                        plain [column][n] layout a box touched 224 different 2 MB pages at N = 1.25M)
 //                                        c in [0, P + q) = [<zz^T> packed | zbar], rewritten after every Z step with one
 //                                        fixed-point scale per column, zscale_c = max_n |MZ[n][c]| (colmax pass)
 // Work item = (block of 128 data dimensions, column tile of 32, row chunk): one TMEM accumulator (224 columns) summed
@@ -452,17 +454,14 @@ digitize_kernel(long long N, long long npad, int ldmz, int nvalid, const double 
         }
     }
     __syncthreads();
-    // rows (plane, column) of 128 bytes -> ZI[ct][plane][column][n0 .. n0 + 128): one warp writes one 128-byte row
-    const int nrem = (N - n0 < 128) ? (int)(N - n0) : 128;
-    for (int row = warp; row < NPL * CT; row += 8) {
-        signed char *dst = ZI + ((size_t)ct * NPL * CT + row) * npad + n0;
-        const int w = *reinterpret_cast<const int *>(&sh[row * PITCH + lane * 4]);
-        if (lane * 4 + 3 < nrem) {
-            *reinterpret_cast<int *>(dst + lane * 4) = w;
-        } else {
-            for (int b = 0; b < 4; ++b)
-                if (lane * 4 + b < nrem) dst[lane * 4 + b] = (signed char)(w >> (8 * b));
-        }
+    // two contiguous 14 KB tiles (64 rows each): ZI[(kb * nct + ct)][plane * 32 + column][64]
+    const int nct = gridDim.y;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long kb = n0 / 64 + h;
+        unsigned int *dst = reinterpret_cast<unsigned int *>(ZI + ((size_t)(kb * nct + ct) * (NPL * CT)) * 64);
+        for (int w = threadIdx.x; w < NPL * CT * 16; w += 256)
+            dst[w] = *reinterpret_cast<const unsigned int *>(&sh[(w >> 4) * PITCH + h * 64 + (w & 15) * 4]);
     }
 }
 
@@ -486,16 +485,15 @@ prepare_maskT_kernel(long long N, int D, long long npad, const double *__restric
         sh[lane * PITCH + r] = m;
     }
     __syncthreads();
-    const int nrem = (N - n0 < 128) ? (int)(N - n0) : 128;
-    for (int row = warp; row < 32; row += 8) {
-        if (d0 + row >= D) break;
-        signed char *dst = maskT + (size_t)(d0 + row) * npad + n0;
-        const int w = *reinterpret_cast<const int *>(&sh[row * PITCH + lane * 4]);
-        if (lane * 4 + 3 < nrem) {
-            *reinterpret_cast<int *>(dst + lane * 4) = w;
-        } else {
-            for (int b = 0; b < 4; ++b)
-                if (lane * 4 + b < nrem) dst[lane * 4 + b] = (signed char)(w >> (8 * b));
+    // maskT[kb][d][64]: 32 data dimensions x 64 bytes per k tile
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long kb = n0 / 64 + h;
+        for (int w = threadIdx.x; w < 32 * 16; w += 256) {
+            const int row = w >> 4;
+            if (d0 + row < D)
+                *reinterpret_cast<unsigned int *>(maskT + ((size_t)kb * D + d0 + row) * 64 + (w & 15) * 4) =
+                    *reinterpret_cast<const unsigned int *>(&sh[row * PITCH + h * 64 + (w & 15) * 4]);
         }
     }
 }
@@ -565,9 +563,9 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / SST) & 1) ^ 1));
                     unsigned char *st = st_base + (size_t)s * (A_B + B_B);
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
-                    const int n = (int)(r0 + (long long)k * BKB);
-                    tma_load_3d_i8(st, &tmA, n, db * BM, 0, &full[s]);             // 128 data dimensions x 64 rows
-                    tma_load_3d_i8(st + A_B, &tmB, n, 0, ct, &full[s]);            // 7 planes x 32 columns x 64 rows
+                    const long long kb = r0 / BKB + k;
+                    tma_load_3d_i8(st, &tmA, 0, (int)(kb * D + db * BM), 0, &full[s]);               // 128 data dimensions x 64 rows
+                    tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
                 }
             }
         }
@@ -690,6 +688,7 @@ bool stats_i8_supported(int D, int q) { return (q == 16 || q == 32 || q == 64) &
 int stats_i8_ncols(int q) { return (i_tri(q) + q + 31) & ~31; }
 long long stats_i8_npad(long long N) { return (N + 127) / 128 * 128; }
 size_t stats_i8_digits_bytes(long long N, int q) { return (size_t)stats_i8_ncols(q) * NPL * (size_t)stats_i8_npad(N); }
+size_t stats_i8_maskt_bytes(long long N, int D) { return (size_t)D * (size_t)stats_i8_npad(N) + (size_t)BM * BKB; }
 size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * ldmz + stats_i8_ncols(q); }
 
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
@@ -742,18 +741,19 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     CUtensorMap tmA, tmB;
-    {   // maskT [D][npad] with N valid columns; ZI [nct][224][npad] with N valid columns: reads past N are zero filled
+    {   // tile-major operands: maskT [npad / 64][D][64] (+ one box of slack), ZI [npad / 64][nct][224][64]
         EncodeTiledFn enc = get_encode_i8();
         if (!enc) return cudaErrorNotSupported;
+        const cuuint64_t nkb = (cuuint64_t)(npad / BKB);
+        if (nkb * (cuuint64_t)D + BM >= (1ULL << 31) || nkb * nct * (NPL * CT) >= (1ULL << 31)) return cudaErrorNotSupported;
         cuuint32_t es[3] = {1, 1, 1};
-        cuuint64_t da[3] = {(cuuint64_t)N, (cuuint64_t)D, 1}, sa[2] = {(cuuint64_t)npad, (cuuint64_t)npad * D};
+        cuuint64_t da[3] = {BKB, nkb * D + BM, 1}, sa[2] = {BKB, (nkb * D + BM) * BKB};
         cuuint32_t ba[3] = {BKB, BM, 1};
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(maskT), da, sa, ba, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-        cuuint64_t db[3] = {(cuuint64_t)N, (cuuint64_t)(NPL * CT), (cuuint64_t)nct};
-        cuuint64_t sb[2] = {(cuuint64_t)npad, (cuuint64_t)npad * NPL * CT};
+        cuuint64_t db[3] = {BKB, nkb * nct * (NPL * CT), 1}, sb[2] = {BKB, nkb * nct * (NPL * CT) * BKB};
         cuuint32_t bb[3] = {BKB, NPL * CT, 1};
         r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ZI, db, sb, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

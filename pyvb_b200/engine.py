@@ -171,7 +171,7 @@ class PlateEngine(object):
         if self.use_i8_stats:
             try:
                 self.npad = int(self.lib.pyvb_stats_i8_npad(N))
-                self.maskT = torch.empty(D, self.npad, dtype=torch.int8, device=dev)
+                self.maskT = torch.empty(int(self.lib.pyvb_stats_i8_maskt_bytes(N, D)), dtype=torch.int8, device=dev)
                 self.ZI = torch.empty(int(self.lib.pyvb_stats_i8_digits_bytes(N, q)), dtype=torch.int8, device=dev)
                 self.i8_scratch = torch.empty(int(self.lib.pyvb_stats_i8_scratch_len(q)), dtype=f64, device=dev)
                 self.ws_bytes = max(self.ws_bytes, int(self.lib.pyvb_stats_i8_workspace_bytes(N, D, q)))
