@@ -148,6 +148,7 @@ int pyvb_peer_export(void *dptr, unsigned char *handle64 /* host out, 64 bytes *
 int pyvb_peer_import(const unsigned char *handle64 /* host */, void **dptr /* host out */);
 int pyvb_peer_close(void *dptr);
 int pyvb_algo_supported(int algo, int D, int q);       /* 1/0 */
+int pyvb_zsums_kw(int q);   /* doubles per K2 partial: [column sums (Pp + q) | 4 scalars | column maxima (Pp + q)] */
 
 int pyvb_pack_gw_f64(int D, int q, const double *Wbar, const double *Wvar, const double *mu,
                      double *Gw, int ldg, void *stream);
@@ -206,13 +207,15 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
  * planes of a 2^-54 fixed-point representation (relative to the column maximum), so mask @ G is a sum of exact
  * integer GEMMs recombined in FP64.  The eta columns (X real) stay on the FP64 tensor cores.  Mode B only.
  * q in {16, 32, 64}, D % 64 == 0, D small enough for the resident mask block (pyvb_i8_supported).
- *   mask   [N][D] int8, 1 = observed: pyvb_prepare_mask_i8 (once per data set)
+ *   mask   pyvb_i8_mask_bytes(N, D) bytes, int8 tiles [n / 128][d / 64][128][64], 1 = observed: pyvb_prepare_mask_i8
+ *          (once per data set).  A sub-range of rows starting at a multiple of 128 starts at mask + first_row * D.
  *   GI     pyvb_i8_digits_bytes(D, q) bytes, gscale pyvb_i8_ncols(q) doubles: per-sweep scratch (filled by the call)
  *   MZ     the interleaved rows of the DMMA path (ldmz = pyvb_mz_pitch(q)); Gw as for pyvb_zstep_f64 (DMMA pitch)
  * k1_only (measurement): 1 leaves [qprec packed | eta] in the rows; 2 runs the INT8 part alone, 3 the eta part alone. */
 int pyvb_i8_supported(int D, int q);
 size_t pyvb_i8_digits_bytes(int D, int q);
 int pyvb_i8_ncols(int q);
+size_t pyvb_i8_mask_bytes(long long N, int D);
 int pyvb_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, void *stream);
 int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx, const void *mask, const double *Wbar,
                       const double *Wvar, const double *Gw, int ldg, const double *P0, const double *h0, double *gl,
@@ -290,6 +293,9 @@ int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X,
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
  * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.
  * bench.py times it with CUDA events to obtain the FP64 tensor roofline of the box it runs on. */
+/* Measurement: `iters` x 2 back-to-back tcgen05.mma (M = 128, N = n, 32 bytes of K each; kind 0 = i8, 1 = bf16) on fixed
+ * shared-memory operands per CTA; clk_out[block] = SM clocks from the first issue to the completion of the last. */
+int pyvb_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, void *stream);
 int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch /* blocks*256 doubles */, void *stream);
 
 #ifdef __cplusplus

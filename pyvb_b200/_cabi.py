@@ -35,6 +35,7 @@ SIGNATURES = {
     "pyvb_algo_supported": (c_int, [c_int, c_int, c_int]),
     "pyvb_pack_gw_f64": (c_int, [c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
     "pyvb_zsums_len": (c_sz, [c_ll, c_int]),
+    "pyvb_zsums_kw": (c_int, [c_int]),
     "pyvb_zstep_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_int, c_dp, c_dp, c_dp,
                                c_dp, c_ll, c_dp, c_ll, c_dp, c_dp, c_dp, c_int, c_dp]),
     "pyvb_zsolve_f64": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "pyvb_i8_supported": (c_int, [c_int, c_int]),
     "pyvb_i8_digits_bytes": (c_sz, [c_int, c_int]),
     "pyvb_i8_ncols": (c_int, [c_int]),
+    "pyvb_i8_mask_bytes": (c_sz, [c_ll, c_int]),
     "pyvb_prepare_mask_i8": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp]),
     "pyvb_zstep_i8_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_int, c_dp, c_dp, c_dp,
                                   c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
@@ -77,6 +79,7 @@ SIGNATURES = {
     "pyvb_global_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                 ctypes.POINTER(Consts), c_dp, c_dp]),
     "pyvb_bench_dmma_f64": (c_int, [c_int, c_int, c_dp, c_dp]),
+    "pyvb_bench_umma": (c_int, [c_int, c_int, c_int, c_int, c_dp, c_dp]),
     "pyvb_impute_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),
 }
 

@@ -76,6 +76,8 @@ size_t pyvb_zsums_len_f32(long long N, int q) {
     return (size_t)nblk * kw;
 }
 
+int pyvb_zsums_kw(int q) { return 2 * (gw_woff(q) + q) + PYVB_ZS_EXTRA; }
+
 size_t pyvb_zsums_len(long long N, int q) {
     int nblk, kw;
     zsolve_partials(N, q, nblk, kw);
@@ -262,6 +264,7 @@ size_t pyvb_i8_digits_bytes(int D, int q) {
     return align256(i8_digits_bytes(D, q)) + align256((size_t)D * zstep_eta_pitch(q) * sizeof(double));
 }
 int pyvb_i8_ncols(int q) { return i8_ncols(q); }
+size_t pyvb_i8_mask_bytes(long long N, int D) { return i8_mask_bytes(N, D); }
 
 int pyvb_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, void *stream) {
     ARG(N >= 0 && D >= 4 && (D % 4) == 0 && ldx >= D && (ldx % 2) == 0, "N, D (% 4), ldx (even)");
@@ -344,7 +347,10 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     int nzblk = 0, zkw = 0;
     if (zsums) zsolve_partials(N, q, nzblk, zkw);
     const int nch = stats_i8_nchunks(N, D, q);
-    cudaError_t e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch, st);
+    // the default K2 kernels leave bounds on the column maxima behind their column sums: [sums OROW | 4 | maxima OROW]
+    const bool kmax = nzblk > 0 && (k2_impl(q) == 1 || k2_impl(q) == 2);
+    cudaError_t e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch,
+                                    kmax ? zsums + (gw_woff(q) + q + PYVB_ZS_EXTRA) : NULL, nzblk, zkw, st);
     if (e == cudaSuccess) e = launch_stats_x_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st);
     double *ws_sc = NULL;
     const int nblk = rowscalars_nblk(N);
@@ -450,6 +456,12 @@ int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X,
     cudaError_t e = launch_lds_iterate(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb, alpha0, a0, b0, niters,
                                        status, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "lds_iterate");
+}
+
+int pyvb_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, void *stream) {
+    ARG(blocks >= 1 && iters >= 1 && n >= 16 && n <= 256 && (n % 16) == 0 && (kind == 0 || kind == 1) && clk_out, "arguments");
+    cudaError_t e = launch_bench_umma(blocks, iters, n, kind, clk_out, (cudaStream_t)stream);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "bench_umma");
 }
 
 int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch, void *stream) {

@@ -96,6 +96,7 @@ cudaError_t launch_stats_f32(long long N, long long nalloc, int D, int q, const 
 // ---- exact mask contraction on the INT8 tensor cores (kernels_i8.cu) ----
 bool i8_supported(int D, int q);
 size_t i8_digits_bytes(int D, int q);          // bytes of the digit planes of G
+size_t i8_mask_bytes(long long N, int D);      // bytes of the tile-major int8 mask
 int i8_ncols(int q);                           // packed columns rounded up to 32 (length of gscale)
 cudaError_t launch_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, cudaStream_t st);
 cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wvar, void *GI, double *gscale,
@@ -113,7 +114,8 @@ size_t stats_i8_scratch_len(int q, int ldmz);               // doubles: partial 
 int stats_i8_nchunks(long long N, int D, int q);
 cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long long ldx, void *maskT, cudaStream_t st);
 cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,
-                            double *scratch, double *ws, int nchunks, cudaStream_t st);
+                            double *scratch, double *ws, int nchunks, const double *zmax, int nzblk, int zkw,
+                            cudaStream_t st);
 cudaError_t launch_stats_x_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                                 double *ws_main, int nchunks, cudaStream_t st);
 
@@ -124,5 +126,6 @@ cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, doub
                                double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st);
 
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
+cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, cudaStream_t st);
 
 }  // namespace pyvb

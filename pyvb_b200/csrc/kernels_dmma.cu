@@ -461,7 +461,7 @@ template <int Q> struct K2T {
     // broadcast scratch, 2 mbarriers
     static constexpr int WARP_D = 2 * RPP * OROW + RPP * P + 2 * MI * 32 + 2 + OROW;
     static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8 + 16;
-    static constexpr int KW = OROW + PYVB_ZS_EXTRA;           // doubles per CTA in the column-sum partials
+    static constexpr int KW = 2 * OROW + PYVB_ZS_EXTRA;       // doubles per CTA in the partials: [sums | 4 scalars | maxima (unused: 0)]
     static_assert(WARP_D % 2 == 0 && OROW % 2 == 0 && P % 2 == 0, "16-byte alignment of the per-warp buffers");
 };
 

@@ -20,6 +20,8 @@
 // 2-9: epilogue (two warps per TMEM lane quarter, 16 columns each).  Operands are K-major TMA tiles with 64-byte rows
 // (SWIZZLE_64B), the same byte geometry as the bf16 kernels of kernels_f32.cu.
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -33,31 +35,38 @@ namespace {
 __host__ __device__ constexpr int i_tri(int i) { return i * (i + 1) / 2; }
 __host__ __device__ constexpr int i_nc8(int q) { return (i_tri(q) + 31) & ~31; }          // packed columns rounded to 32
 constexpr int NPL = 7;                                                                    // digit planes
-constexpr int BM = 128, BKB = 64, ST = 4, CT = 32;       // rows per tile, K bytes per chunk, digit stages, columns per tile
+constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, digit stages, columns per tile
 constexpr int A_B = BM * BKB, B_B = NPL * CT * BKB;      // 8192, 14336
 constexpr int NTHR = 10 * 32;
 
 // ------------------------------------------------------------------ operand preparation
+// mask[rb][kb][128 rows][64 bytes] (rb = n / 128, kb = d / 64): every TMA box of the kernel is one contiguous 8 KB block
+// (64-byte rows at a stride of D bytes were half cache lines: twice the L2 requests per byte); rows >= N are zero
 __global__ void __launch_bounds__(256)
 prepare_mask_i8_kernel(long long N, int D, const double *__restrict__ X, long long ldx, signed char *__restrict__ mask) {
-    const long long total = N * (long long)(D / 4);
+    const long long npad = (N + BM - 1) / BM * BM;
+    const int nk = D / BKB;
+    const long long total = npad * (long long)(D / 4);
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const long long n = e / (D / 4);
         const int d = (int)(e - n * (D / 4)) * 4;
-        const double2 a = *reinterpret_cast<const double2 *>(X + n * ldx + d);
-        const double2 b = *reinterpret_cast<const double2 *>(X + n * ldx + d + 2);
-        char4 m;
-        m.x = (a.x == a.x) ? 1 : 0;
-        m.y = (a.y == a.y) ? 1 : 0;
-        m.z = (b.x == b.x) ? 1 : 0;
-        m.w = (b.y == b.y) ? 1 : 0;
-        *reinterpret_cast<char4 *>(mask + n * D + d) = m;
+        char4 m = make_char4(0, 0, 0, 0);
+        if (n < N) {
+            const double2 a = *reinterpret_cast<const double2 *>(X + n * ldx + d);
+            const double2 b = *reinterpret_cast<const double2 *>(X + n * ldx + d + 2);
+            m.x = (a.x == a.x) ? 1 : 0;
+            m.y = (a.y == a.y) ? 1 : 0;
+            m.z = (b.x == b.x) ? 1 : 0;
+            m.w = (b.y == b.y) ? 1 : 0;
+        }
+        const size_t dst = (((size_t)(n / BM) * nk + d / BKB) * BM + (size_t)(n % BM)) * BKB + (d % BKB);
+        *reinterpret_cast<char4 *>(mask + dst) = m;
     }
 }
 
 // one CTA per output column c: scale_c = max_d |G[d][c]|, then the seven balanced base-256 digits of
-// round(G / scale_c * 2^54).  GI[ct][plane][c % 32][d] (int8), ct = c / 32: the B tile of column tile ct is one
-// [224 rows][D] block.
+// round(G / scale_c * 2^54).  GI[kb][ct][plane][c % 32][64] (int8), kb = d / 64, ct = c / 32: the B tile of (kb, ct) is
+// one contiguous [224 rows][64 bytes] block.
 __global__ void __launch_bounds__(256)
 pack_g_i8_kernel(int D, int q, const double *__restrict__ Wbar, const double *__restrict__ Wvar,
                  signed char *__restrict__ GI, double *__restrict__ gscale) {
@@ -87,7 +96,7 @@ pack_g_i8_kernel(int D, int q, const double *__restrict__ Wbar, const double *__
     const double scale = (sh[32] > 0.0 && sh[32] < 1e300) ? sh[32] : 1.0;
     if (threadIdx.x == 0) gscale[c] = scale;
     const double inv = 18014398509481984.0 / scale;                     // 2^54 / scale
-    signed char *base = GI + ((size_t)(c >> 5) * NPL * CT + (c & 31)) * D;
+    const int nct = gridDim.x / CT;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         double g = 0.0;
         if (c < P) {
@@ -98,7 +107,7 @@ pack_g_i8_kernel(int D, int q, const double *__restrict__ Wbar, const double *__
 #pragma unroll
         for (int t = 0; t < NPL; ++t) {
             const long long dg = ((v + 128) & 255) - 128;               // balanced digit in [-128, 127]
-            base[(size_t)t * CT * D + d] = (signed char)dg;
+            GI[((((size_t)(d / BKB) * nct + (c >> 5)) * NPL + t) * CT + (c & 31)) * BKB + (d % BKB)] = (signed char)dg;
             v = (v - dg) >> 8;
         }
     }
@@ -140,6 +149,31 @@ __device__ __forceinline__ void tma_load_3d_i8(void *dst_smem, const void *tmap,
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+// the same box delivered to the same shared-memory offset of every CTA in `mask` (and complete_tx on each CTA's barrier)
+__device__ __forceinline__ void tma_load_3d_i8_mc(void *dst_smem, const void *tmap, int c0, int c1, int c2, uint64_t *bar,
+                                                  uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, "
+        "%4}], [%5], %6;" ::"r"(smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+// tcgen05.commit that arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -150,12 +184,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
 __device__ __forceinline__ double i2d(int a) {
     return __hiloint2double(0x43300000, (int)((unsigned)a ^ 0x80000000u)) - 4503601774854144.0;
 }
-// sum_t 256^t a_t for seven INT32 accumulators (|a_t| <= 2^22: pairs fit INT32); one rounding (the last FMA)
+// sum_t 256^t a_t for seven INT32 accumulators (|a_t| <= 2^18): two exact 64-bit integer halves (multiply-add-wide),
+// each converted through the 2^52 + 2^51 bit pattern (exact for |x| < 2^51), then ONE rounding in the final FMA
 __device__ __forceinline__ double combine7(const int (&a)[NPL]) {
-    const int t01 = a[0] + (a[1] * 256), t23 = a[2] + (a[3] * 256), t45 = a[4] + (a[5] * 256);
-    double v = fma(i2d(a[6]), 65536.0, i2d(t45));
-    v = fma(v, 65536.0, i2d(t23));
-    return fma(v, 65536.0, i2d(t01));
+    const long long lo = (long long)a[3] * 16777216LL + ((long long)a[2] * 65536LL + ((long long)a[1] * 256LL + (long long)a[0]));
+    const long long hi = (long long)a[6] * 65536LL + ((long long)a[5] * 256LL + (long long)a[4]);
+    const double dlo = __longlong_as_double(0x4338000000000000LL + lo) - 6755399441055744.0;
+    const double dhi = __longlong_as_double(0x4338000000000000LL + hi) - 6755399441055744.0;
+    return fma(dhi, 4294967296.0, dlo);
+}
+// 2-D tiled TMA store shared -> global (rows / columns outside the tensor are clipped)
+__device__ __forceinline__ void tma_store_2d(const void *tmap, int c0, int c1, const void *src_smem) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
 }
 
 struct I8Geom {
@@ -167,35 +209,67 @@ struct I8Geom {
         NCT = NC8 / CT;
     }
 };
-size_t i8_smem_bytes(int D, int q) {
+constexpr int OUT_B = 8 * 32 * 16 * 8;                  // epilogue staging: 8 warps x (32 rows x 16 columns) doubles
+size_t i8_smem_bytes(int D, int q, int nst) {
     const I8Geom g(q);
     const int nk = D / BKB;
-    return 1024 + (size_t)nk * A_B + (size_t)ST * B_B + (size_t)(2 * g.NC8) * 8 + (size_t)(2 * nk + 2 * ST + 4) * 8 + 16;
+    return 1024 + (size_t)nk * A_B + (size_t)nst * B_B + OUT_B + (size_t)(2 * g.NC8) * 8 + (size_t)(2 * nk + 2 * nst + 4) * 8 + 16;
+}
+int i8_stages(int D, int q) {                            // digit-tile stages that fit next to the resident mask block
+    for (int nst = ST; nst >= 2; --nst)
+        if (i8_smem_bytes(D, q, nst) <= 227 * 1024) return nst;
+    return 0;
 }
 
 // ------------------------------------------------------------------ K1-i8: qprec columns of the MZ rows
+// CL > 1: clusters of CL CTAs (consecutive row blocks) share every digit tile: each CTA fetches 1 / CL of it and the
+// copy is multicast to all of them (the digit tiles come from L2 and their traffic, not the MMAs, bounds the kernel);
+// a stage is released by the MMA commits of ALL the CTAs (multicast tcgen05.commit on every CTA's `empty` barrier).
+template <int CL>
 __global__ void __launch_bounds__(NTHR, 1)
-zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long N, int D, int q,
-                const double *__restrict__ P0, const double *__restrict__ gscale, const double *__restrict__ gl,
-                double *__restrict__ MZ, int ldmz, int nrb) {
+zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, long long N, int D, int q, const double *__restrict__ P0,
+                const double *__restrict__ gscale, const double *__restrict__ gl, int nrb, int nst, long long *prof) {
     const I8Geom G(q);
+    long long w0 = 0, w1 = 0, w2 = 0;                          // PYVB_I8_PROF: clocks spent waiting, per role
+    const long long tstart = clock64();
+#define PROF_WAIT(acc, stmt)                    \
+    do {                                        \
+        if (prof) {                             \
+            const long long t_ = clock64();     \
+            stmt;                               \
+            acc += clock64() - t_;              \
+        } else {                                \
+            stmt;                               \
+        }                                       \
+    } while (0)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int nk = D / BKB;
     unsigned char *a_base = smem;                                              // [nk][128 x 64 B] resident mask block
-    unsigned char *b_base = smem + (size_t)nk * A_B;                           // [ST][224 x 64 B] digit tiles
-    double *p0v = reinterpret_cast<double *>(b_base + ST * B_B);               // [NC8]: packed P0, zero pad
+    unsigned char *b_base = smem + (size_t)nk * A_B;                           // [nst][224 x 64 B] digit tiles
+    unsigned char *o_base = b_base + (size_t)nst * B_B;                        // [8 warps][32 rows x 128 B] output staging (swizzled)
+    double *p0v = reinterpret_cast<double *>(o_base + OUT_B);                  // [NC8]: packed P0, zero pad
     double *fcol = p0v + G.NC8;                                                // [NC8]: tau * scale_c * 2^-54
     uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nk]
     uint64_t *aempty = afull + nk;                                             // [nk]
-    uint64_t *full = aempty + nk;                                              // [ST]
-    uint64_t *empty = full + ST;                                               // [ST]
-    uint64_t *tfull = empty + ST;                                              // [2]
+    uint64_t *full = aempty + nk;                                              // [nst]
+    uint64_t *empty = full + nst;                                              // [nst]
+    uint64_t *tfull = empty + nst;                                             // [2]
     uint64_t *tempty = tfull + 2;                                              // [2]
     uint32_t *tbase = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double tau = gl[PYVB_GL_TAU];
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    // every CTA of a cluster runs the same number of row blocks (a CTA past the last block works on zero-filled rows)
+    const int first = (int)blockIdx.x - crank;
+    const int niter = (first < nrb) ? (nrb - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
+    // every cluster walks the (column tile, K chunk) grid from its own starting point: 148 CTAs stepping through the
+    // same few MB of digit tiles in lockstep would all hit the same L2 lines at the same time
+    const int rot = (int)(blockIdx.x / CL) % (G.NCT * nk);
+    const int ct0 = rot / nk, kb0 = rot % nk;
 
     for (int p = tid; p < G.NC8; p += NTHR) {
         double v = 0.0;
@@ -210,13 +284,14 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
         for (int k = 0; k < nk; ++k) {
             mbar_init(&afull[k], 1);
             mbar_init(&aempty[k], 1);
         }
-        for (int s = 0; s < ST; ++s) {
+        for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
@@ -227,26 +302,37 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) umma::tmem_alloc(tbase, 512);
     umma::fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                            // the peers' barriers are initialised before anyone signals them
     umma::fence_after_sync();
     const uint32_t tmem = *tbase;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            int it = 0, rl = 0;
-            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rl) {
-                const int row0 = rb * BM;
-                for (int ct = 0; ct < G.NCT; ++ct) {
-                    for (int kb = 0; kb < nk; ++kb, ++it) {
-                        if (ct == 0) {      // the mask chunk of the previous row block has been consumed by its last column tile
-                            umma::mbar_wait_bounded(&aempty[kb], (uint32_t)((rl & 1) ^ 1));
+            int s = 0;
+            uint32_t ph = 0;
+            for (int rl = 0; rl < niter; ++rl) {
+                const int rb = (int)blockIdx.x + rl * (int)gridDim.x;
+                for (int ci = 0; ci < G.NCT; ++ci) {
+                    const int ct = (ci + ct0 < G.NCT) ? ci + ct0 : ci + ct0 - G.NCT;
+                    for (int ki = 0; ki < nk; ++ki) {
+                        const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
+                        if (ci == 0) {      // the mask chunk of the previous row block has been consumed by its last column tile
+                            PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[kb], (uint32_t)((rl & 1) ^ 1)));
                             mbar_arrive_expect_tx(&afull[kb], (uint32_t)A_B);
-                            tma_load_3d_i8(a_base + (size_t)kb * A_B, &tmA, kb * BKB, row0, 0, &afull[kb]);   // rows past N: zero fill
+                            tma_load_3d_i8(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, &afull[kb]);   // past the end: zero fill
                         }
-                        const int s = it % ST;
-                        umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / ST) & 1) ^ 1));
+                        PROF_WAIT(w0, umma::mbar_wait_bounded(&empty[s], ph ^ 1));
                         mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
-                        tma_load_3d_i8(b_base + s * B_B, &tmB, kb * BKB, 0, ct, &full[s]);                    // 7 planes x 32 columns
+                        if (CL == 1)
+                            tma_load_3d_i8(b_base + s * B_B, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT), 0, &full[s]);   // 7 planes x 32 columns
+                        else                                                                                   // this CTA's slice, to everybody
+                            tma_load_3d_i8_mc(b_base + s * B_B + crank * (B_B / CL), &tmB, 0,
+                                              (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / CL), 0, &full[s], CMASK);
+                        if (++s == nst) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                 }
             }
@@ -255,25 +341,31 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
-            int it = 0, tl = 0, rl = 0;
-            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rl) {
-                for (int ct = 0; ct < G.NCT; ++ct, ++tl) {
+            int s = 0, tl = 0;
+            uint32_t ph = 0;
+            for (int rl = 0; rl < niter; ++rl) {
+                for (int ci = 0; ci < G.NCT; ++ci, ++tl) {
                     const int buf = tl & 1;
-                    umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));
+                    PROF_WAIT(w1, umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1)));
                     umma::fence_after_sync();
                     const uint32_t dacc = tmem + (uint32_t)(buf * 256);
-                    for (int kb = 0; kb < nk; ++kb, ++it) {
-                        const int s = it % ST;
-                        if (ct == 0) umma::mbar_wait_bounded(&afull[kb], (uint32_t)(rl & 1));
-                        umma::mbar_wait_bounded(&full[s], (uint32_t)((it / ST) & 1));
+                    for (int ki = 0; ki < nk; ++ki) {
+                        const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
+                        if (ci == 0) PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[kb], (uint32_t)(rl & 1)));
+                        PROF_WAIT(w0, umma::mbar_wait_bounded(&full[s], ph));
                         umma::fence_after_sync();
                         const uint32_t a0 = smem_u32(a_base + (size_t)kb * A_B), b0 = smem_u32(b_base + s * B_B);
 #pragma unroll
                         for (int ks = 0; ks < BKB / 32; ++ks)
                             umma::mma_i8(dacc, umma::desc_kmajor_sw64(a0, ks), umma::desc_kmajor_sw64(b0, ks), idesc,
-                                         (kb | ks) ? 1u : 0u);
-                        umma::mma_commit(&empty[s]);
-                        if (ct == G.NCT - 1) umma::mma_commit(&aempty[kb]);
+                                         (ki | ks) ? 1u : 0u);
+                        if (CL == 1) umma::mma_commit(&empty[s]);
+                        else mma_commit_mc(&empty[s], CMASK);
+                        if (ci == G.NCT - 1) umma::mma_commit(&aempty[kb]);
+                        if (++s == nst) {
+                            s = 0;
+                            ph ^= 1;
+                        }
                     }
                     umma::mma_commit(&tfull[buf]);
                 }
@@ -284,12 +376,13 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int wq = warp & 3;                               // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                      // which 16 of the tile's 32 columns
         int tl = 0;
-        for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-            const long long rowbase = (long long)rb * BM + wq * 32;
-            for (int ct = 0; ct < G.NCT; ++ct, ++tl) {
+        for (int rl = 0; rl < niter; ++rl) {
+            const long long rowbase = ((long long)blockIdx.x + (long long)rl * gridDim.x) * BM + wq * 32;
+            for (int ci = 0; ci < G.NCT; ++ci, ++tl) {
+                const int ct = (ci + ct0 < G.NCT) ? ci + ct0 : ci + ct0 - G.NCT;
                 const int c0 = ct * CT + half * 16;
                 const int buf = tl & 1;
-                umma::mbar_wait_bounded(&tfull[buf], (uint32_t)((tl >> 1) & 1));
+                PROF_WAIT(w0, umma::mbar_wait_bounded(&tfull[buf], (uint32_t)((tl >> 1) & 1)));
                 umma::fence_after_sync();
                 const uint32_t taddr = tmem + (uint32_t)(buf * 256 + half * 16) + ((uint32_t)(wq * 32) << 16);
                 uint32_t a[2][NPL][8];
@@ -301,56 +394,85 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 umma::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[buf]);       // the accumulator buffer is free again
-                // lane = row: 16 outputs (8 column pairs) per lane
-                double o[16];
+                // lane = row: 16 outputs per lane, staged in this warp's [32 rows][128 B] tile (16-byte chunks XOR-swizzled
+                // with the row, the SWIZZLE_128B pattern of the store map: conflict-free 16-byte shared-memory stores)
+                // and written by ONE TMA tensor store (rows >= N and columns >= PP are clipped by the map).  Per-lane
+                // 16-byte global stores touched 32 rows per instruction and a shuffle transposition cost ~25 instructions
+                // per output: both made the epilogue, not the MMAs, the limit.
+                unsigned char *stage = o_base + (warp - 2) * 4096;
+                if (lane == 0) PROF_WAIT(w1, bulk_wait_read_all());   // the previous store of this warp has read the tile
+                __syncwarp();
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch)
+                for (int ch = 0; ch < 2; ++ch) {
+                    if (c0 + ch * 8 >= G.PP) continue;          // a chunk of 8 columns is entirely in or out
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        int dg[NPL];
+                    for (int k = 0; k < 8; k += 2) {
+                        int d0[NPL], d1[NPL];
 #pragma unroll
-                        for (int p = 0; p < NPL; ++p) dg[p] = (int)a[ch][p][k];
-                        const int c = c0 + ch * 8 + k;
-                        o[ch * 8 + k] = fma(fcol[c], combine7(dg), p0v[c]);
-                    }
-                // 8 x 8 transposition of the column pairs inside every group of 8 lanes (three butterfly stages): lane
-                // (g, k) ends up with pair k of the rows 8g .. 8g+7, so that one store instruction covers 4 rows x 128
-                // contiguous bytes instead of 32 rows x 16 bytes (32 cache lines per instruction made the stores,
-                // not the MMAs, the bottleneck)
-#pragma unroll
-                for (int m = 1; m < 8; m <<= 1) {
-                    const bool up = (lane & m) != 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (k & m) continue;
-                        const int lo = 2 * k, hi = 2 * (k | m);
-                        const double s0 = up ? o[lo] : o[hi], s1 = up ? o[lo + 1] : o[hi + 1];
-                        const double r0 = __shfl_xor_sync(0xffffffffu, s0, m), r1 = __shfl_xor_sync(0xffffffffu, s1, m);
-                        if (up) {
-                            o[lo] = r0;
-                            o[lo + 1] = r1;
-                        } else {
-                            o[hi] = r0;
-                            o[hi + 1] = r1;
+                        for (int p = 0; p < NPL; ++p) {
+                            d0[p] = (int)a[ch][p][k];
+                            d1[p] = (int)a[ch][p][k + 1];
                         }
+                        const int c = c0 + ch * 8 + k;
+                        const double2 f2 = *reinterpret_cast<const double2 *>(&fcol[c]);
+                        const double2 p2 = *reinterpret_cast<const double2 *>(&p0v[c]);
+                        double2 o;
+                        o.x = fma(f2.x, combine7(d0), p2.x);
+                        o.y = fma(f2.y, combine7(d1), p2.y);
+                        const int chunk = ch * 4 + (k >> 1);
+                        *reinterpret_cast<double2 *>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
                     }
                 }
-                const int col = c0 + 2 * (lane & 7);
-                if (col < G.PP) {                               // PP is even: a pair is entirely in or out
-                    const long long r0 = rowbase + 8 * (lane >> 3);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (r0 + j < N)
-                            *reinterpret_cast<double2 *>(MZ + (r0 + j) * ldmz + col) = make_double2(o[2 * j], o[2 * j + 1]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0 && c0 < G.PP) {
+                    tma_store_2d(&tmO, c0, (int)rowbase, stage);
+                    bulk_commit();
                 }
             }
         }
+        if (lane == 0) bulk_wait_read_all();
+    }
+#undef PROF_WAIT
+    if (prof && lane == 0 && warp < 3) {   // [producer: empty, aempty, -][MMA: full, tempty, afull][epilogue warp 2: tfull, store-read, -][total]
+        long long *o = prof + (size_t)blockIdx.x * 10 + warp * 3;
+        o[0] = w0;
+        o[1] = w1;
+        o[2] = w2;
+        if (warp == 0) prof[(size_t)blockIdx.x * 10 + 9] = clock64() - tstart;
     }
     umma::fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still multicast into it or signal its barriers
     if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
+// launch with a cluster dimension (cl = 1: plain launch)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_cluster(void (*kern)(KArgs...), int grid, int block, size_t smem, int cl, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = cl > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+int i8_cluster_size() {                     // PYVB_I8_CLUSTER = 1 | 2 | 4 (default 2)
+    static int cl = 0;
+    if (!cl) {
+        const char *e = getenv("PYVB_I8_CLUSTER");
+        cl = e ? atoi(e) : 2;
+        if (cl != 1 && cl != 2 && cl != 4) cl = 2;
+    }
+    return cl;
+}
 
 // =====================================================================================================================
 // K3-i8: the mask-type sufficient statistics  T1 = O^T vec<zz^T>,  Bst = O^T Zbar  (hstack, nodes/nodes_todo.py:50-61)
@@ -502,6 +624,9 @@ size_t si8_smem_bytes(int q) {
     return 1024 + (size_t)SST * (A_B + B_B) + (size_t)((i_tri(q) + q + 31) & ~31) * 8 + (size_t)(2 * SST + 4) * 8 + 16;
 }
 
+// CL > 1: the CTAs of a cluster take CL consecutive blocks of data dimensions of the same (column tile, chunk) item and
+// share its digit tiles by multicast, as in K1-i8.
+template <int CL>
 __global__ void __launch_bounds__(NTHR, 1)
 stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long N, int D, int q,
                 const double *__restrict__ zscale, double *__restrict__ ws, long long rows_per_chunk, int nchunks, int ndb,
@@ -518,14 +643,18 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t *tbase = reinterpret_cast<uint32_t *>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nitems = ndb * nct * nchunks;
+    const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
+    const int ndg = (ndb + CL - 1) / CL;                       // groups of CL blocks of data dimensions
+    const int nitems = ndg * nct * nchunks;                    // items of a CLUSTER
+    const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     for (int c = tid; c < NCZ; c += NTHR) fcol[c] = zscale[c] * 5.5511151231257827e-17;   // 2^-54
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < SST; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
@@ -536,15 +665,17 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) umma::tmem_alloc(tbase, 512);
     umma::fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     umma::fence_after_sync();
     const uint32_t tmem = *tbase;
 
-    // item -> (chunk, dblk, ct), chunk-major; K steps of the chunk
+    // item -> (chunk, group of blocks of data dimensions, ct), chunk-major; K steps of the chunk
     auto item_geom = [&](int item, int &chunk, int &db, int &ct, long long &r0, int &nsteps) {
-        chunk = item / (ndb * nct);
-        const int rem = item - chunk * (ndb * nct);
-        db = rem / nct;
-        ct = rem - db * nct;
+        chunk = item / (ndg * nct);
+        const int rem = item - chunk * (ndg * nct);
+        const int dg = rem / nct;
+        ct = rem - dg * nct;
+        db = dg * CL + crank;                                   // may be >= ndb (an odd block count): its rows are discarded
         r0 = (long long)chunk * rows_per_chunk;
         long long r1 = r0 + rows_per_chunk;
         if (r1 > N) r1 = N;
@@ -554,7 +685,7 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {
             int it = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (int item = cid; item < nitems; item += ncl) {
                 int chunk, db, ct, nsteps;
                 long long r0;
                 item_geom(item, chunk, db, ct, r0, nsteps);
@@ -565,7 +696,11 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
                     const long long kb = r0 / BKB + k;
                     tma_load_3d_i8(st, &tmA, 0, (int)(kb * D + db * BM), 0, &full[s]);               // 128 data dimensions x 64 rows
-                    tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
+                    if (CL == 1)
+                        tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
+                    else
+                        tma_load_3d_i8_mc(st + A_B + crank * (B_B / CL), &tmB, 0,
+                                          (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / CL)), 0, &full[s], CMASK);
                 }
             }
         }
@@ -573,7 +708,7 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) {
             const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
             int it = 0, tl = 0;
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tl) {
+            for (int item = cid; item < nitems; item += ncl, ++tl) {
                 int chunk, db, ct, nsteps;
                 long long r0;
                 item_geom(item, chunk, db, ct, r0, nsteps);
@@ -590,7 +725,8 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int ks = 0; ks < BKB / 32; ++ks)
                         umma::mma_i8(dacc, umma::desc_kmajor_sw64(a0, ks), umma::desc_kmajor_sw64(a0 + A_B, ks), idesc,
                                      (k | ks) ? 1u : 0u);
-                    umma::mma_commit(&empty[s]);
+                    if (CL == 1) umma::mma_commit(&empty[s]);
+                    else mma_commit_mc(&empty[s], CMASK);
                 }
                 umma::mma_commit(&tfull[buf]);
             }
@@ -599,7 +735,7 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const StatLayout L(D, q);
         const int wq = warp & 3, half = (warp - 2) >> 2;
         int tl = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++tl) {
+        for (int item = cid; item < nitems; item += ncl, ++tl) {
             int chunk, db, ct, nsteps;
             long long r0;
             item_geom(item, chunk, db, ct, r0, nsteps);
@@ -639,20 +775,72 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     umma::fence_before_sync();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+
+// ---- microbenchmark: back-to-back tcgen05.mma on fixed shared-memory operands (no loads): the tensor-core rate of the
+// box for kind::i8 (kind = 0) or kind::f16 / bf16 (kind = 1) at M = 128, N = n, one K step of 32 bytes per instruction.
+__global__ void __launch_bounds__(128, 1) bench_umma_kernel(int iters, int n, int kind, long long *clk_out) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tb;
+    for (int i = threadIdx.x; i < (A_B + 256 * BKB) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < 32) umma::tmem_alloc(&tb, 512);
+    fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tb;
+    if (threadIdx.x == 0) {
+        const uint32_t a0 = smem_u32(smem), b0 = a0 + A_B;
+        const uint32_t idesc = kind == 0 ? umma::idesc_s8_s32(BM, n) : umma::idesc_bf16_f32(BM, n, 0, 0);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const uint32_t d = tmem + (uint32_t)((it & 1) * 256);
+            if (kind == 0) {
+                umma::mma_i8(d, umma::desc_kmajor_sw64(a0, 0), umma::desc_kmajor_sw64(b0, 0), idesc, 1u);
+                umma::mma_i8(d, umma::desc_kmajor_sw64(a0, 1), umma::desc_kmajor_sw64(b0, 1), idesc, 1u);
+            } else {
+                umma::mma_bf16(d, umma::desc_kmajor_sw64(a0, 0), umma::desc_kmajor_sw64(b0, 0), idesc, 1u);
+                umma::mma_bf16(d, umma::desc_kmajor_sw64(a0, 1), umma::desc_kmajor_sw64(b0, 1), idesc, 1u);
+            }
+        }
+        umma::mma_commit(&bar);
+        umma::mbar_wait_bounded(&bar, 0);
+        clk_out[blockIdx.x] = clock64() - t0;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) umma::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
 
+cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, cudaStream_t st) {
+    const size_t smem = 1024 + A_B + 256 * BKB;
+    cudaError_t e = cudaFuncSetAttribute(bench_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bench_umma_kernel<<<blocks, 128, smem, st>>>(iters, n, kind, clk_out);
+    return cudaGetLastError();
+}
+
 bool i8_supported(int D, int q) {
-    return (q == 16 || q == 32 || q == 64) && D >= 64 && (D % 64) == 0 && i8_smem_bytes(D, q) <= 227 * 1024;
+    return (q == 16 || q == 32 || q == 64) && D >= 64 && (D % 64) == 0 && i8_stages(D, q) >= 2;
 }
 size_t i8_digits_bytes(int D, int q) { return (size_t)(i_nc8(q) / CT) * NPL * CT * D; }
+size_t i8_mask_bytes(long long N, int D) { return (size_t)((N + BM - 1) / BM * BM) * (size_t)D; }
 int i8_ncols(int q) { return i_nc8(q); }
 
 cudaError_t launch_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    long long b = (N * (long long)(D / 4) + 255) / 256;
+    long long b = (((N + BM - 1) / BM * BM) * (long long)(D / 4) + 255) / 256;
     if (b > 148 * 16) b = 148 * 16;
     prepare_mask_i8_kernel<<<(unsigned)b, 256, 0, st>>>(N, D, X, ldx, static_cast<signed char *>(mask));
     return cudaGetLastError();
@@ -669,18 +857,53 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
     if (N <= 0) return cudaSuccess;
     if (!i8_supported(D, q)) return cudaErrorNotSupported;
     const I8Geom g(q);
-    CUtensorMap tmA, tmB;
-    cudaError_t e = make_map_u8_3d(&tmA, mask, (uint64_t)D, (uint64_t)N, 1, BKB, BM);
-    if (e != cudaSuccess) return e;
-    e = make_map_u8_3d(&tmB, GI, (uint64_t)D, (uint64_t)(NPL * CT), (uint64_t)g.NCT, BKB, NPL * CT);
-    if (e != cudaSuccess) return e;
-    const size_t smem = i8_smem_bytes(D, q);
-    e = cudaFuncSetAttribute(zstep_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const long long nrb = (N + BM - 1) / BM;
-    const int grid = (int)(nrb < 148 ? nrb : 148);
-    zstep_i8_kernel<<<grid, NTHR, smem, st>>>(tmA, tmB, N, D, q, P0, gscale, gl, MZ, ldmz, (int)nrb);
-    return cudaGetLastError();
+    int cl = i8_cluster_size();
+    while (cl > 1 && nrb < 2LL * cl) cl >>= 1;               // tiny problems: no point in pairing
+    CUtensorMap tmA, tmB;
+    const uint64_t nk = (uint64_t)(D / BKB);
+    if ((uint64_t)nrb * nk * BM >= (1ULL << 31)) return cudaErrorNotSupported;
+    cudaError_t e = make_map_u8_3d(&tmA, mask, BKB, (uint64_t)nrb * nk * BM, 1, BKB, BM);
+    if (e != cudaSuccess) return e;
+    e = make_map_u8_3d(&tmB, GI, BKB, nk * g.NCT * (NPL * CT), 1, BKB, NPL * CT / cl);
+    if (e != cudaSuccess) return e;
+    CUtensorMap tmO;
+    {   // the qprec columns [0, PP) of the MZ rows, as [N][PP] doubles with the row pitch ldmz: 16-column x 32-row boxes
+        EncodeTiledFn enc = get_encode_i8();
+        if (!enc) return cudaErrorNotSupported;
+        cuuint64_t dims[2] = {(cuuint64_t)g.PP, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)ldmz * sizeof(double)};
+        cuuint32_t box[2] = {16, 32}, es[2] = {1, 1};
+        CUresult r = enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, MZ, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+    const int nst = i8_stages(D, q);
+    const size_t smem = i8_smem_bytes(D, q, nst);
+    long long gl_ = (nrb + cl - 1) / cl * cl;
+    const int grid = (int)(gl_ < 148 ? gl_ : 148 / cl * cl);
+    auto kern = cl == 4 ? zstep_i8_kernel<4> : cl == 2 ? zstep_i8_kernel<2> : zstep_i8_kernel<1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    static long long *prof = nullptr;
+    static int prof_on = -1;
+    if (prof_on < 0) {
+        prof_on = getenv("PYVB_I8_PROF") ? 1 : 0;
+        if (prof_on && cudaMalloc(&prof, 148 * 10 * sizeof(long long)) != cudaSuccess) prof_on = 0;
+    }
+    e = launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, tmO, N, D, q, P0, gscale, gl, (int)nrb, nst,
+                       prof_on ? prof : (long long *)nullptr);
+    if (prof_on && e == cudaSuccess) {      // diagnosis only: synchronises
+        long long h[148 * 10];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+        double a[10] = {0};
+        for (int b = 0; b < grid; ++b)
+            for (int k = 0; k < 10; ++k) a[k] += (double)h[b * 10 + k] / grid;
+        fprintf(stderr, "[i8 prof] N=%lld D=%d q=%d cl=%d nst=%d total %.0f clk | producer: empty %.0f aempty %.0f | mma: full %.0f tempty %.0f afull %.0f | epilogue(w2): tfull %.0f store-read %.0f\n",
+                N, D, q, cl, nst, a[9], a[0], a[1], a[3], a[4], a[5], a[6], a[7]);
+    }
+    return e;
 }
 
 // ---- K3-i8 host side
@@ -694,11 +917,13 @@ size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * ldmz +
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
 // chunks: items = ndb * nct * nchunks a whole number of rounds over 148 CTAs, chunks of >= 32 K steps, <= 2^23 rows
 int stats_i8_nchunks(long long N, int D, int q) {
-    const long long per = (long long)((D + BM - 1) / BM) * (stats_i8_ncols(q) / CT);
-    const long long step = 148 / gcd_ll(148, per);
+    const int cl = i8_cluster_size();
+    const long long ncl = 148 / cl;
+    const long long per = (long long)(((D + BM - 1) / BM + cl - 1) / cl) * (stats_i8_ncols(q) / CT);   // items of a cluster per chunk
+    const long long step = ncl / gcd_ll(ncl, per);
     long long by_rows = N / (32LL * BKB);
     if (by_rows < 1) by_rows = 1;
-    long long k = (6 * 148LL + per * step - 1) / (per * step);      // ~6 items per CTA
+    long long k = (6 * ncl + per * step - 1) / (per * step);        // ~6 items per cluster
     if (k < 1) k = 1;
     long long c = k * step;
     if (c > by_rows) c = (by_rows >= step) ? (by_rows / step) * step : by_rows;
@@ -721,21 +946,28 @@ cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long lo
 }
 
 // colmax -> zscale -> digit planes of the MZ rows -> T1, Bst partial sums of every row chunk in ws[chunk][stat layout]
+// zmax (nullable): per-CTA bounds on the column maxima left by K2 next to its column sums (nzblk partials of stride zkw,
+// column c at zmax[c]); without it one more pass over the MZ rows finds the maxima
 cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,
-                            double *scratch, double *ws, int nchunks, cudaStream_t st) {
+                            double *scratch, double *ws, int nchunks, const double *zmax, int nzblk, int zkw,
+                            cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int P = i_tri(q), NCZ = stats_i8_ncols(q), nct = NCZ / CT, ndb = (D + BM - 1) / BM;
     const long long npad = stats_i8_npad(N);
     double *pm = scratch, *zscale = scratch + (size_t)CM_BLOCKS * ldmz;
-    int nblk = CM_BLOCKS;
-    long long rpb = (N + nblk - 1) / nblk;
-    if (rpb < 64) rpb = 64;
-    nblk = (int)((N + rpb - 1) / rpb);
-    const size_t cms = (size_t)ldmz * sizeof(double);
-    if (q == 16) colmax_kernel<5><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-    else if (q == 32) colmax_kernel<18><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-    else colmax_kernel<68><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-    colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, ldmz, pm, nblk, zscale);
+    if (zmax != nullptr && nzblk > 0) {
+        colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, zkw, zmax, nzblk, zscale);
+    } else {
+        int nblk = CM_BLOCKS;
+        long long rpb = (N + nblk - 1) / nblk;
+        if (rpb < 64) rpb = 64;
+        nblk = (int)((N + rpb - 1) / rpb);
+        const size_t cms = (size_t)ldmz * sizeof(double);
+        if (q == 16) colmax_kernel<5><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
+        else if (q == 32) colmax_kernel<18><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
+        else colmax_kernel<68><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
+        colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, ldmz, pm, nblk, zscale);
+    }
     dim3 gd((unsigned)((N + 127) / 128), (unsigned)nct);
     digitize_kernel<<<gd, 256, 0, st>>>(N, npad, ldmz, P + q, MZ, zscale, static_cast<signed char *>(ZI));
     cudaError_t e = cudaGetLastError();
@@ -754,19 +986,20 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
         cuuint64_t db[3] = {BKB, nkb * nct * (NPL * CT), 1}, sb[2] = {BKB, nkb * nct * (NPL * CT) * BKB};
-        cuuint32_t bb[3] = {BKB, NPL * CT, 1};
+        cuuint32_t bb[3] = {BKB, (cuuint32_t)(NPL * CT / i8_cluster_size()), 1};
         r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, ZI, db, sb, bb, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     }
     const size_t smem = si8_smem_bytes(q);
-    e = cudaFuncSetAttribute(stats_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int cl = i8_cluster_size();
+    auto kern = cl == 4 ? stats_i8_kernel<4> : cl == 2 ? stats_i8_kernel<2> : stats_i8_kernel<1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const long long nitems = (long long)ndb * nct * nchunks;
-    const int grid = (int)(nitems < 148 ? nitems : 148);
-    stats_i8_kernel<<<grid, NTHR, smem, st>>>(tmA, tmB, N, D, q, zscale, ws, stats_i8_rows_per_chunk(N, nchunks), nchunks,
-                                              ndb, nct);
-    return cudaGetLastError();
+    const long long nitems = (long long)((ndb + cl - 1) / cl) * nct * nchunks;
+    const int grid = (int)(nitems < 148 / cl ? nitems : 148 / cl) * cl;
+    return launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, N, D, q, (const double *)zscale, ws,
+                          stats_i8_rows_per_chunk(N, nchunks), nchunks, ndb, nct);
 }
 
 }  // namespace pyvb

@@ -48,9 +48,9 @@ template <int Q> struct KB {
     static constexpr int P = kb_tri(Q), PP = (P + 7) & ~7, OROW = PP + Q, LDG = kb_pitch(Q);
     static constexpr int WARPS = KBC<Q>::WARPS, OCC = KBC<Q>::OCC, MPW = KBC<Q>::MPW;
     static constexpr bool ZS = KBC<Q>::ZS;
-    static constexpr int KW = OROW + PYVB_ZS_EXTRA;
+    static constexpr int KW = 2 * OROW + PYVB_ZS_EXTRA;   // [column sums OROW | 4 scalars | bounds on the column maxima OROW]
     static constexpr int MAT_D = NBLK * 64 + 2 * Q;                             // per matrix: blocks | eta | z
-    static constexpr int WARP_D = MPW * MAT_D + (ZS ? OROW : 0) + 4;            // ... | column sums | scalars
+    static constexpr int WARP_D = MPW * MAT_D + (ZS ? OROW : 0) + 4 + (ZS ? 2 * Q : 0);   // ... | column sums | scalars | max <z_i^2>, max |z_i|
     static constexpr int TAB_B = ((P * 4) + 15) & ~15;                         // one uint32 table
     static constexpr int UNR = (P / 32 >= 16) ? 16 : (P + 31) / 32;            // global loads in flight per lane
     static constexpr size_t SMEM = (size_t)TAB_B + (size_t)WARPS * WARP_D * 8;
@@ -96,6 +96,10 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
     double *wbase = reinterpret_cast<double *>(smem_kb + T::TAB_B) + (size_t)warp * T::WARP_D;
     double *csum = wbase + MPW * T::MAT_D;                       // [OROW] when ZS
     double *wsc = csum + (T::ZS ? T::OROW : 0);                  // [4]
+    double *wmx = wsc + 4;                                       // [2 Q] when ZS: max_n <z_i z_i>, max_n |<z_i>| of this warp's rows
+    double dmx[(Q + 31) / 32], zmx[(Q + 31) / 32];
+#pragma unroll
+    for (int k = 0; k < (Q + 31) / 32; ++k) dmx[k] = zmx[k] = 0.0;
 
     for (int p = tid; p < T::P; p += 32 * T::WARPS) {
         int i, j;
@@ -351,11 +355,20 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
                 if (sg) sg[p] = s;
                 if (T::ZS) csum[p] += mm;
             }
-            for (int c = lane; c < Q; c += 32) {
+#pragma unroll
+            for (int k = 0; k < (Q + 31) / 32; ++k) {
+                const int c = lane + 32 * k;
+                if (c >= Q) continue;
                 const double z = zv[m][c];
                 row[m][IO::ZOFF + c] = (io_t)z;
                 if (F32) store_split3(MP + n * IO::PITCH + IO::ZOFF + c, (size_t)N * IO::PITCH, (float)z);
-                if (T::ZS) csum[T::PP + c] += z;
+                if (T::ZS) {
+                    csum[T::PP + c] += z;
+                    // <z_c z_c> = Sigma_cc + z_c^2: with the diagonal maxima, |<z_i z_j>| <= sqrt(<z_i z_i> <z_j z_j>) bounds
+                    // every column of the packed rows (the fixed-point scales of the INT8 statistics)
+                    dmx[k] = fmax(dmx[k], fma(z, z, blk[m][kb_boff(c >> 3, c >> 3) + kb_sw(c & 7, c & 7)]));
+                    zmx[k] = fmax(zmx[k], fabs(z));
+                }
             }
             if (lane == 0) {
                 logdet[n] = ldsum;
@@ -375,13 +388,38 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
         wsc[2] = s_n;
         wsc[3] = 0.0;
     }
+#pragma unroll
+    for (int k = 0; k < (Q + 31) / 32; ++k)
+        if (lane + 32 * k < Q) {
+            wmx[lane + 32 * k] = dmx[k];
+            wmx[Q + lane + 32 * k] = zmx[k];
+        }
     __syncthreads();
     double *out = zsums + (size_t)blockIdx.x * T::KW;
     const double *w0 = reinterpret_cast<const double *>(smem_kb + T::TAB_B) + MPW * T::MAT_D;   // csum of warp 0
-    for (int c = tid; c < T::KW; c += 32 * T::WARPS) {
+    for (int c = tid; c < T::OROW + 4; c += 32 * T::WARPS) {
         double a = 0.0;
         for (int w = 0; w < T::WARPS; ++w) a += w0[(size_t)w * T::WARP_D + c];   // [csum OROW | scalars 4] is contiguous
         out[c] = a;
+    }
+    // CTA maxima of the diagonal second moments and of |z| (fold the warps into warp 0's slots), then the column bounds
+    double *m0 = const_cast<double *>(w0) + T::OROW + 4;
+    __syncthreads();
+    for (int c = tid; c < 2 * Q; c += 32 * T::WARPS) {
+        double a = 0.0;
+        for (int w = 0; w < T::WARPS; ++w) a = fmax(a, m0[(size_t)w * T::WARP_D + c]);
+        m0[c] = a;
+    }
+    __syncthreads();
+    for (int c = tid; c < T::OROW; c += 32 * T::WARPS) {
+        double a = 0.0;
+        if (c < T::P) {
+            const uint32_t t = tab[c];
+            a = sqrt(m0[(t >> 12) & 63] * m0[t >> 18]);
+        } else if (c >= T::PP) {
+            a = m0[Q + c - T::PP];
+        }
+        out[T::OROW + 4 + c] = a;
     }
 }
 

@@ -44,8 +44,8 @@ template <int Q> struct TK {
     static constexpr int WARPS = 5;
     static constexpr int WARP_D = NE * LP;
     static constexpr int NU = (P + 31) / 32;              // packed elements per lane in the cooperative copies
-    static constexpr int KW = OROW + PYVB_ZS_EXTRA;
-    static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8 + (size_t)WARPS * (OROW + 4) * 8;
+    static constexpr int KW = 2 * OROW + PYVB_ZS_EXTRA;   // [column sums OROW | 4 scalars | column maxima of |.| OROW]
+    static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8 + (size_t)WARPS * KW * 8;
 };
 
 // 8 x 8 lower triangle in registers (packed, A[t_idx(i, j)]).  In: SPD block.  Out: X = chol(A)^-1 (lower triangular);
@@ -120,12 +120,13 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
     extern __shared__ __align__(16) double smem_t[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *sm = smem_t + (size_t)warp * T::WARP_D;
-    double *wsum = smem_t + (size_t)T::WARPS * T::WARP_D + (size_t)warp * (T::OROW + 4);
+    double *wsum = smem_t + (size_t)T::WARPS * T::WARP_D + (size_t)warp * T::KW;
 #define EL(e) sm[(e) * LP + lane]
     // column sums of the finished rows, kept in registers: packed element lane + 32 u, zbar element lane (if < Q)
     double cs[T::NU], cz = 0.0, s_qld = 0.0, s_ld = 0.0, s_n = 0.0;
+    double cm[T::NU], czm = 0.0;                            // ... and their maxima of |.| (the scales of the INT8 statistics)
 #pragma unroll
-    for (int u = 0; u < T::NU; ++u) cs[u] = 0.0;
+    for (int u = 0; u < T::NU; ++u) cs[u] = cm[u] = 0.0;
 
     const long long nwarps = (long long)gridDim.x * T::WARPS;
     const long long nbatch = (N + 31) / 32;
@@ -374,6 +375,7 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
                     row[IO::POFF + e] = (io_t)v;
                     if (F32) split3_store(MP + (n0 + m) * IO::PITCH + IO::POFF + e, (size_t)N * IO::PITCH, (float)v);
                     cs[u] += v;
+                    cm[u] = fmax(cm[u], fabs(v));
                 }
             }
             if (lane < Q) {
@@ -381,6 +383,7 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
                 row[IO::ZOFF + lane] = (io_t)v;
                 if (F32) split3_store(MP + (n0 + m) * IO::PITCH + IO::ZOFF + lane, (size_t)N * IO::PITCH, (float)v);
                 cz += v;
+                czm = fmax(czm, fabs(v));
             }
         }
         __syncwarp();
@@ -388,12 +391,18 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
 #undef EL
     if (zsums == nullptr) return;                                  // kernel-uniform
     // ---- CTA partial of the column sums: [packed P | pad | zbar q | sum 0.5/logdet | sum logdet | rows | 0]
-    for (int c = lane; c < T::OROW + 4; c += 32) wsum[c] = 0.0;
+    for (int c = lane; c < T::KW; c += 32) wsum[c] = 0.0;
     __syncwarp();
 #pragma unroll
     for (int u = 0; u < T::NU; ++u)
-        if (lane + 32 * u < P) wsum[lane + 32 * u] = cs[u];
-    if (lane < Q) wsum[T::PP + lane] = cz;
+        if (lane + 32 * u < P) {
+            wsum[lane + 32 * u] = cs[u];
+            wsum[T::OROW + 4 + lane + 32 * u] = cm[u];
+        }
+    if (lane < Q) {
+        wsum[T::PP + lane] = cz;
+        wsum[T::OROW + 4 + T::PP + lane] = czm;
+    }
     s_qld = warp_sum(s_qld);
     s_ld = warp_sum(s_ld);
     s_n = warp_sum(s_n);
@@ -407,7 +416,10 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
     const double *w0 = smem_t + (size_t)T::WARPS * T::WARP_D;
     for (int c = threadIdx.x; c < T::KW; c += 32 * T::WARPS) {
         double a = 0.0;
-        for (int w = 0; w < T::WARPS; ++w) a += w0[(size_t)w * (T::OROW + 4) + c];
+        if (c < T::OROW + 4)
+            for (int w = 0; w < T::WARPS; ++w) a += w0[(size_t)w * T::KW + c];
+        else
+            for (int w = 0; w < T::WARPS; ++w) a = fmax(a, w0[(size_t)w * T::KW + c]);
         out[c] = a;
     }
 }

@@ -130,7 +130,7 @@ class PlateEngine(object):
         elif self.use_i8 and not i8_ok:
             raise ValueError("algo='i8' needs mode B, FP64, q in (16, 32, 64), D % 64 == 0 and D <= ~1280")
         if self.use_i8:
-            self.mask8 = torch.empty(N, D, dtype=torch.int8, device=dev)
+            self.mask8 = torch.empty(int(self.lib.pyvb_i8_mask_bytes(N, D)), dtype=torch.int8, device=dev)
             self.GI = torch.empty(int(self.lib.pyvb_i8_digits_bytes(D, q)), dtype=torch.int8, device=dev)
             self.gscale = torch.empty(int(self.lib.pyvb_i8_ncols(q)), dtype=f64, device=dev)
         self._mask_valid = False
@@ -308,7 +308,7 @@ class PlateEngine(object):
 
     def _zsums_from_state(self):
         """FP32 variant: the column sums K2 would have left, from an injected state (one partial, rest zero)."""
-        kw = self.lib.pyvb_gw_woff(self.q) + self.q + 4
+        kw = int(self.lib.pyvb_zsums_kw(self.q))
         z = self.zsums.view(-1, kw)
         z.zero_()
         pp = int(self.lib.pyvb_gw_woff(self.q))
@@ -482,7 +482,7 @@ class PlateEngine(object):
             return
         full = (lo == 0 and hi == self.N and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA))
         self._zsums_valid = False
-        if self.use_i8:
+        if self.use_i8 and lo % 128 == 0:                   # (the int8 mask is tiled by 128 rows: other offsets take the DMMA path)
             if not self._mask_valid:                        # the int8 mask follows X (static in mode B)
                 rc = self.lib.pyvb_prepare_mask_i8(hi - lo, D, self.X.data_ptr() + lo * D * 8, D,
                                                    self.mask8.data_ptr() + lo * D, self._stream())
@@ -596,7 +596,7 @@ class PlateEngine(object):
         self._mask_valid = False
         self._maskT_valid = False
         step = (N + nchunks - 1) // nchunks
-        step = (step + 63) // 64 * 64
+        step = (step + 127) // 128 * 128
         for lo in range(0, N, step):
             hi = min(N, lo + step)
             with torch.cuda.stream(cs):

@@ -88,7 +88,8 @@ def test_i8_qprec_is_exact_to_rounding(eng, shape):
     assert np.all(np.abs(got - ref) <= bound), float(np.max(np.abs(got - ref) / bound))
     X0 = np.where(O, X - init["mu"][None, :], 0.0)
     assert tensor_rel(eta, tau * (X0 @ W)) < 1e-12
-    assert np.array_equal(e.mask8.cpu().numpy().astype(bool), O)
+    m = e.mask8.cpu().numpy().reshape(-1, D // 64, 128, 64).transpose(0, 2, 1, 3).reshape(-1, D)   # tiles -> rows
+    assert np.array_equal(m[:N].astype(bool), O) and not m[N:].any()
 
 
 @pytest.mark.parametrize("shape", [(3000, 256, 16), (1200, 64, 32), (700, 128, 64)])

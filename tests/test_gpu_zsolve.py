@@ -78,7 +78,19 @@ def test_zsolve_matches_lapack(impl, q, N):
     assert tensor_rel(logdet, 0.5 * np.linalg.slogdet(A)[1]) < 1e-12
     assert float(gl[11]) == 0.0
     if zs is not None:
-        tot = zs.reshape(-1, zoff + q + 4).sum(0)
+        kw = 2 * (zoff + q) + 4                         # [column sums | 4 scalars | column maxima of |.|]
+        part = zs.reshape(-1, kw)
+        tot = part[:, :zoff + q + 4].sum(0)
+        if impl != "reg":                               # the default kernels also leave (bounds on) the column maxima
+            mx = part[:, zoff + q + 4:].max(0)
+            true = np.abs(out).max(0)
+            cols = list(range(P)) + list(range(zoff, zoff + q))
+            assert np.all(mx[cols] >= true[cols] * (1 - 1e-12))
+            if impl == "tpm":
+                assert np.allclose(mx[cols], true[cols], rtol=1e-12)
+            else:                                       # PSD bound sqrt(max <z_i z_i> max <z_j z_j>): tight on the diagonal
+                di = [i * (i + 1) // 2 + i for i in range(q)]
+                assert np.allclose(mx[di], true[di], rtol=1e-12)
         assert tensor_rel(tot[:P], out[:, :P].sum(0)) < 1e-12
         assert tensor_rel(tot[zoff:zoff + q], out[:, zoff:zoff + q].sum(0)) < 1e-12
         assert tot[zoff + q + 2] == N
