@@ -124,9 +124,14 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
 #define EL(e) sm[(e) * LP + lane]
     // column sums of the finished rows, kept in registers: packed element lane + 32 u, zbar element lane (if < Q)
     double cs[T::NU], cz = 0.0, s_qld = 0.0, s_ld = 0.0, s_n = 0.0;
-    double cm[T::NU], czm = 0.0;                            // ... and their maxima of |.| (the scales of the INT8 statistics)
+    // ... and upper bounds on their maxima of |.| (the scales of the INT8 statistics): the maximum of the high words of
+    // |v| as integers (two integer instructions per element), rounded up by one unit of the high word at the end
+    int cm[T::NU], czm = 0;
 #pragma unroll
-    for (int u = 0; u < T::NU; ++u) cs[u] = cm[u] = 0.0;
+    for (int u = 0; u < T::NU; ++u) {
+        cs[u] = 0.0;
+        cm[u] = 0;
+    }
 
     const long long nwarps = (long long)gridDim.x * T::WARPS;
     const long long nbatch = (N + 31) / 32;
@@ -375,7 +380,7 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
                     row[IO::POFF + e] = (io_t)v;
                     if (F32) split3_store(MP + (n0 + m) * IO::PITCH + IO::POFF + e, (size_t)N * IO::PITCH, (float)v);
                     cs[u] += v;
-                    cm[u] = fmax(cm[u], fabs(v));
+                    cm[u] = max(cm[u], __double2hiint(v) & 0x7fffffff);
                 }
             }
             if (lane < Q) {
@@ -383,7 +388,7 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
                 row[IO::ZOFF + lane] = (io_t)v;
                 if (F32) split3_store(MP + (n0 + m) * IO::PITCH + IO::ZOFF + lane, (size_t)N * IO::PITCH, (float)v);
                 cz += v;
-                czm = fmax(czm, fabs(v));
+                czm = max(czm, __double2hiint(v) & 0x7fffffff);
             }
         }
         __syncwarp();
@@ -397,11 +402,11 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
     for (int u = 0; u < T::NU; ++u)
         if (lane + 32 * u < P) {
             wsum[lane + 32 * u] = cs[u];
-            wsum[T::OROW + 4 + lane + 32 * u] = cm[u];
+            wsum[T::OROW + 4 + lane + 32 * u] = cm[u] ? __hiloint2double(cm[u] + 1, 0) : 0.0;
         }
     if (lane < Q) {
         wsum[T::PP + lane] = cz;
-        wsum[T::OROW + 4 + T::PP + lane] = czm;
+        wsum[T::OROW + 4 + T::PP + lane] = czm ? __hiloint2double(czm + 1, 0) : 0.0;
     }
     s_qld = warp_sum(s_qld);
     s_ld = warp_sum(s_ld);

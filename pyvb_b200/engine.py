@@ -459,7 +459,7 @@ class PlateEngine(object):
         _cabi.check(rc, "pyvb_wupdate_f64")
         self._gw_fresh = False
 
-    def update_Z(self, lo=0, hi=None):
+    def update_Z(self, lo=0, hi=None, _chunk_zsums=False):
         hi = self.N if hi is None else hi
         self._stats_fresh = False
         if hi <= lo:
@@ -481,6 +481,8 @@ class PlateEngine(object):
             self._zsums_valid = full
             return
         full = (lo == 0 and hi == self.N and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA))
+        # (_chunk_zsums: iterate_from_host takes the K2 partials of a row chunk for that chunk's statistics)
+        zs = self.zsums.data_ptr() if ((full or _chunk_zsums) and self.zsums is not None) else 0
         self._zsums_valid = False
         if self.use_i8 and lo % 128 == 0:                   # (the int8 mask is tiled by 128 rows: other offsets take the DMMA path)
             if not self._mask_valid:                        # the int8 mask follows X (static in mode B)
@@ -493,8 +495,7 @@ class PlateEngine(object):
                                             self.Gw.data_ptr(), self.ldg, self.P0.data_ptr(), self.h0.data_ptr(),
                                             self.gl.data_ptr(), self.MZ.data_ptr() + lo * self.ldmz * 8, self.ldmz,
                                             self.GI.data_ptr(), self.gscale.data_ptr(), sig,
-                                            self.logdet.data_ptr() + lo * 8, self.zsums.data_ptr() if full else 0,
-                                            0, self._stream())
+                                            self.logdet.data_ptr() + lo * 8, zs, 0, self._stream())
             _cabi.check(rc, "pyvb_zstep_i8_f64")
             self._zsums_valid = full
             return
@@ -502,8 +503,7 @@ class PlateEngine(object):
                                      self.ldg, self.P0.data_ptr(), self.h0.data_ptr(), self.gl.data_ptr(),
                                      self.Zbar.data_ptr() + lo * self.ldmz * 8, self.ldmz,
                                      self.M2.data_ptr() + lo * self.ldmz * 8, self.ldmz, sig,
-                                     self.logdet.data_ptr() + lo * 8, self.zsums.data_ptr() if full else 0,
-                                     self.algo, self._stream())
+                                     self.logdet.data_ptr() + lo * 8, zs, self.algo, self._stream())
         _cabi.check(rc, "pyvb_zstep_f64")
         self._zsums_valid = full
         self._stats_fresh = False
@@ -581,8 +581,10 @@ class PlateEngine(object):
     def iterate_from_host(self, Xh, nchunks=8):
         """One mode-B sweep whose data shard comes from (pinned) HOST memory: the upload is cut into row chunks on
         a copy stream and the Z step of chunk c (K1 + K2) runs while chunk c+1 is still on the PCIe bus.  The W
-        update needs no data (it uses the statistics of the previous sweep), so it goes first; the statistics
-        pass needs all rows and goes last.  Returns the trace slot of the bound (no host synchronisation)."""
+        update needs no data (it uses the statistics of the previous sweep), so it goes first.  The statistics are sums
+        over rows: on the tensor-core paths every chunk's statistics are taken right behind its Z step and added up, so
+        that only the last chunk's work is left when the upload ends.  Returns the trace slot of the bound (no host
+        synchronisation)."""
         assert self.mode == "B"
         N = self.N
         cur = torch.cuda.current_stream(self.device)
@@ -597,6 +599,12 @@ class PlateEngine(object):
         self._maskT_valid = False
         step = (N + nchunks - 1) // nchunks
         step = (step + 127) // 128 * 128
+        chunked = (not self.f32 and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA)
+                   and bool(self.lib.pyvb_algo_supported(ALGO_DMMA, self.D, self.q)))
+        if chunked:
+            if getattr(self, "_acc", None) is None:
+                self._acc, self._tmp = torch.zeros_like(self.stats), torch.zeros_like(self.stats)
+            self._acc.zero_()
         for lo in range(0, N, step):
             hi = min(N, lo + step)
             with torch.cuda.stream(cs):
@@ -604,7 +612,21 @@ class PlateEngine(object):
                 ev = torch.cuda.Event()
                 ev.record(cs)
             cur.wait_event(ev)
-            self.update_Z(lo, hi)
+            self.update_Z(lo, hi, _chunk_zsums=chunked)
+            if chunked:
+                rc = self.lib.pyvb_stats_f64(hi - lo, self.D, self.q, self.X.data_ptr() + lo * self.D * 8, self.D, 0, 0, 0,
+                                             self.Zbar.data_ptr() + lo * self.ldmz * 8, self.ldmz,
+                                             self.M2.data_ptr() + lo * self.ldmz * 8, self.ldmz,
+                                             self.logdet.data_ptr() + lo * 8, self._tmp.data_ptr(), self.ws.data_ptr(),
+                                             self.ws_bytes, 0, 0, self.zsums.data_ptr(), 1, None, ALGO_DMMA, self._stream())
+                _cabi.check(rc, "pyvb_stats_f64 (chunk)")
+                self._acc += self._tmp
+        if chunked:
+            self.stats.copy_(self._acc)
+            if self.distributed:
+                allreduce_stats(self.stats)
+            self._stats_fresh = True
+            self._zsums_valid = False
         slot = self.trace_pos % self.trace.numel()
         self._global(OP_MU | OP_ALPHA | OP_BETA | OP_ELBO, self.trace.data_ptr() + slot * 8)
         self.trace_pos += 1

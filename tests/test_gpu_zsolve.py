@@ -87,7 +87,7 @@ def test_zsolve_matches_lapack(impl, q, N):
             cols = list(range(P)) + list(range(zoff, zoff + q))
             assert np.all(mx[cols] >= true[cols] * (1 - 1e-12))
             if impl == "tpm":
-                assert np.allclose(mx[cols], true[cols], rtol=1e-12)
+                assert np.allclose(mx[cols], true[cols], rtol=2e-6)        # high-word maxima, rounded up
             else:                                       # PSD bound sqrt(max <z_i z_i> max <z_j z_j>): tight on the diagonal
                 di = [i * (i + 1) // 2 + i for i in range(q)]
                 assert np.allclose(mx[di], true[di], rtol=1e-12)
