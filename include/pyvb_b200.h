@@ -293,9 +293,11 @@ int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X,
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
  * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.
  * bench.py times it with CUDA events to obtain the FP64 tensor roofline of the box it runs on. */
-/* Measurement: `iters` x 2 back-to-back tcgen05.mma (M = 128, N = n, 32 bytes of K each; kind 0 = i8, 1 = bf16) on fixed
- * shared-memory operands per CTA; clk_out[block] = SM clocks from the first issue to the completion of the last. */
-int pyvb_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, void *stream);
+/* Measurement: `iters` x 2 back-to-back tcgen05.mma (M = 128, N = n, 32 bytes of K each; kind 0 = i8, 1 = bf16) per CTA;
+ * clk_out[block] = SM clocks from the first issue to the completion of the last (clk_out: 2 x 148 entries).
+ * mode bits: 1 rotate through four operand buffers, 2 commit to an mbarrier after every pair, 4 a second warp streams
+ * 14 KB bulk copies from src (blocks MiB) into shared memory meanwhile. */
+int pyvb_bench_umma(int blocks, int iters, int n, int kind, int mode, const void *src, long long *clk_out, void *stream);
 int pyvb_bench_dmma_f64(int blocks, int iters, double *scratch /* blocks*256 doubles */, void *stream);
 
 #ifdef __cplusplus

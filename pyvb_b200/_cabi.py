@@ -79,7 +79,7 @@ SIGNATURES = {
     "pyvb_global_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp,
                                 ctypes.POINTER(Consts), c_dp, c_dp]),
     "pyvb_bench_dmma_f64": (c_int, [c_int, c_int, c_dp, c_dp]),
-    "pyvb_bench_umma": (c_int, [c_int, c_int, c_int, c_int, c_dp, c_dp]),
+    "pyvb_bench_umma": (c_int, [c_int, c_int, c_int, c_int, c_int, c_dp, c_dp, c_dp]),
     "pyvb_impute_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),
 }
 

@@ -458,9 +458,11 @@ int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X,
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "lds_iterate");
 }
 
-int pyvb_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, void *stream) {
-    ARG(blocks >= 1 && iters >= 1 && n >= 16 && n <= 256 && (n % 16) == 0 && (kind == 0 || kind == 1) && clk_out, "arguments");
-    cudaError_t e = launch_bench_umma(blocks, iters, n, kind, clk_out, (cudaStream_t)stream);
+int pyvb_bench_umma(int blocks, int iters, int n, int kind, int mode, const void *src, long long *clk_out, void *stream) {
+    ARG(blocks >= 1 && blocks <= 148 && iters >= 1 && n >= 16 && n <= 256 && (n % 16) == 0 && (kind == 0 || kind == 1) && clk_out,
+        "arguments");
+    ARG(!(mode & 4) || src, "mode 4 needs a source buffer of blocks MiB");
+    cudaError_t e = launch_bench_umma(blocks, iters, n, kind, mode, src, clk_out, (cudaStream_t)stream);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "bench_umma");
 }
 

@@ -126,6 +126,7 @@ cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, doub
                                double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st);
 
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
-cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, cudaStream_t st);
+cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, int mode, const void *src, long long *clk_out,
+                              cudaStream_t st);
 
 }  // namespace pyvb

@@ -329,14 +329,14 @@ zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, c
         mbar_wait(&empty[s], ph ^ 1);
         if (!T::TILED || ETA) {
             // ETA: Gw is the compact [wbar (Q) | mu | pad] array with row pitch GP (pack_weta_kernel): the chunk is one copy
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::GS_B));
                 tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);   // rows past N: zero fill
                 bulk_g2s(gs_base + s * T::GS_B, Gw + (size_t)kc * T::KC * (ETA ? T::GP : T::LDG), T::GS_B, &full[s]);
             }
         } else {
             // one Gw row segment per lane (+ the mu pair for the tile that holds the eta columns)
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(T::XT_B + T::KC * (ngt * 64 + (need_mu ? 16 : 0))));
                 tma_load_2d(xs_base + s * T::XT_B, &tmX, kc * T::KC, (int)row0, &full[s]);
             }
@@ -857,7 +857,7 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const long long nb = r0 + (long long)it * T::KC;     // chunk boundaries are multiples of KC; rows >= N are
         double *vs = reinterpret_cast<double *>(vs_base + s * T::VS_B);   // zero filled by the tensor copies
         if (T::BTILE) {
-            if (lane == 0) {
+            if (elect_one()) {        // (not `lane == 0`: that wraps every TMA instruction in an election loop)
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(nsub * T::SUB_B + T::VS_B));
                 for (int t = 0; t < nsub; ++t)
                     tma_load_2d(as_base + s * T::AS_B + t * T::SUB_B, &tmX, d0 + t * 16, (int)nb, &full[s]);
@@ -869,7 +869,7 @@ stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             for (int r = nval; r < T::KC; ++r)
                 for (int c = lane; c < T::VPS; c += 32) vs[r * T::VPS + c] = 0.0;
             __syncwarp();
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&full[s], (uint32_t)(nsub * T::SUB_B + nval * wcols * 8));
                 for (int t = 0; t < nsub; ++t)
                     tma_load_2d(as_base + s * T::AS_B + t * T::SUB_B, &tmX, d0 + t * 16, (int)nb, &full[s]);

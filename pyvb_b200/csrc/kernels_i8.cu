@@ -307,68 +307,75 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem = *tbase;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int rl = 0; rl < niter; ++rl) {
-                const int rb = (int)blockIdx.x + rl * (int)gridDim.x;
-                for (int ci = 0; ci < G.NCT; ++ci) {
-                    const int ct = (ci + ct0 < G.NCT) ? ci + ct0 : ci + ct0 - G.NCT;
-                    for (int ki = 0; ki < nk; ++ki) {
-                        const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
-                        if (ci == 0) {      // the mask chunk of the previous row block has been consumed by its last column tile
-                            PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[kb], (uint32_t)((rl & 1) ^ 1)));
+        // ===================== TMA producer (whole warp, one elected lane issues) =====================
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int rl = 0; rl < niter; ++rl) {
+            const int rb = (int)blockIdx.x + rl * (int)gridDim.x;
+            for (int ci = 0; ci < G.NCT; ++ci) {
+                const int ct = (ci + ct0 < G.NCT) ? ci + ct0 : ci + ct0 - G.NCT;
+                for (int ki = 0; ki < nk; ++ki) {
+                    const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
+                    if (ci == 0) {      // the mask chunk of the previous row block has been consumed by its last column tile
+                        PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[kb], (uint32_t)((rl & 1) ^ 1)));
+                        if (leader) {
                             mbar_arrive_expect_tx(&afull[kb], (uint32_t)A_B);
                             tma_load_3d_i8(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, &afull[kb]);   // past the end: zero fill
                         }
-                        PROF_WAIT(w0, umma::mbar_wait_bounded(&empty[s], ph ^ 1));
+                    }
+                    PROF_WAIT(w0, umma::mbar_wait_bounded(&empty[s], ph ^ 1));
+                    if (leader) {
                         mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
                         if (CL == 1)
                             tma_load_3d_i8(b_base + s * B_B, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT), 0, &full[s]);   // 7 planes x 32 columns
-                        else                                                                                   // this CTA's slice, to everybody
+                        else                                                                               // this CTA's slice, to everybody
                             tma_load_3d_i8_mc(b_base + s * B_B + crank * (B_B / CL), &tmB, 0,
                                               (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / CL), 0, &full[s], CMASK);
-                        if (++s == nst) {
-                            s = 0;
-                            ph ^= 1;
-                        }
+                    }
+                    __syncwarp();
+                    if (++s == nst) {
+                        s = 0;
+                        ph ^= 1;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
-            int s = 0, tl = 0;
-            uint32_t ph = 0;
-            for (int rl = 0; rl < niter; ++rl) {
-                for (int ci = 0; ci < G.NCT; ++ci, ++tl) {
-                    const int buf = tl & 1;
-                    PROF_WAIT(w1, umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1)));
+        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+        const bool leader = elect_one();
+        const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
+        // descriptors: the start-address field counts 16-byte units, so stage / chunk / K-step offsets are plain adds
+        const uint64_t adesc0 = umma::desc_kmajor_sw64(smem_u32(a_base), 0), bdesc0 = umma::desc_kmajor_sw64(smem_u32(b_base), 0);
+        int s = 0, tl = 0;
+        uint32_t ph = 0;
+        for (int rl = 0; rl < niter; ++rl) {
+            for (int ci = 0; ci < G.NCT; ++ci, ++tl) {
+                const int buf = tl & 1;
+                PROF_WAIT(w1, umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1)));
+                umma::fence_after_sync();
+                const uint32_t dacc = tmem + (uint32_t)(buf * 256);
+                for (int ki = 0; ki < nk; ++ki) {
+                    const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
+                    if (ci == 0) PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[kb], (uint32_t)(rl & 1)));
+                    PROF_WAIT(w0, umma::mbar_wait_bounded(&full[s], ph));
                     umma::fence_after_sync();
-                    const uint32_t dacc = tmem + (uint32_t)(buf * 256);
-                    for (int ki = 0; ki < nk; ++ki) {
-                        const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
-                        if (ci == 0) PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[kb], (uint32_t)(rl & 1)));
-                        PROF_WAIT(w0, umma::mbar_wait_bounded(&full[s], ph));
-                        umma::fence_after_sync();
-                        const uint32_t a0 = smem_u32(a_base + (size_t)kb * A_B), b0 = smem_u32(b_base + s * B_B);
-#pragma unroll
-                        for (int ks = 0; ks < BKB / 32; ++ks)
-                            umma::mma_i8(dacc, umma::desc_kmajor_sw64(a0, ks), umma::desc_kmajor_sw64(b0, ks), idesc,
-                                         (ki | ks) ? 1u : 0u);
+                    if (leader) {
+                        const uint64_t ad = adesc0 + (uint64_t)(kb * (A_B >> 4)), bd = bdesc0 + (uint64_t)(s * (B_B >> 4));
+                        umma::mma_i8(dacc, ad, bd, idesc, ki ? 1u : 0u);
+                        umma::mma_i8(dacc, ad + 2, bd + 2, idesc, 1u);
                         if (CL == 1) umma::mma_commit(&empty[s]);
                         else mma_commit_mc(&empty[s], CMASK);
                         if (ci == G.NCT - 1) umma::mma_commit(&aempty[kb]);
-                        if (++s == nst) {
-                            s = 0;
-                            ph ^= 1;
-                        }
                     }
-                    umma::mma_commit(&tfull[buf]);
+                    __syncwarp();
+                    if (++s == nst) {
+                        s = 0;
+                        ph ^= 1;
+                    }
                 }
+                if (leader) umma::mma_commit(&tfull[buf]);
+                __syncwarp();
             }
         }
     } else {
@@ -434,7 +441,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (lane == 0) bulk_wait_read_all();
     }
 #undef PROF_WAIT
-    if (prof && lane == 0 && warp < 3) {   // [producer: empty, aempty, -][MMA: full, tempty, afull][epilogue warp 2: tfull, store-read, -][total]
+    if (prof && lane == 0 && warp < 3) {    // (all lanes of a role wait together: lane 0's clocks are the role's)   // [producer: empty, aempty, -][MMA: full, tempty, afull][epilogue warp 2: tfull, store-read, -][total]
         long long *o = prof + (size_t)blockIdx.x * 10 + warp * 3;
         o[0] = w0;
         o[1] = w1;
@@ -683,15 +690,17 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            int it = 0;
-            for (int item = cid; item < nitems; item += ncl) {
-                int chunk, db, ct, nsteps;
-                long long r0;
-                item_geom(item, chunk, db, ct, r0, nsteps);
-                for (int k = 0; k < nsteps; ++k, ++it) {
-                    const int s = it % SST;
-                    umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / SST) & 1) ^ 1));
+        // TMA producer: whole warp, one elected lane issues (see elect_one)
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int item = cid; item < nitems; item += ncl) {
+            int chunk, db, ct, nsteps;
+            long long r0;
+            item_geom(item, chunk, db, ct, r0, nsteps);
+            for (int k = 0; k < nsteps; ++k) {
+                umma::mbar_wait_bounded(&empty[s], ph ^ 1);
+                if (leader) {
                     unsigned char *st = st_base + (size_t)s * (A_B + B_B);
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
                     const long long kb = r0 / BKB + k;
@@ -702,34 +711,46 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tma_load_3d_i8_mc(st + A_B + crank * (B_B / CL), &tmB, 0,
                                           (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / CL)), 0, &full[s], CMASK);
                 }
+                __syncwarp();
+                if (++s == SST) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
-            int it = 0, tl = 0;
-            for (int item = cid; item < nitems; item += ncl, ++tl) {
-                int chunk, db, ct, nsteps;
-                long long r0;
-                item_geom(item, chunk, db, ct, r0, nsteps);
-                const int buf = tl & 1;
-                umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));
+        // MMA issuer: whole warp, one elected lane issues
+        const bool leader = elect_one();
+        const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
+        const uint64_t adesc0 = umma::desc_kmajor_sw64(smem_u32(st_base), 0), bdesc0 = umma::desc_kmajor_sw64(smem_u32(st_base + A_B), 0);
+        int s = 0, tl = 0;
+        uint32_t ph = 0;
+        for (int item = cid; item < nitems; item += ncl, ++tl) {
+            int chunk, db, ct, nsteps;
+            long long r0;
+            item_geom(item, chunk, db, ct, r0, nsteps);
+            const int buf = tl & 1;
+            umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));
+            umma::fence_after_sync();
+            const uint32_t dacc = tmem + (uint32_t)(buf * 256);
+            for (int k = 0; k < nsteps; ++k) {
+                umma::mbar_wait_bounded(&full[s], ph);
                 umma::fence_after_sync();
-                const uint32_t dacc = tmem + (uint32_t)(buf * 256);
-                for (int k = 0; k < nsteps; ++k, ++it) {
-                    const int s = it % SST;
-                    umma::mbar_wait_bounded(&full[s], (uint32_t)((it / SST) & 1));
-                    umma::fence_after_sync();
-                    const uint32_t a0 = smem_u32(st_base + (size_t)s * (A_B + B_B));
-#pragma unroll
-                    for (int ks = 0; ks < BKB / 32; ++ks)
-                        umma::mma_i8(dacc, umma::desc_kmajor_sw64(a0, ks), umma::desc_kmajor_sw64(a0 + A_B, ks), idesc,
-                                     (k | ks) ? 1u : 0u);
+                if (leader) {
+                    const uint64_t off = (uint64_t)(s * ((A_B + B_B) >> 4));
+                    umma::mma_i8(dacc, adesc0 + off, bdesc0 + off, idesc, k ? 1u : 0u);
+                    umma::mma_i8(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
                     if (CL == 1) umma::mma_commit(&empty[s]);
                     else mma_commit_mc(&empty[s], CMASK);
                 }
-                umma::mma_commit(&tfull[buf]);
+                __syncwarp();
+                if (++s == SST) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
+            if (leader) umma::mma_commit(&tfull[buf]);
+            __syncwarp();
         }
     } else {
         const StatLayout L(D, q);
@@ -782,14 +803,23 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // ---- microbenchmark: back-to-back tcgen05.mma on fixed shared-memory operands (no loads): the tensor-core rate of the
 // box for kind::i8 (kind = 0) or kind::f16 / bf16 (kind = 1) at M = 128, N = n, one K step of 32 bytes per instruction.
-__global__ void __launch_bounds__(128, 1) bench_umma_kernel(int iters, int n, int kind, long long *clk_out) {
+// mode bits: 1 = rotate through 4 operand stage buffers, 2 = tcgen05.commit to an mbarrier after every pair of MMAs,
+//            4 = warp 1 streams 14 KB bulk copies from global memory into other shared-memory buffers meanwhile
+__global__ void __launch_bounds__(128, 1) bench_umma_kernel(int iters, int n, int kind, int mode, const unsigned char *src,
+                                                           long long *clk_out) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
-    __shared__ uint64_t bar;
+    constexpr int STG = A_B + 256 * BKB;                    // 24 KB per stage
+    __shared__ uint64_t bar, cbar[4], lbar[2];
     __shared__ uint32_t tb;
-    for (int i = threadIdx.x; i < (A_B + 256 * BKB) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+    __shared__ int stop;
+    for (int i = threadIdx.x; i < 4 * STG / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&cbar[i], 1);
+        mbar_init(&lbar[0], 1);
+        mbar_init(&lbar[1], 1);
+        stop = 0;
         mbar_fence_init();
     }
     if (threadIdx.x < 32) umma::tmem_alloc(&tb, 512);
@@ -799,11 +829,11 @@ __global__ void __launch_bounds__(128, 1) bench_umma_kernel(int iters, int n, in
     umma::fence_after_sync();
     const uint32_t tmem = tb;
     if (threadIdx.x == 0) {
-        const uint32_t a0 = smem_u32(smem), b0 = a0 + A_B;
         const uint32_t idesc = kind == 0 ? umma::idesc_s8_s32(BM, n) : umma::idesc_bf16_f32(BM, n, 0, 0);
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
             const uint32_t d = tmem + (uint32_t)((it & 1) * 256);
+            const uint32_t a0 = smem_u32(smem) + ((mode & 1) ? (uint32_t)((it & 3) * STG) : 0u), b0 = a0 + A_B;
             if (kind == 0) {
                 umma::mma_i8(d, umma::desc_kmajor_sw64(a0, 0), umma::desc_kmajor_sw64(b0, 0), idesc, 1u);
                 umma::mma_i8(d, umma::desc_kmajor_sw64(a0, 1), umma::desc_kmajor_sw64(b0, 1), idesc, 1u);
@@ -811,10 +841,33 @@ __global__ void __launch_bounds__(128, 1) bench_umma_kernel(int iters, int n, in
                 umma::mma_bf16(d, umma::desc_kmajor_sw64(a0, 0), umma::desc_kmajor_sw64(b0, 0), idesc, 1u);
                 umma::mma_bf16(d, umma::desc_kmajor_sw64(a0, 1), umma::desc_kmajor_sw64(b0, 1), idesc, 1u);
             }
+            if (mode & 2) umma::mma_commit(&cbar[it & 3]);
         }
         umma::mma_commit(&bar);
         umma::mbar_wait_bounded(&bar, 0);
         clk_out[blockIdx.x] = clock64() - t0;
+        *reinterpret_cast<volatile int *>(&stop) = 1;
+    } else if (threadIdx.x == 32 && (mode & 4)) {
+        // background fill traffic: 14 KB copies, two in flight, into a scratch area behind the operand stages
+        unsigned char *dst = smem + 4 * STG;
+        uint32_t ph[2] = {0, 0};
+        int k = 0;
+        const unsigned char *g = src + (size_t)blockIdx.x * (1 << 20);
+        mbar_arrive_expect_tx(&lbar[0], B_B);
+        bulk_g2s(dst, g, B_B, &lbar[0]);
+        mbar_arrive_expect_tx(&lbar[1], B_B);
+        bulk_g2s(dst + B_B, g + B_B, B_B, &lbar[1]);
+        while (!*reinterpret_cast<volatile int *>(&stop)) {
+            const int b = k & 1;
+            umma::mbar_wait_bounded(&lbar[b], ph[b]);
+            ph[b] ^= 1;
+            ++k;
+            mbar_arrive_expect_tx(&lbar[b], B_B);
+            bulk_g2s(dst + b * B_B, g + (size_t)((k * B_B) & ((1 << 20) - 32768)), B_B, &lbar[b]);
+        }
+        umma::mbar_wait_bounded(&lbar[0], ph[0]);
+        umma::mbar_wait_bounded(&lbar[1], ph[1]);
+        clk_out[148 + blockIdx.x] = k;
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -823,11 +876,12 @@ __global__ void __launch_bounds__(128, 1) bench_umma_kernel(int iters, int n, in
 
 }  // namespace
 
-cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, long long *clk_out, cudaStream_t st) {
-    const size_t smem = 1024 + A_B + 256 * BKB;
+cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, int mode, const void *src, long long *clk_out,
+                              cudaStream_t st) {
+    const size_t smem = 1024 + 4 * (A_B + 256 * BKB) + 2 * B_B;
     cudaError_t e = cudaFuncSetAttribute(bench_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bench_umma_kernel<<<blocks, 128, smem, st>>>(iters, n, kind, clk_out);
+    bench_umma_kernel<<<blocks, 128, smem, st>>>(iters, n, kind, mode, static_cast<const unsigned char *>(src), clk_out);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,16 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // make generic-proxy shared-memory writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// One lane of the (converged) warp.  The producer and MMA warps run their loops with ALL lanes (uniform control flow, so
+// that addresses and descriptors live in uniform registers) and only issue under this predicate: a loop entered by
+// `lane == 0` alone made the compiler wrap every TMA / tcgen05 instruction in an election loop with register ->
+// uniform-register moves, ~20 dependent instructions (~100 clocks of a single lane) per MMA -- slower than the MMA itself.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
