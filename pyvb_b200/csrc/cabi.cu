@@ -1,5 +1,6 @@
 // extern "C" boundary of libpyvb_b200.so -- see include/pyvb_b200.h for the contract.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +24,31 @@ static int cuda_fail(cudaError_t e, const char *where) {
     } while (0)
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Helper stream of the INT8 path: the FP64-tensor kernels on X (eta, Ast) are independent of the INT8 kernels on the mask and
+// bound by different units, so they can run next to them (fork / join with two events around the pair).  Created on first
+// use, one per device.  OFF unless PYVB_I8_OVERLAP=1: measured, the pairs do not overlap in practice (C2: 0.824 vs 0.838 ms for
+// the K1 pair, the sweep unchanged) and the fork / join slows the chunked end-to-end path down.
+struct AuxStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int state = 0;   // 0 not tried, 1 ready, -1 unavailable
+};
+static AuxStream *aux_stream() {
+    static AuxStream aux[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    AuxStream &a = aux[dev];
+    if (a.state == 0) {
+        const char *e = getenv("PYVB_I8_OVERLAP");
+        a.state = -1;
+        if ((e && e[0] == '1') && cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess)
+            a.state = 1;
+    }
+    return a.state == 1 ? &a : nullptr;
+}
 
 static int pick_algo(int algo, int D, int q) {
     if (algo == PYVB_ALGO_AUTO) return dmma_supported(D, q) ? PYVB_ALGO_DMMA : PYVB_ALGO_GENERIC;
@@ -288,13 +314,26 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     cudaStream_t st = (cudaStream_t)stream;
     // k1_only: 0 whole Z step, 1 contraction only (INT8 qprec + DMMA eta), 2 INT8 part only, 3 eta part only
     cudaError_t e = cudaSuccess;
-    if (k1_only != 3) {
+    AuxStream *aux = (k1_only < 2) ? aux_stream() : nullptr;     // both parts wanted: the eta kernel runs next to the INT8 kernel
+    cudaStream_t st2 = st;
+    if (aux) {
+        e = cudaEventRecord(aux->fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s, aux->fork, 0);
+        if (e != cudaSuccess) return cuda_fail(e, "zstep_i8 (fork)");
+        st2 = aux->s;
+    }
+    if (k1_only != 3) {      // first: its CTAs take one slot per SM, the eta kernel's CTAs fill what is left
         e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, st);
         if (e == cudaSuccess) e = launch_zstep_i8(N, D, q, mask, GI, P0, gscale, gl, MZ, (int)ldmz, st);
     }
     if (e == cudaSuccess && k1_only != 2) {
         double *weta = (double *)((char *)GI + align256(i8_digits_bytes(D, q)));
-        e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, weta, P0, h0, gl, MZ, st);
+        e = launch_zstep_eta_dmma(N, D, q, X, ldx, Gw, weta, P0, h0, gl, MZ, st2);
+    }
+    if (aux) {
+        cudaError_t e2 = cudaEventRecord(aux->join, aux->s);
+        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, aux->join, 0);
+        if (e == cudaSuccess) e = e2;
     }
     if (e == cudaSuccess && !k1_only) e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_i8");
@@ -349,9 +388,23 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     const int nch = stats_i8_nchunks(N, D, q);
     // the default K2 kernels leave bounds on the column maxima behind their column sums: [sums OROW | 4 | maxima OROW]
     const bool kmax = nzblk > 0 && (k2_impl(q) == 1 || k2_impl(q) == 2);
-    cudaError_t e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch,
-                                    kmax ? zsums + (gw_woff(q) + q + PYVB_ZS_EXTRA) : NULL, nzblk, zkw, st);
-    if (e == cudaSuccess) e = launch_stats_x_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st);
+    AuxStream *aux = aux_stream();                              // Ast (FP64 tensor cores on X) next to digitize + the INT8 kernel
+    cudaStream_t st2 = st;
+    cudaError_t e = cudaSuccess;
+    if (aux) {
+        e = cudaEventRecord(aux->fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(aux->s, aux->fork, 0);
+        if (e != cudaSuccess) return cuda_fail(e, "stats_i8 (fork)");
+        st2 = aux->s;
+    }
+    e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch,
+                        kmax ? zsums + (gw_woff(q) + q + PYVB_ZS_EXTRA) : NULL, nzblk, zkw, st);
+    if (e == cudaSuccess) e = launch_stats_x_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st2);
+    if (aux) {
+        cudaError_t e2 = cudaEventRecord(aux->join, aux->s);
+        if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, aux->join, 0);
+        if (e == cudaSuccess) e = e2;
+    }
     double *ws_sc = NULL;
     const int nblk = rowscalars_nblk(N);
     if (e == cudaSuccess && nzblk == 0) {        // no K2 partials (q = 64): the MZ column sums and the per-row scalars take a pass

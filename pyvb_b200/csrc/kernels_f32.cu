@@ -196,8 +196,10 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem = *tbase;
 
     if (warp == 0) {
-        // ===================== TMA producer (one lane) =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp in uniform control flow, one elected lane issues: a loop
+        // entered by lane 0 alone makes the compiler wrap every TMA / tcgen05 instruction in an election loop) ==========
+        const bool leader = elect_one();
+        {
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int ct = tile % T::NCT;
@@ -207,6 +209,7 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int s = it % T::ST;
                     umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / T::ST) & 1) ^ 1));
                     unsigned char *st = stage0 + s * T::STAGE_B;
+                    if (leader) {
                     mbar_arrive_expect_tx(&full[s], (uint32_t)(T::A_B + 3 * T::G_B + (eta ? 2 * T::A_B + 3 * T::W_B : 0)));
                     tma_load_3d(st, &tmA, kb * T::BK, row0, 0, &full[s]);                 // mask
                     for (int p = 0; p < 3; ++p)
@@ -217,12 +220,15 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int p = 0; p < 3; ++p)
                             tma_load_3d(st + 3 * T::A_B + 3 * T::G_B + p * T::W_B, &tmW, kb * T::BK, 0, p, &full[s]);
                     }
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one lane) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
+        const bool leader = elect_one();
+        {
             int it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
                 const int ct = tile % T::NCT;
@@ -241,6 +247,7 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     umma::fence_after_sync();
                     const uint32_t a0 = smem_u32(stage0 + s * T::STAGE_B);
                     const uint32_t g0 = a0 + 3 * T::A_B, w0 = g0 + 3 * T::G_B;
+                    if (leader) {
 #pragma unroll
                     for (int ks = 0; ks < T::BK / 16; ++ks) {
 #pragma unroll
@@ -258,8 +265,11 @@ zstep_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                     umma::mma_commit(&empty[s]);               // the stage is free once these MMAs have read it
+                    }
+                    __syncwarp();
                 }
-                umma::mma_commit(&tfull[buf]);                 // accumulator complete
+                if (leader) umma::mma_commit(&tfull[buf]);     // accumulator complete
+                __syncwarp();
             }
         }
     } else {
@@ -395,12 +405,14 @@ stats_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem = *tbase;
 
     if (warp == 0) {
-        if (lane == 0) {
+        const bool leader = elect_one();                   // whole warp, one elected lane issues (see zstep_f32_kernel)
+        {
             for (int it = 0; it < nsteps; ++it) {
                 const int s = it % T::ST;
                 umma::mbar_wait_bounded(&empty[s], (uint32_t)(((it / T::ST) & 1) ^ 1));
                 unsigned char *st = stage0 + s * T::STAGE_B;
                 const int nb = (int)(r0 + (long long)it * T::BKN);       // rows >= N are zero-filled by the copies
+                if (leader) {
                 mbar_arrive_expect_tx(&full[s], (uint32_t)((xt ? 3 : 1) * T::A_B + 3 * (nt / 64) * T::BLK_B));
                 for (int p = 0; p < (xt ? 3 : 1); ++p)
                     for (int j = 0; j < 2; ++j)
@@ -408,10 +420,13 @@ stats_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int p = 0; p < 3; ++p)
                     for (int j = 0; j < nt / 64; ++j)
                         tma_load_3d(st + 3 * T::A_B + p * T::B_B + j * T::BLK_B, &tmB, c0 + j * 64, nb, p, &full[s]);
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        const bool leader = elect_one();
+        {
             const uint32_t id_t = umma::idesc_bf16_f32(T::BD, nt, 1, 1);
             const uint32_t id_x = umma::idesc_bf16_f32(T::BD, 64, 1, 1);
             const uint32_t dT = tmem, dX = tmem + (uint32_t)T::NT;
@@ -421,6 +436,7 @@ stats_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma::fence_after_sync();
                 const uint32_t a0 = smem_u32(stage0 + s * T::STAGE_B);
                 const uint32_t b0 = a0 + 3 * T::A_B;
+                if (leader) {
 #pragma unroll
                 for (int ks = 0; ks < T::BKN / 16; ++ks) {
                     const uint64_t am = umma::desc_mnmajor_sw128(a0, ks, T::BLK_B);
@@ -442,8 +458,11 @@ stats_f32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 }
                 umma::mma_commit(&empty[s]);
+                }
+                __syncwarp();
             }
-            umma::mma_commit(&tfull[0]);
+            if (leader) umma::mma_commit(&tfull[0]);
+            __syncwarp();
         }
     } else {
         // ===================== epilogue: lane = data dimension d, columns -> T1 / Bst / Ast partials (FP64) ==========

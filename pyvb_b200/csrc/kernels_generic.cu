@@ -601,9 +601,15 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
               const double *__restrict__ P0, const double *__restrict__ h0, const pyvb_consts c,
               double *elbo_out) {
     __shared__ double sh[33];
+    __shared__ unsigned short ijtab[PYVB_QMAX * (PYVB_QMAX + 1) / 2];   // packed index -> (i << 8) | j
     const StatLayout L(D, q);
     const int P = L.P;
     const int tid = threadIdx.x, nt = blockDim.x;
+    for (int p = tid; p < P; p += nt) {
+        int i, j;
+        unpack_p(p, i, j);
+        ijtab[p] = (unsigned short)((i << 8) | j);
+    }
     const double *T1 = stats + L.t1, *Bst = stats + L.bst, *Ast = stats + L.ast;
     const double *cnt = stats + L.cnt, *colx = stats + L.colx, *S = stats + L.S, *zsum = stats + L.zsum;
     const double *sc = stats + L.scal;
@@ -652,14 +658,24 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
             const double m = mu[d];
             part += -2.0 * (s1 + m * colx[d]) + 2.0 * m * s2 + cnt[d] * (m * m + muvar[d]);
         }
-        for (long long idx = tid; idx < (long long)D * P; idx += nt) {
-            const int d = (int)(idx / P), p = (int)(idx % P);
-            int i, j;
-            unpack_p(p, i, j);
-            double g = Wbar[(size_t)d * q + i] * Wbar[(size_t)d * q + j];
-            if (i == j) g += Wvar[(size_t)d * q + i];
-            else g *= 2.0;
-            part = fma(g, T1[idx], part);
+        // (d, p) advance incrementally and (i, j) come from a table: a 64-bit division and a square root per element made
+        //  this loop 0.5 ms at D = 1024, q = 32)
+        {
+            int d = tid / P, pp = tid - (tid / P) * P;
+            const int dstep = nt / P, pstep = nt - (nt / P) * P;
+            for (long long idx = tid; idx < (long long)D * P; idx += nt) {
+                const int ij = ijtab[pp], i = ij >> 8, j = ij & 255;
+                double g = Wbar[(size_t)d * q + i] * Wbar[(size_t)d * q + j];
+                if (i == j) g += Wvar[(size_t)d * q + i];
+                else g *= 2.0;
+                part = fma(g, T1[idx], part);
+                d += dstep;
+                pp += pstep;
+                if (pp >= P) {
+                    pp -= P;
+                    ++d;
+                }
+            }
         }
         resid2 = block_sum(part, sh) + sc[PYVB_SC_SXX] + sc[PYVB_SC_SUMV];
         if (ops & PYVB_OP_BETA) {

@@ -35,7 +35,7 @@ namespace {
 __host__ __device__ constexpr int i_tri(int i) { return i * (i + 1) / 2; }
 __host__ __device__ constexpr int i_nc8(int q) { return (i_tri(q) + 31) & ~31; }          // packed columns rounded to 32
 constexpr int NPL = 7;                                                                    // digit planes
-constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, digit stages, columns per tile
+constexpr int BM = 128, BKB = 64, ST = 4, CT = 32;       // (ST: more stages measured no gain and leave no room for the eta kernel next to it)       // rows per tile, K bytes per chunk, digit stages, columns per tile
 constexpr int A_B = BM * BKB, B_B = NPL * CT * BKB;      // 8192, 14336
 constexpr int NTHR = 10 * 32;
 

@@ -380,7 +380,7 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
                     row[IO::POFF + e] = (io_t)v;
                     if (F32) split3_store(MP + (n0 + m) * IO::PITCH + IO::POFF + e, (size_t)N * IO::PITCH, (float)v);
                     cs[u] += v;
-                    cm[u] = max(cm[u], __double2hiint(v) & 0x7fffffff);
+                    if (!F32) cm[u] = max(cm[u], __double2hiint(v) & 0x7fffffff);
                 }
             }
             if (lane < Q) {
@@ -388,7 +388,7 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
                 row[IO::ZOFF + lane] = (io_t)v;
                 if (F32) split3_store(MP + (n0 + m) * IO::PITCH + IO::ZOFF + lane, (size_t)N * IO::PITCH, (float)v);
                 cz += v;
-                czm = max(czm, __double2hiint(v) & 0x7fffffff);
+                if (!F32) czm = max(czm, __double2hiint(v) & 0x7fffffff);
             }
         }
         __syncwarp();
