@@ -35,7 +35,7 @@ namespace {
 __host__ __device__ constexpr int i_tri(int i) { return i * (i + 1) / 2; }
 __host__ __device__ constexpr int i_nc8(int q) { return (i_tri(q) + 31) & ~31; }          // packed columns rounded to 32
 constexpr int NPL = 7;                                                                    // digit planes
-constexpr int BM = 128, BKB = 64, ST = 4, CT = 32;       // (ST: more stages measured no gain and leave no room for the eta kernel next to it)       // rows per tile, K bytes per chunk, digit stages, columns per tile
+constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, max digit stages, columns per tile       // rows per tile, K bytes per chunk, digit stages, columns per tile
 constexpr int A_B = BM * BKB, B_B = NPL * CT * BKB;      // 8192, 14336
 constexpr int NTHR = 10 * 32;
 
@@ -495,7 +495,7 @@ int i8_cluster_size() {                     // PYVB_I8_CLUSTER = 1 | 2 | 4 (defa
 // over the whole chunk, then recombined to FP64 and written to the chunk's partial-sum buffer (the deterministic
 // second stage, stats_reduce_kernel, adds the chunks).  Items are dealt round-robin to 148 persistent CTAs, chunk-major,
 // so that the CTAs running at the same time share their operand tiles through L2.
-constexpr int SST = 6;                                   // stages of the K3-i8 ring (22 KB each)
+constexpr int SST = 9;                                   // stages of the K3-i8 ring (22 KB each)
 constexpr int CM_BLOCKS = 148 * 4;                       // partial column maxima
 
 // column maxima of |MZ| over a block of rows: pm[blk][ldmz].  Warp per row, lane l owns the columns l, l + 32, ...
@@ -559,16 +559,19 @@ digitize_kernel(long long N, long long npad, int ldmz, int nvalid, const double 
     // v + sum_t 128 256^t has the unsigned bytes (digit_t + 128); flipping bit 7 of every byte gives the signed digits.
     // A warp takes 16 consecutive rows, four at a time: one 32-bit shared-memory store per plane and four rows.
     constexpr unsigned long long BIAS = 0x0080808080808080ULL;
+    double xv[16];                                           // all 16 loads of this thread in flight before the first use
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const long long n = n0 + warp * 16 + k;
+        xv[k] = (cv && n < N) ? MZ[n * ldmz + c] : 0.0;
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const int r = warp * 16 + g * 4;
         unsigned int lo[4], hi[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const long long n = n0 + r + k;
-            double x = 0.0;
-            if (cv && n < N) x = MZ[n * ldmz + c];
-            double t = x * inv;
+            double t = xv[g * 4 + k] * inv;
             t = (fabs(t) <= 18014398509481984.0) ? t : 0.0;  // NaN / inf (a non-PD row, reported separately) -> 0
             const unsigned long long u = ((unsigned long long)__double2ll_rn(t) + BIAS) ^ BIAS;
             lo[k] = (unsigned int)u;
