@@ -169,6 +169,12 @@ class PlateEngine(object):
         assert self.L.len == int(self.lib.pyvb_stats_len(D, q))
         self.ws_bytes = int(self.lib.pyvb_stats_workspace_bytes(N, D, q, ALGO_F32 if self.f32 else self.algo))
         if self.use_i8_stats:
+            # the digit planes cost 7 bytes per MZ entry: when they would take more than 40 % of the free memory (config 4
+            # at full size on one GPU) the statistics stay on the FP64 tensor cores
+            need = int(self.lib.pyvb_stats_i8_digits_bytes(N, q)) + int(self.lib.pyvb_stats_i8_maskt_bytes(N, D))
+            if need > 0.4 * torch.cuda.mem_get_info(dev)[0]:
+                self.use_i8_stats = False
+        if self.use_i8_stats:
             try:
                 self.npad = int(self.lib.pyvb_stats_i8_npad(N))
                 self.maskT = torch.empty(int(self.lib.pyvb_stats_i8_maskt_bytes(N, D)), dtype=torch.int8, device=dev)
