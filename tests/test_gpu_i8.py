@@ -111,6 +111,33 @@ def test_i8_iterations_match_oracle(eng, shape):
     e.check()
 
 
+@pytest.mark.parametrize("shape", [(129, 64, 16), (257, 128, 16), (385, 1280, 16), (130, 1024, 32), (300, 1024, 64)])
+def test_i8_edge_shapes_one_sweep(eng, shape):
+    """Odd numbers of 128-row blocks (a cluster's second CTA runs past the end), the largest supported D, tiny N."""
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.3, seed=D + N)
+    init = rand_init(N, D, q, seed=3)
+    ed, ei = eng(X, q, mode="B", algo="dmma"), eng(X, q, mode="B", algo="i8")
+    for e in (ed, ei):
+        e.set_state(init)
+        e._ensure_stats()
+    vals = [(ed.iterate(), ei.iterate()) for _ in range(2)]
+    for a, b in vals:
+        assert abs(a - b) <= 1e-10 * abs(a), (shape, vals)
+    sd, si = ed.get_state(), ei.get_state()
+    for k in ("Wbar", "mu", "Zbar", "Sig"):
+        assert tensor_rel(si[k], sd[k]) < 1e-10, (shape, k)
+    ei.check()
+
+
+def test_i8_auto_falls_back_where_the_mask_block_does_not_fit(eng):
+    X = synth_pca(300, 1280, 64, 0.2, seed=2)          # q = 64 at D = 1280: constants + mask block exceed shared memory
+    e = eng(X, 64, mode="B")
+    assert not e.use_i8
+    with pytest.raises(ValueError):
+        eng(X, 64, mode="B", algo="i8")
+
+
 def test_i8_rejects_unsupported_shape(eng):
     X = synth_pca(40, 48, 16, 0.1, seed=1)
     with pytest.raises(ValueError):
