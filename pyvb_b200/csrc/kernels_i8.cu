@@ -8,17 +8,18 @@
 // scale_c 2^-55 absolute -- finer than the FP64 spacing of the column's large entries.  Then
 //     mask @ G = scale_c 2^-54 sum_t 256^t (mask @ digit_t)
 // where every mask @ digit_t is an EXACT integer GEMM (|sum| <= 128 D << 2^31).  The seven INT32 results per output
-// are recombined in the epilogue (pairs in INT32, then three FP64 FMAs): no accumulation error at all, one rounding
-// at the end -- at least as accurate as an FP64 accumulation, at the INT8 tensor rate instead of the FP64 (DMMA) one.
+// are recombined in the epilogue (two exact 64-bit integer halves, one FP64 FMA): no accumulation error at all, one
+// rounding at the end -- at least as accurate as an FP64 accumulation, at the INT8 tensor rate instead of the FP64 one.
 // The eta columns (both operands real) stay on the DMMA kernel (ZT<Q, true> in kernels_dmma.cu).
 //
 // Tiling: CTA tile = 128 rows x 32 output columns x 7 digit planes = one tcgen05.mma with N = 224 per 32-byte K step.
 // The 128 x D mask block of a row tile stays RESIDENT in shared memory (D / 64 chunks of 128 x 64 bytes, each with its
 // own full / empty mbarrier) while the CTA walks over the column tiles; only the 14 KB digit tiles stream through a
-// 4-stage ring (they come from L2: the whole digit array is a few MB).  TMEM holds two accumulators (2 x 256 columns)
+// ring of up to 8 stages (as many as fit next to the mask block; they come from L2: the digit array is a few MB).  TMEM holds two accumulators (2 x 256 columns)
 // so that the epilogue of one tile overlaps the MMAs of the next.  Warp 0: TMA producer, warp 1: MMA issuer, warps
-// 2-9: epilogue (two warps per TMEM lane quarter, 16 columns each).  Operands are K-major TMA tiles with 64-byte rows
-// (SWIZZLE_64B), the same byte geometry as the bf16 kernels of kernels_f32.cu.
+// 2-9: epilogue (two warps per TMEM lane quarter, 16 columns each; one TMA tensor store per warp and tile).  Operands
+// are K-major TMA tiles with 64-byte rows (SWIZZLE_64B), tile-major in global memory so that every box is one
+// contiguous block.  K3-i8 (the mask-type statistics) further down uses the same machinery with the roles turned.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -35,7 +36,7 @@ namespace {
 __host__ __device__ constexpr int i_tri(int i) { return i * (i + 1) / 2; }
 __host__ __device__ constexpr int i_nc8(int q) { return (i_tri(q) + 31) & ~31; }          // packed columns rounded to 32
 constexpr int NPL = 7;                                                                    // digit planes
-constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, max digit stages, columns per tile       // rows per tile, K bytes per chunk, digit stages, columns per tile
+constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, max digit stages, columns per tile
 constexpr int A_B = BM * BKB, B_B = NPL * CT * BKB;      // 8192, 14336
 constexpr int NTHR = 10 * 32;
 
