@@ -381,6 +381,7 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     }
     ARG(X && maskT && MZ && ZI && scratch && xcache, "null pointer (xcache is required)");
     ARG(zsums || logdet, "zsums or logdet");
+    ARG(logdet || (k2_impl(q) == 1 || k2_impl(q) == 2), "logdet is needed when the K2 partials carry no column maxima");
     ARG(ldx >= D && (ldx % 2) == 0 && ldmz == pyvb_mz_pitch(q), "ldx, ldmz");
     ARG(ws_bytes >= pyvb_stats_i8_workspace_bytes(N, D, q), "workspace too small");
     int nzblk = 0, zkw = 0;
@@ -397,25 +398,19 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
         if (e != cudaSuccess) return cuda_fail(e, "stats_i8 (fork)");
         st2 = aux->s;
     }
-    e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch,
-                        kmax ? zsums + (gw_woff(q) + q + PYVB_ZS_EXTRA) : NULL, nzblk, zkw, st);
+    // K2's partials when they carry the maxima, else one pass over the MZ rows builds the same partials in `scratch`
+    const double *zs = NULL;
+    int zn = 0, zk = 0;
+    e = launch_stats_i8(N, D, q, maskT, MZ, (int)ldmz, ZI, scratch, (double *)ws, nch, zsums, nzblk, zkw, kmax ? 1 : 0, logdet,
+                        &zs, &zn, &zk, st);
     if (e == cudaSuccess) e = launch_stats_x_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st2);
     if (aux) {
         cudaError_t e2 = cudaEventRecord(aux->join, aux->s);
         if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, aux->join, 0);
         if (e == cudaSuccess) e = e2;
     }
-    double *ws_sc = NULL;
-    const int nblk = rowscalars_nblk(N);
-    if (e == cudaSuccess && nzblk == 0) {        // no K2 partials (q = 64): the MZ column sums and the per-row scalars take a pass
-        ARG(logdet, "logdet is needed without zsums");
-        ws_sc = (double *)((char *)ws + align256((size_t)nch * L.len * sizeof(double)));
-        e = launch_mzsums(N, D, q, MZ + gw_woff(q), ldmz, MZ, ldmz, (double *)ws, nch, st);
-        if (e == cudaSuccess) e = launch_rowscalars(N, D, X, ldx, NULL, NULL, NULL, logdet, ws_sc, nblk, 1, st);
-    }
     if (e != cudaSuccess) return cuda_fail(e, "stats_i8");
-    e = launch_stats_reduce(D, q, (const double *)ws, nch, ws_sc, nblk, stats, const_cast<double *>(xcache), 1,
-                            nzblk > 0 ? zsums : NULL, nzblk, zkw,
+    e = launch_stats_reduce(D, q, (const double *)ws, nch, NULL, 0, stats, const_cast<double *>(xcache), 1, zs, zn, zk,
                             peers ? peers->bufs : NULL, peers ? peers->world : 1, peers ? peers->rank : 0,
                             peers ? peers->epoch : 0ULL, st);
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "stats_reduce");

@@ -114,8 +114,8 @@ size_t stats_i8_scratch_len(int q, int ldmz);               // doubles: partial 
 int stats_i8_nchunks(long long N, int D, int q);
 cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long long ldx, void *maskT, cudaStream_t st);
 cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,
-                            double *scratch, double *ws, int nchunks, const double *zmax, int nzblk, int zkw,
-                            cudaStream_t st);
+                            double *scratch, double *ws, int nchunks, const double *zsums, int nzblk, int zkw, int trusted,
+                            const double *logdet, const double **zs_out, int *nzblk_out, int *zkw_out, cudaStream_t st);
 cudaError_t launch_stats_x_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
                                 double *ws_main, int nchunks, cudaStream_t st);
 

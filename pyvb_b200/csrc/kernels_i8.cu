@@ -533,6 +533,71 @@ colmax_kernel(long long N, int ldmz, const double *__restrict__ MZ, double *__re
     }
     for (int c = threadIdx.x; c < ldmz; c += 256) pm[(size_t)blockIdx.x * ldmz + c] = cm_sh[c];
 }
+// The partials K2 would have left for a block of rows -- [column sums (ldmz - 4) | sum 0.5/logdet, sum logdet, rows, 0 |
+// column maxima of |.| (ldmz - 4)] -- in ONE pass over the MZ rows, for the cases where K2 leaves none (q = 64, or rows
+// written from outside the kernels): replaces three passes (column sums, per-row scalars, column maxima).  A warp takes
+// a slice of 32 x 17 columns and every (8 / slices)-th row; the warps of a slice are combined in a fixed order.
+constexpr int MZP_KPL = 17;
+__global__ void __launch_bounds__(256)
+mzpart_kernel(long long N, int ldmz, const double *__restrict__ MZ, const double *__restrict__ logdet,
+              double *__restrict__ part, long long rows_per_blk) {
+    extern __shared__ double mz_sh[];                       // [sums ldmz | maxima ldmz | 4 scalars]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int orow = ldmz - 4, kw = 2 * orow + 4;
+    const int ns = (ldmz + 32 * MZP_KPL - 1) / (32 * MZP_KPL);         // column slices: 1, 2 or 4
+    const int slice = warp % ns, rg = warp / ns, nrg = 8 / ns;
+    const long long r0 = (long long)blockIdx.x * rows_per_blk;
+    long long r1 = r0 + rows_per_blk;
+    if (r1 > N) r1 = N;
+    double sm[MZP_KPL], mx[MZP_KPL], s_qld = 0.0, s_ld = 0.0, s_n = 0.0;
+#pragma unroll
+    for (int k = 0; k < MZP_KPL; ++k) sm[k] = mx[k] = 0.0;
+    const int cbase = slice * 32 * MZP_KPL + lane;
+    for (long long n = r0 + rg; n < r1; n += nrg) {
+        const double *row = MZ + n * ldmz;
+#pragma unroll
+        for (int k = 0; k < MZP_KPL; ++k) {
+            const int c = cbase + 32 * k;
+            if (c < ldmz) {
+                const double v = row[c];
+                sm[k] += v;
+                mx[k] = fmax(mx[k], fabs(v));
+            }
+        }
+        if (slice == 0 && lane == 0) {
+            const double ld = logdet[n];
+            s_qld += 0.5 / ld;
+            s_ld += ld;
+            s_n += 1.0;
+        }
+    }
+    double *ssum = mz_sh, *smax = mz_sh + ldmz, *ssc = mz_sh + 2 * ldmz;
+    for (int w = 0; w < 8; ++w) {                           // fixed order: deterministic sums
+        if (warp == w) {
+#pragma unroll
+            for (int k = 0; k < MZP_KPL; ++k) {
+                const int c = cbase + 32 * k;
+                if (c < ldmz) {
+                    ssum[c] = (rg == 0) ? sm[k] : ssum[c] + sm[k];
+                    smax[c] = (rg == 0) ? mx[k] : fmax(smax[c], mx[k]);
+                }
+            }
+            if (slice == 0 && lane == 0) {
+                ssc[0] = (rg == 0) ? s_qld : ssc[0] + s_qld;
+                ssc[1] = (rg == 0) ? s_ld : ssc[1] + s_ld;
+                ssc[2] = (rg == 0) ? s_n : ssc[2] + s_n;
+            }
+        }
+        __syncthreads();
+    }
+    double *out = part + (size_t)blockIdx.x * kw;
+    for (int c = threadIdx.x; c < orow; c += 256) {
+        out[c] = ssum[c];
+        out[orow + 4 + c] = smax[c];
+    }
+    if (threadIdx.x < 4) out[orow + threadIdx.x] = (threadIdx.x < 3) ? ssc[threadIdx.x] : 0.0;
+}
+
 // one warp per column: max over the row-block partials
 __global__ void __launch_bounds__(256)
 colmax_reduce_kernel(int ncols, int nvalid, int ldmz, const double *__restrict__ pm, int nblk, double *__restrict__ zscale) {
@@ -970,7 +1035,7 @@ int stats_i8_ncols(int q) { return (i_tri(q) + q + 31) & ~31; }
 long long stats_i8_npad(long long N) { return (N + 127) / 128 * 128; }
 size_t stats_i8_digits_bytes(long long N, int q) { return (size_t)stats_i8_ncols(q) * NPL * (size_t)stats_i8_npad(N); }
 size_t stats_i8_maskt_bytes(long long N, int D) { return (size_t)D * (size_t)stats_i8_npad(N) + (size_t)BM * BKB; }
-size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * ldmz + stats_i8_ncols(q); }
+size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * 2 * ldmz + stats_i8_ncols(q); }
 
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
 // chunks: items = ndb * nct * nchunks a whole number of rounds over 148 CTAs, chunks of >= 32 K steps, <= 2^23 rows
@@ -1004,28 +1069,32 @@ cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long lo
 }
 
 // colmax -> zscale -> digit planes of the MZ rows -> T1, Bst partial sums of every row chunk in ws[chunk][stat layout]
-// zmax (nullable): per-CTA bounds on the column maxima left by K2 next to its column sums (nzblk partials of stride zkw,
-// column c at zmax[c]); without it one more pass over the MZ rows finds the maxima
+// zsums (nullable): K2's per-CTA partials [column sums | 4 scalars | bounds on the column maxima] (nzblk partials of zkw
+// doubles).  Without them (or when `trusted` is 0: a K2 kernel that leaves no maxima) one pass over the MZ rows builds the same
+// partials in `scratch` (logdet needed); *zs_out / *nzblk_out / *zkw_out say which partials the second stage must add up.
 cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,
-                            double *scratch, double *ws, int nchunks, const double *zmax, int nzblk, int zkw,
-                            cudaStream_t st) {
+                            double *scratch, double *ws, int nchunks, const double *zsums, int nzblk, int zkw, int trusted,
+                            const double *logdet, const double **zs_out, int *nzblk_out, int *zkw_out, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
     const int P = i_tri(q), NCZ = stats_i8_ncols(q), nct = NCZ / CT, ndb = (D + BM - 1) / BM;
     const long long npad = stats_i8_npad(N);
-    double *pm = scratch, *zscale = scratch + (size_t)CM_BLOCKS * ldmz;
-    if (zmax != nullptr && nzblk > 0) {
-        colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, zkw, zmax, nzblk, zscale);
-    } else {
+    const int orow = ldmz - 4;
+    double *pm = scratch, *zscale = scratch + (size_t)CM_BLOCKS * 2 * ldmz;
+    if (!(zsums != nullptr && nzblk > 0 && trusted)) {
+        if (logdet == nullptr) return cudaErrorInvalidValue;
         int nblk = CM_BLOCKS;
         long long rpb = (N + nblk - 1) / nblk;
         if (rpb < 64) rpb = 64;
         nblk = (int)((N + rpb - 1) / rpb);
-        const size_t cms = (size_t)ldmz * sizeof(double);
-        if (q == 16) colmax_kernel<5><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-        else if (q == 32) colmax_kernel<18><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-        else colmax_kernel<68><<<nblk, 256, cms, st>>>(N, ldmz, MZ, pm, rpb);
-        colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, ldmz, pm, nblk, zscale);
+        mzpart_kernel<<<nblk, 256, (size_t)(2 * ldmz + 4) * sizeof(double), st>>>(N, ldmz, MZ, logdet, pm, rpb);
+        zsums = pm;
+        nzblk = nblk;
+        zkw = 2 * orow + 4;
     }
+    *zs_out = zsums;
+    *nzblk_out = nzblk;
+    *zkw_out = zkw;
+    colmax_reduce_kernel<<<(NCZ + 7) / 8, 256, 0, st>>>(NCZ, P + q, zkw, zsums + orow + 4, nzblk, zscale);
     dim3 gd((unsigned)((N + 127) / 128), (unsigned)nct);
     digitize_kernel<<<gd, 256, 0, st>>>(N, npad, ldmz, P + q, MZ, zscale, static_cast<signed char *>(ZI));
     cudaError_t e = cudaGetLastError();
