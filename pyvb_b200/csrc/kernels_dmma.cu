@@ -113,8 +113,9 @@ template <int Q, bool ETA = false> struct ZT {
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7, NGO = PP / 8, NGE = Q / 8, NG = NGO + NGE;
     // ETA: 2 x Q / 8 tensor-core instructions per 4 x 8 data entries -- the kernel streams X at HBM speed only with many
     // small stages in flight (8 stages, 2 CTAs per SM: > 100 KB outstanding per SM)
-    static constexpr int WM = ETA ? C::WM * C::WN : C::WM, WN = ETA ? 1 : C::WN, RGW = C::RGW, KC = C::KC;
-    static constexpr int ST = ETA ? 8 : C::ST, OCC = ETA ? 2 : C::OCC;
+    // (ETA always takes 16 data dimensions per stage: its Gw tile is tiny, and half as many barrier round trips per byte)
+    static constexpr int WM = ETA ? C::WM * C::WN : C::WM, WN = ETA ? 1 : C::WN, RGW = C::RGW, KC = ETA ? 16 : C::KC;
+    static constexpr int ST = ETA ? (Q <= 16 ? 8 : 5) : C::ST, OCC = ETA ? 2 : C::OCC;
     static constexpr int NCT = ETA ? 1 : C::NCT;
     static constexpr bool TILED = ETA || NCT > 1;
     static constexpr int CG0 = ETA ? NGO : 0;          // first column group this kernel computes
@@ -788,7 +789,7 @@ template <int Q, bool XO = false> struct STT {
     using C = SC<Q>;
     static constexpr int P = c_tri(Q), PP = (P + 7) & ~7;
     static constexpr int NGO = XO ? 0 : (PP + Q) / 8, NGX = Q / 8, NG = NGO + NGX;   // O-type: [<zz^T> | pad | zbar]; X-type: zbar
-    static constexpr int WM = XO ? C::WM * C::WN : C::WM, WN = XO ? 1 : C::WN, RGW = C::RGW, KC = C::KC, ST = XO ? 4 : C::ST;
+    static constexpr int WM = XO ? C::WM * C::WN : C::WM, WN = XO ? 1 : C::WN, RGW = C::RGW, KC = XO ? 16 : C::KC, ST = XO ? 4 : C::ST;
     static constexpr int NCT = XO ? 1 : C::NCT;
     static constexpr bool TILED = NCT > 1;      // output columns split over NCT CTAs (q = 64)
     static constexpr int NGT = (NG + NCT - 1) / NCT;
