@@ -211,15 +211,27 @@ struct I8Geom {
     }
 };
 constexpr int OUT_B = 8 * 32 * 16 * 8;                  // epilogue staging: 8 warps x (32 rows x 16 columns) doubles
-size_t i8_smem_bytes(int D, int q, int nst) {
+// hstage: the epilogue stages (and stores) 8 columns at a time: half the staging memory, one more digit stage at D = 1024
+size_t i8_smem_bytes(int D, int q, int nst, int hstage) {
     const I8Geom g(q);
     const int nk = D / BKB;
-    return 1024 + (size_t)nk * A_B + (size_t)nst * B_B + OUT_B + (size_t)(2 * g.NC8) * 8 + (size_t)(2 * nk + 2 * nst + 4) * 8 + 16;
+    return 1024 + (size_t)nk * A_B + (size_t)nst * B_B + (hstage ? OUT_B / 2 : OUT_B) + (size_t)(2 * g.NC8) * 8 +
+           (size_t)(2 * nk + 2 * nst + 4) * 8 + 16;
 }
-int i8_stages(int D, int q) {                            // digit-tile stages that fit next to the resident mask block
+int i8_stages(int D, int q, int hstage) {                // digit-tile stages that fit next to the resident mask block
     for (int nst = ST; nst >= 2; --nst)
-        if (i8_smem_bytes(D, q, nst) <= 227 * 1024) return nst;
+        if (i8_smem_bytes(D, q, nst, hstage) <= 227 * 1024) return nst;
     return 0;
+}
+int i8_hstage(int D, int q) {                            // half staging only where it buys a stage and stages are scarce
+    static int force = -2;
+    if (force == -2) {
+        const char *e = getenv("PYVB_I8_HSTAGE");
+        force = e ? atoi(e) : -1;
+    }
+    if (force == 0 || force == 1) return force;
+    const int full = i8_stages(D, q, 0);
+    return (full < 6 && i8_stages(D, q, 1) > full) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ K1-i8: qprec columns of the MZ rows
@@ -229,8 +241,9 @@ int i8_stages(int D, int q) {                            // digit-tile stages th
 template <int CL>
 __global__ void __launch_bounds__(NTHR, 1)
 zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmO, long long N, int D, int q, const double *__restrict__ P0,
-                const double *__restrict__ gscale, const double *__restrict__ gl, int nrb, int nst, long long *prof) {
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO8, long long N, int D, int q,
+                const double *__restrict__ P0, const double *__restrict__ gscale, const double *__restrict__ gl, int nrb,
+                int nst, int hstage, long long *prof) {
     const I8Geom G(q);
     long long w0 = 0, w1 = 0, w2 = 0;                          // PYVB_I8_PROF: clocks spent waiting, per role
     const long long tstart = clock64();
@@ -250,7 +263,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     unsigned char *a_base = smem;                                              // [nk][128 x 64 B] resident mask block
     unsigned char *b_base = smem + (size_t)nk * A_B;                           // [nst][224 x 64 B] digit tiles
     unsigned char *o_base = b_base + (size_t)nst * B_B;                        // [8 warps][32 rows x 128 B] output staging (swizzled)
-    double *p0v = reinterpret_cast<double *>(o_base + OUT_B);                  // [NC8]: packed P0, zero pad
+    double *p0v = reinterpret_cast<double *>(o_base + (hstage ? OUT_B / 2 : OUT_B));   // [NC8]: packed P0, zero pad
     double *fcol = p0v + G.NC8;                                                // [NC8]: tau * scale_c * 2^-54
     uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nk]
     uint64_t *aempty = afull + nk;                                             // [nk]
@@ -286,6 +299,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
+        tma_prefetch_desc(&tmO8);
         for (int k = 0; k < nk; ++k) {
             mbar_init(&afull[k], 1);
             mbar_init(&aempty[k], 1);
@@ -407,35 +421,68 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 // and written by ONE TMA tensor store (rows >= N and columns >= PP are clipped by the map).  Per-lane
                 // 16-byte global stores touched 32 rows per instruction and a shuffle transposition cost ~25 instructions
                 // per output: both made the epilogue, not the MMAs, the limit.
-                unsigned char *stage = o_base + (warp - 2) * 4096;
-                if (lane == 0) PROF_WAIT(w1, bulk_wait_read_all());   // the previous store of this warp has read the tile
-                __syncwarp();
+                if (!hstage) {
+                    unsigned char *stage = o_base + (warp - 2) * 4096;
+                    if (lane == 0) PROF_WAIT(w1, bulk_wait_read_all());   // the previous store of this warp has read the tile
+                    __syncwarp();
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    if (c0 + ch * 8 >= G.PP) continue;          // a chunk of 8 columns is entirely in or out
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if (c0 + ch * 8 >= G.PP) continue;      // a chunk of 8 columns is entirely in or out
 #pragma unroll
-                    for (int k = 0; k < 8; k += 2) {
-                        int d0[NPL], d1[NPL];
+                        for (int k = 0; k < 8; k += 2) {
+                            int d0[NPL], d1[NPL];
 #pragma unroll
-                        for (int p = 0; p < NPL; ++p) {
-                            d0[p] = (int)a[ch][p][k];
-                            d1[p] = (int)a[ch][p][k + 1];
+                            for (int p = 0; p < NPL; ++p) {
+                                d0[p] = (int)a[ch][p][k];
+                                d1[p] = (int)a[ch][p][k + 1];
+                            }
+                            const int c = c0 + ch * 8 + k;
+                            const double2 f2 = *reinterpret_cast<const double2 *>(&fcol[c]);
+                            const double2 p2 = *reinterpret_cast<const double2 *>(&p0v[c]);
+                            double2 o;
+                            o.x = fma(f2.x, combine7(d0), p2.x);
+                            o.y = fma(f2.y, combine7(d1), p2.y);
+                            const int chunk = ch * 4 + (k >> 1);
+                            *reinterpret_cast<double2 *>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
                         }
-                        const int c = c0 + ch * 8 + k;
-                        const double2 f2 = *reinterpret_cast<const double2 *>(&fcol[c]);
-                        const double2 p2 = *reinterpret_cast<const double2 *>(&p0v[c]);
-                        double2 o;
-                        o.x = fma(f2.x, combine7(d0), p2.x);
-                        o.y = fma(f2.y, combine7(d1), p2.y);
-                        const int chunk = ch * 4 + (k >> 1);
-                        *reinterpret_cast<double2 *>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
                     }
-                }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0 && c0 < G.PP) {
-                    tma_store_2d(&tmO, c0, (int)rowbase, stage);
-                    bulk_commit();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && c0 < G.PP) {
+                        tma_store_2d(&tmO, c0, (int)rowbase, stage);
+                        bulk_commit();
+                    }
+                } else {
+                    // half staging: 8 columns (64-byte rows, SWIZZLE_64B pattern: chunk ^ ((row >> 1) & 3)) per store
+                    unsigned char *stage = o_base + (warp - 2) * 2048;
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        if (c0 + ch * 8 >= G.PP) continue;      // warp-uniform
+                        if (lane == 0) PROF_WAIT(w1, bulk_wait_read_all());
+                        __syncwarp();
+#pragma unroll
+                        for (int k = 0; k < 8; k += 2) {
+                            int d0[NPL], d1[NPL];
+#pragma unroll
+                            for (int p = 0; p < NPL; ++p) {
+                                d0[p] = (int)a[ch][p][k];
+                                d1[p] = (int)a[ch][p][k + 1];
+                            }
+                            const int c = c0 + ch * 8 + k;
+                            const double2 f2 = *reinterpret_cast<const double2 *>(&fcol[c]);
+                            const double2 p2 = *reinterpret_cast<const double2 *>(&p0v[c]);
+                            double2 o;
+                            o.x = fma(f2.x, combine7(d0), p2.x);
+                            o.y = fma(f2.y, combine7(d1), p2.y);
+                            *reinterpret_cast<double2 *>(stage + lane * 64 + ((((k >> 1) ^ ((lane >> 1) & 3))) << 4)) = o;
+                        }
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmO8, c0 + ch * 8, (int)rowbase, stage);
+                            bulk_commit();
+                        }
+                    }
                 }
             }
         }
@@ -955,7 +1002,7 @@ cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, int mode, 
 }
 
 bool i8_supported(int D, int q) {
-    return (q == 16 || q == 32 || q == 64) && D >= 64 && (D % 64) == 0 && i8_stages(D, q) >= 2;
+    return (q == 16 || q == 32 || q == 64) && D >= 64 && (D % 64) == 0 && i8_stages(D, q, 1) >= 2;
 }
 size_t i8_digits_bytes(int D, int q) { return (size_t)(i_nc8(q) / CT) * NPL * CT * D; }
 size_t i8_mask_bytes(long long N, int D) { return (size_t)((N + BM - 1) / BM * BM) * (size_t)D; }
@@ -1001,8 +1048,20 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     }
-    const int nst = i8_stages(D, q);
-    const size_t smem = i8_smem_bytes(D, q, nst);
+    const int hstage = i8_hstage(D, q);
+    const int nst = i8_stages(D, q, hstage);
+    if (nst < 2) return cudaErrorNotSupported;
+    const size_t smem = i8_smem_bytes(D, q, nst, hstage);
+    CUtensorMap tmO8;
+    {   // the same rows as 8-column x 32-row boxes (64-byte rows, SWIZZLE_64B) for the half-staging epilogue
+        EncodeTiledFn enc = get_encode_i8();
+        cuuint64_t dims[2] = {(cuuint64_t)g.PP, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)ldmz * sizeof(double)};
+        cuuint32_t box[2] = {8, 32}, es[2] = {1, 1};
+        CUresult r = enc(&tmO8, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, MZ, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
     long long gl_ = (nrb + cl - 1) / cl * cl;
     const int grid = (int)(gl_ < 148 ? gl_ : 148 / cl * cl);
     auto kern = cl == 4 ? zstep_i8_kernel<4> : cl == 2 ? zstep_i8_kernel<2> : zstep_i8_kernel<1>;
@@ -1014,7 +1073,7 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
         prof_on = getenv("PYVB_I8_PROF") ? 1 : 0;
         if (prof_on && cudaMalloc(&prof, 148 * 10 * sizeof(long long)) != cudaSuccess) prof_on = 0;
     }
-    e = launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, tmO, N, D, q, P0, gscale, gl, (int)nrb, nst,
+    e = launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, tmO, tmO8, N, D, q, P0, gscale, gl, (int)nrb, nst, hstage,
                        prof_on ? prof : (long long *)nullptr);
     if (prof_on && e == cudaSuccess) {      // diagnosis only: synchronises
         long long h[148 * 10];
