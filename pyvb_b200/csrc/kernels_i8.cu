@@ -4,8 +4,9 @@
 // m1 = tr(<w_i w_j^T> Lambda_n), nodes/node.py:213-227, with a masked precision), multiplies a 0/1 matrix with a small
 // real one.  The mask is exact in int8; every column of G is written in fixed point with its own scale,
 //     G[d][c] = scale_c 2^-54 sum_{t<7} digit_t[d][c] 256^t,     digit_t in [-128, 127]   (balanced base 256),
-// |round(G / scale_c 2^54)| <= 2^54 < 2^55 = the range of seven balanced digits, i.e. every entry is kept to
-// scale_c 2^-55 absolute -- finer than the FP64 spacing of the column's large entries.  Then
+// scale_c = the power of two above max_d |G[d][c]|, so that |round(G / scale_c 2^54)| < 2^54 < 2^55 = the range of seven
+// balanced digits, the scaling itself is exact, every entry is rounded once to scale_c 2^-55, and entries within a factor
+// 4 of the column maximum are represented EXACTLY (finer than FP64 for the column's large entries).  Then
 //     mask @ G = scale_c 2^-54 sum_t 256^t (mask @ digit_t)
 // where every mask @ digit_t is an EXACT integer GEMM (|sum| <= 128 D << 2^31).  The seven INT32 results per output
 // are recombined in the epilogue (two exact 64-bit integer halves, one FP64 FMA): no accumulation error at all, one
@@ -39,6 +40,14 @@ constexpr int NPL = 7;                                                          
 constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, max digit stages, columns per tile
 constexpr int A_B = BM * BKB, B_B = NPL * CT * BKB;      // 8192, 14336
 constexpr int NTHR = 10 * 32;
+
+// smallest power of two > m (1 for m = 0, NaN, inf): a fixed-point scale whose reciprocal multiplies exactly
+__device__ __forceinline__ double pow2_above(double m) {
+    if (!(m > 0.0 && m < 1e300)) return 1.0;
+    int e;
+    frexp(m, &e);                                        // m = f 2^e, f in [0.5, 1)
+    return ldexp(1.0, e);
+}
 
 // ------------------------------------------------------------------ operand preparation
 // mask[rb][kb][128 rows][64 bytes] (rb = n / 128, kb = d / 64): every TMA box of the kernel is one contiguous 8 KB block
@@ -94,7 +103,9 @@ pack_g_i8_kernel(int D, int q, const double *__restrict__ Wbar, const double *__
         if (threadIdx.x == 0) sh[32] = t;
     }
     __syncthreads();
-    const double scale = (sh[32] > 0.0 && sh[32] < 1e300) ? sh[32] : 1.0;
+    // the scale is the power of two above the column maximum: g * (2^54 / scale) is then an EXACT scaling, so every entry is
+    // rounded once, to scale 2^-55, and entries within a factor 4 of the column maximum are represented exactly
+    const double scale = pow2_above(sh[32]);
     if (threadIdx.x == 0) gscale[c] = scale;
     const double inv = 18014398509481984.0 / scale;                     // 2^54 / scale
     const int nct = gridDim.x / CT;
@@ -654,7 +665,7 @@ colmax_reduce_kernel(int ncols, int nvalid, int ldmz, const double *__restrict__
     if (c < nvalid)
         for (int b = lane; b < nblk; b += 32) m = fmax(m, pm[(size_t)b * ldmz + c]);
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) zscale[c] = (m > 0.0 && m < 1e300) ? m : 1.0;   // NaN / inf rows (non-PD) are reported by K2, not here
+    if (lane == 0) zscale[c] = pow2_above(m);              // NaN / inf rows (non-PD) are reported by K2, not here
 }
 
 // MZ rows -> digit planes, transposed: CTA = 128 rows x 32 columns

@@ -83,9 +83,13 @@ def test_i8_qprec_is_exact_to_rounding(eng, shape):
     G = W[:, ii] * W[:, jj] + np.where(ii == jj, Wv[:, ii], 0.0)                  # D x P
     tau = e.get_state()["tau"]
     ref = np.eye(q)[ii, jj][None, :] + tau * (O.astype(np.longdouble) @ G.astype(np.longdouble)).astype(np.float64)
-    scale = np.abs(G).max(0)
+    from oracle.i8_oracle import column_scales, mask_contract_i8
+    scale = column_scales(G)                                   # the power of two above the column maximum
     bound = tau * O.sum(1)[:, None] * scale[None, :] * 2.0 ** -55 + 4 * np.finfo(np.float64).eps * np.abs(ref)
     assert np.all(np.abs(got - ref) <= bound), float(np.max(np.abs(got - ref) / bound))
+    # the numpy restatement of the kernel steps (oracle/i8_oracle.py) agrees to the last rounding (FMA vs multiply + add)
+    rest = mask_contract_i8(O, G, tau=tau, add=np.eye(q)[ii, jj][None, :])
+    assert np.all(np.abs(got - rest) <= 2 * np.finfo(np.float64).eps * np.abs(rest))
     X0 = np.where(O, X - init["mu"][None, :], 0.0)
     assert tensor_rel(eta, tau * (X0 @ W)) < 1e-12
     m = e.mask8.cpu().numpy().reshape(-1, D // 64, 128, 64).transpose(0, 2, 1, 3).reshape(-1, D)   # tiles -> rows
