@@ -86,6 +86,8 @@ extern "C" {
 #define PYVB_GL_ELBO_ALPHA 9
 #define PYVB_GL_RESID2 10
 #define PYVB_GL_NONPD 11     /* rows whose posterior precision was not positive definite (as a double) */
+#define PYVB_GL_I8BAD 12     /* INT8 path: rows of the LAST Z step whose qprec failed the accuracy guard (then redone on DMMA) */
+#define PYVB_GL_I8FALL 14    /* INT8 path: Z steps that fell back to the FP64 tensor cores so far (diagnostic) */
 #define PYVB_GL_ALPHA 16     /* [64] <alpha_i>  (constant prior precision when ARD is off) */
 #define PYVB_GL_ALQB 80      /* [64] ARD Gamma qb_i */
 #define PYVB_GL_LEN 144
@@ -211,7 +213,13 @@ int pyvb_impute_f64(long long N, int D, int q, const double *Xorig, long long ld
  *          (once per data set).  A sub-range of rows starting at a multiple of 128 starts at mask + first_row * D.
  *   GI     pyvb_i8_digits_bytes(D, q) bytes, gscale pyvb_i8_ncols(q) doubles: per-sweep scratch (filled by the call)
  *   MZ     the interleaved rows of the DMMA path (ldmz = pyvb_mz_pitch(q)); Gw as for pyvb_zstep_f64 (DMMA pitch)
- * k1_only (measurement): 1 leaves [qprec packed | eta] in the rows; 2 runs the INT8 part alone, 3 the eta part alone. */
+ * k1_only (measurement): 1 leaves [qprec packed | eta] in the rows; 2 runs the INT8 part alone, 3 the eta part alone.
+ * Accuracy guard: the fixed point is relative to the COLUMN maximum of G, so a row that observes none of a column's large
+ * entries keeps at most tau * n_obs * scale_c * 2^-55 of rounding.  The batched solve checks every finished qprec row:
+ * when tau * D * max_c scale_c * 2^-55 > 2^-38 * max_i qprec_ii for any row (gl[PYVB_GL_I8BAD] counts them), the whole
+ * call is redone on the FP64 tensor cores by conditional launches that exit at once otherwise (gl[PYVB_GL_I8FALL] counts
+ * the fall-backs).  The result is therefore accurate to 2^-38 of max_i qprec_ii per row for ANY input range; on the
+ * normalised data of BASELINE.json's configurations the bound sits at ~2^-50 and the guard never fires. */
 int pyvb_i8_supported(int D, int q);
 size_t pyvb_i8_digits_bytes(int D, int q);
 int pyvb_i8_ncols(int q);
@@ -230,12 +238,15 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
  * Z step that produced these rows, or NULL (then logdet [N] is read and the MZ column sums take one more pass).
  *   maskT  pyvb_stats_i8_maskt_bytes(N, D) bytes, [n / 64][D][64] int8: pyvb_prepare_maskt_i8 (once per data set)
  *   ZI     pyvb_stats_i8_digits_bytes(N, q) bytes, scratch pyvb_stats_i8_scratch_len(q) doubles: per-call scratch
- *   ws     pyvb_stats_i8_workspace_bytes(N, D, q) */
+ *   ws     pyvb_stats_i8_workspace_bytes(N, D, q)
+ * Accuracy guard, as for pyvb_zstep_i8_f64: a data dimension d with cnt_d * max_c zscale_c * 2^-55 > 2^-38 * max_i T1[d][ii]
+ * (outlier rows that d does not observe) sends the whole pass to the FP64 tensor cores, before the exchange. */
 int pyvb_stats_i8_supported(int D, int q);
 long long pyvb_stats_i8_npad(long long N);
 size_t pyvb_stats_i8_digits_bytes(long long N, int q);
 size_t pyvb_stats_i8_maskt_bytes(long long N, int D);
 size_t pyvb_stats_i8_scratch_len(int q);
+size_t pyvb_stats_i8_guard_offset(int q);   /* scratch[off] = data dimensions that failed the guard in the last call, [off+1] = fall-backs so far */
 size_t pyvb_stats_i8_workspace_bytes(long long N, int D, int q);
 int pyvb_prepare_maskt_i8(long long N, int D, const double *X, long long ldx, void *maskT, void *stream);
 int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx, const void *maskT, const double *MZ,

@@ -73,3 +73,21 @@ def exact_fixed_sum(mask, G):
         for c in range(C):
             out[n][c] = sum(vl[d][c] for d in idx)
     return out, scale
+
+
+# ---- the accuracy guard (pyvb_b200/csrc/cabi.cu: I8_TOL; kernels.h: I8Check; kernels_i8.cu: stats_i8_check_kernel) ----
+I8_TOL = 2.0 ** -38
+
+
+def zstep_guard_rows(qprec_diag_max, G, tau, D, tol=I8_TOL):
+    """Rows of a Z step the batched solve flags: the fixed-point bound  tau * D * max_c scale_c * 2^-55  exceeds
+    tol * max_i qprec_ii.  qprec_diag_max: [N] largest diagonal entry of every row's posterior precision."""
+    thr = tau * (D * 2.0 ** -55 / tol) * float(np.max(column_scales(G)))
+    return thr > np.asarray(qprec_diag_max)
+
+
+def stats_guard_dims(T1_diag_max, cnt, MZcols, tol=I8_TOL):
+    """Data dimensions of a statistics pass the check kernel flags: cnt_d * max_c zscale_c * 2^-55 > tol * max_i T1[d][ii].
+    MZcols: [N][P] the <zz^T> columns that were digitised (their column maxima give the scales)."""
+    sz = float(np.max(column_scales(MZcols))) * 2.0 ** -55
+    return np.asarray(cnt) * sz > tol * np.asarray(T1_diag_max)

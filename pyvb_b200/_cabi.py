@@ -53,6 +53,7 @@ SIGNATURES = {
     "pyvb_stats_i8_digits_bytes": (c_sz, [c_ll, c_int]),
     "pyvb_stats_i8_maskt_bytes": (c_sz, [c_ll, c_int]),
     "pyvb_stats_i8_scratch_len": (c_sz, [c_int]),
+    "pyvb_stats_i8_guard_offset": (c_sz, [c_int]),
     "pyvb_stats_i8_workspace_bytes": (c_sz, [c_ll, c_int, c_int]),
     "pyvb_prepare_maskt_i8": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp]),
     "pyvb_stats_i8_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp, c_sz,

@@ -6,6 +6,8 @@ SC_SXX, SC_SUMV, SC_NE, SC_QLDZ, SC_LOGDETZ, SC_LATQLD, SC_NLAT, SC_PNMISS, SC_P
 GL_QA, GL_QB, GL_TAU, GL_ELBO, GL_ELBO_W, GL_ELBO_MU, GL_ELBO_Z, GL_ELBO_X, GL_ELBO_BETA, GL_ELBO_ALPHA = range(10)
 GL_RESID2 = 10
 GL_NONPD = 11
+GL_I8BAD = 12
+GL_I8FALL = 14
 GL_ALPHA = 16
 GL_ALQB = 80
 GL_LEN = 144

@@ -50,6 +50,19 @@ static AuxStream *aux_stream() {
     return a.state == 1 ? &a : nullptr;
 }
 
+// Accuracy guard of the INT8 path: relative accuracy (max norm, per row of qprec / per data dimension of T1)
+// below which the fixed-point contraction is redone on the FP64 tensor cores.  PYVB_I8_GUARD=0 switches the guard off
+// (measurement only), PYVB_I8_GUARD=force makes every call fall back (tests of the fall-back plumbing).
+static const double I8_TOL = 3.637978807091713e-12;     // 2^-38
+static int i8_guard_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("PYVB_I8_GUARD");
+        mode = (e && e[0] == '0') ? 0 : (e && e[0] == 'f') ? 2 : 1;
+    }
+    return mode;
+}
+
 static int pick_algo(int algo, int D, int q) {
     if (algo == PYVB_ALGO_AUTO) return dmma_supported(D, q) ? PYVB_ALGO_DMMA : PYVB_ALGO_GENERIC;
     if (algo == PYVB_ALGO_DMMA_K1) return PYVB_ALGO_DMMA;
@@ -323,7 +336,7 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
         st2 = aux->s;
     }
     if (k1_only != 3) {      // first: its CTAs take one slot per SM, the eta kernel's CTAs fill what is left
-        e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, st);
+        e = launch_pack_g_i8(D, q, Wbar, Wvar, GI, gscale, gl, st);
         if (e == cudaSuccess) e = launch_zstep_i8(N, D, q, mask, GI, P0, gscale, gl, MZ, (int)ldmz, st);
     }
     if (e == cudaSuccess && k1_only != 2) {
@@ -335,7 +348,20 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
         if (e2 == cudaSuccess) e2 = cudaStreamWaitEvent(st, aux->join, 0);
         if (e == cudaSuccess) e = e2;
     }
-    if (e == cudaSuccess && !k1_only) e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, st);
+    if (e == cudaSuccess && !k1_only) {
+        // K2 checks every finished qprec row against the fixed-point bound of K1-i8 (kernels.h: I8Check); when a row fails,
+        // the whole step is redone on the FP64 tensor cores by two conditional launches that exit at once otherwise
+        const int guard = (k2_impl(q) == 0) ? 0 : i8_guard_mode();
+        I8Check chk;
+        if (guard) {
+            chk.gscale = gscale;
+            chk.ncols = q * (q + 1) / 2;
+            chk.fac = (guard == 2) ? 1e300 : (double)D * 2.7755575615628914e-17 / I8_TOL;     // D * 2^-55 / tol
+        }
+        e = launch_zsolve(N, q, MZ, Sig, logdet, gl, zsums, st, nullptr, chk);
+        if (e == cudaSuccess && guard)
+            e = launch_zstep_dmma(N, D, q, X, ldx, Gw, ldg, P0, h0, gl, MZ, Sig, logdet, zsums, 0, st, gl + PYVB_GL_I8BAD);
+    }
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "zstep_i8");
 }
 
@@ -344,6 +370,9 @@ long long pyvb_stats_i8_npad(long long N) { return stats_i8_npad(N); }
 size_t pyvb_stats_i8_digits_bytes(long long N, int q) { return stats_i8_digits_bytes(N, q); }
 size_t pyvb_stats_i8_maskt_bytes(long long N, int D) { return stats_i8_maskt_bytes(N, D); }
 size_t pyvb_stats_i8_scratch_len(int q) { return stats_i8_scratch_len(q, pyvb_mz_pitch(q)); }
+size_t pyvb_stats_i8_guard_offset(int q) {
+    return (size_t)(stats_i8_guard((double *)0, q, pyvb_mz_pitch(q)) - (double *)0);
+}
 size_t pyvb_stats_i8_workspace_bytes(long long N, int D, int q) {
     const StatLayout L(D, q);
     if (N <= 0) return align256((L.len + PYVB_NSCAL) * sizeof(double));
@@ -410,6 +439,15 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
         if (e == cudaSuccess) e = e2;
     }
     if (e != cudaSuccess) return cuda_fail(e, "stats_i8");
+    if (i8_guard_mode()) {
+        // the same guard for T1 / Bst: a data dimension whose sums are not accurate to I8_TOL sends the whole pass to the
+        // FP64 tensor cores (one conditional launch that exits at once otherwise); both before the exchange
+        double *guard = stats_i8_guard(scratch, q, (int)ldmz);
+        e = launch_stats_i8_check(D, q, (const double *)ws, nch, xcache, scratch, (int)ldmz,
+                                  i8_guard_mode() == 2 ? 1e300 : I8_TOL, st);
+        if (e == cudaSuccess) e = launch_stats_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st, guard);
+        if (e != cudaSuccess) return cuda_fail(e, "stats_i8 (guard)");
+    }
     e = launch_stats_reduce(D, q, (const double *)ws, nch, NULL, 0, stats, const_cast<double *>(xcache), 1, zs, zn, zk,
                             peers ? peers->bufs : NULL, peers ? peers->world : 1, peers ? peers->rank : 0,
                             peers ? peers->epoch : 0ULL, st);

@@ -7,6 +7,16 @@
 
 namespace pyvb {
 
+// Accuracy guard of the INT8 mask contraction (K1-i8): the qprec entries of a row carry at most tau * n_obs * scale_c * 2^-55
+// of fixed-point rounding (scale_c = the power of two above the column maximum of G).  K2 reads the finished qprec row anyway:
+// with gscale != NULL it flags every row whose bound  tau * fac * max_c scale_c  (fac = D * 2^-55 / tol) exceeds the largest
+// diagonal entry of the row, i.e. whose qprec is not accurate to `tol` in the max norm, into gl[PYVB_GL_I8BAD].
+struct I8Check {
+    const double *gscale = nullptr;    // [ncols] fixed-point scales of the G columns (NULL: no check)
+    int ncols = 0;
+    double fac = 0.0;
+};
+
 // ---- generic (any D, q <= 64) ------------------------------------------------
 cudaError_t launch_pack_gw(int D, int q, const double *Wbar, const double *Wvar, const double *mu,
                            double *Gw, int ldg, cudaStream_t st);
@@ -47,33 +57,34 @@ cudaError_t launch_impute(long long N, int D, int q, const double *Xorig, long l
 bool dmma_supported(int D, int q);
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                               int ldg, const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                              double *logdet, double *zsums, int k1_only, cudaStream_t st);
+                              double *logdet, double *zsums, int k1_only, cudaStream_t st, const double *cond = nullptr);
 int zstep_eta_pitch(int q);
 cudaError_t launch_zstep_eta_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw,
                                   double *weta, const double *P0, const double *h0, double *gl, double *MZ,
                                   cudaStream_t st);
+// cond (nullable, device): the kernel exits at once unless *cond > 0 (the conditional fall-back launches of the INT8 path)
 cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
-                          cudaStream_t st);
+                          cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
 // K2 leaves nblk partials of kw doubles each in zsums (0, 0: no fast K2 for this q)
 void zsolve_partials(long long N, int q, int &nblk, int &kw);
 // blocked tensor-core K2 (kernels_k2.cu): q in {8, 16, 32, 64}
 int zsolve_blocked_blocks(long long N, int q);
 int zsolve_blocked_kw(int q);
 cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl,
-                                  double *zsums, cudaStream_t st);
+                                  double *zsums, cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
 int k2_impl(int q);   // 0 register-resident, 1 blocked tensor-core, 2 thread per matrix (PYVB_K2 overrides)
 // thread-per-matrix K2 (kernels_k2t.cu): q in {8, 16}
 int zsolve_tpm_blocks(long long N, int q);
 int zsolve_tpm_kw(int q);
 cudaError_t launch_zsolve_tpm(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
-                              cudaStream_t st);
+                              cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
 cudaError_t launch_zsolve_tpm_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
                                   double *zsums, cudaStream_t st);
 cudaError_t launch_zsolve_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
                               double *zsums, cudaStream_t st);
 int stats_dmma_nchunks(long long N, int D, int q);
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
-                              double *ws_main, int nchunks, cudaStream_t st);
+                              double *ws_main, int nchunks, cudaStream_t st, const double *cond = nullptr);
 
 // ---- FP32 variant: tcgen05 / TMEM contraction on bf16 x 3 splits (kernels_f32.cu) ----
 int f32_ncp(int q);                 // floats per MZ32 row
@@ -99,7 +110,8 @@ size_t i8_digits_bytes(int D, int q);          // bytes of the digit planes of G
 size_t i8_mask_bytes(long long N, int D);      // bytes of the tile-major int8 mask
 int i8_ncols(int q);                           // packed columns rounded up to 32 (length of gscale)
 cudaError_t launch_prepare_mask_i8(long long N, int D, const double *X, long long ldx, void *mask, cudaStream_t st);
-cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wvar, void *GI, double *gscale,
+// also clears gl[PYVB_GL_I8BAD] (the guard counter of the Z step that follows)
+cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wvar, void *GI, double *gscale, double *gl,
                              cudaStream_t st);
 cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const void *GI, const double *P0,
                             const double *gscale, const double *gl, double *MZ, int ldmz, cudaStream_t st);
@@ -110,7 +122,12 @@ int stats_i8_ncols(int q);
 long long stats_i8_npad(long long N);                       // rows of maskT / ZI rounded up to 128
 size_t stats_i8_digits_bytes(long long N, int q);           // bytes of ZI
 size_t stats_i8_maskt_bytes(long long N, int D);            // bytes of maskT
-size_t stats_i8_scratch_len(int q, int ldmz);               // doubles: partial column maxima + zscale
+size_t stats_i8_scratch_len(int q, int ldmz);               // doubles: partial column maxima + zscale + guard block
+double *stats_i8_guard(double *scratch, int q, int ldmz);   // [0] data dimensions that failed the guard, [1] fall-backs taken
+// after launch_stats_i8: flags (guard[0] > 0) the data dimensions d whose T1 row is not accurate to tol in the max norm:
+// cnt_d * max_c zscale_c * 2^-55 > tol * max_i T1[d][ii]  (cnt = the first D entries of xcache)
+cudaError_t launch_stats_i8_check(int D, int q, const double *ws, int nchunks, const double *xcache, double *scratch,
+                                  int ldmz, double tol, cudaStream_t st);
 int stats_i8_nchunks(long long N, int D, int q);
 cudaError_t launch_prepare_maskT_i8(long long N, int D, const double *X, long long ldx, void *maskT, cudaStream_t st);
 cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const double *MZ, int ldmz, void *ZI,

@@ -277,8 +277,9 @@ template <int Q, bool ETA>
 __global__ void __launch_bounds__(ZT<Q, ETA>::NTHR, ZT<Q, ETA>::OCC)
 zstep_dmma_kernel(const __grid_constant__ CUtensorMap tmX, long long N, int D, const double *__restrict__ Gw,
                   const double *__restrict__ P0, const double *__restrict__ h0, const double *__restrict__ gl,
-                  double *__restrict__ MZ, long long ntiles) {
+                  double *__restrict__ MZ, long long ntiles, const double *__restrict__ cond) {
     using T = ZT<Q, ETA>;
+    if (cond != nullptr && !(*cond > 0.0)) return;              // conditional (fall-back) launch of the INT8 path
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
     // shared address space so that fragment loads compile to LDS, not generic LD
@@ -654,7 +655,7 @@ static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double 
 // kernel (kernels_k2.cu), 2 = thread per matrix (kernels_k2t.cu).  q = 64 only exists blocked.  PYVB_K2 = reg /
 // blocked / tpm overrides the default (measured per 1M rows, FP64: q = 16: 1.62 / 2.0 / see DESIGN ms; q = 32: 9.0 / 5.8).
 int k2_impl(int q) {
-    const char *e = getenv("PYVB_K2");               // read per call: tests flip it
+    const char *e = getenv("PYVB_K2");               // read per call (tests flip it); callers size zsums with pyvb_zsums_len
     int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : -1;
     if (q == 64) return 1;
     if (mode == 2 && q > 16) mode = -1;
@@ -698,7 +699,7 @@ static cudaError_t launch_k1_q(long long N, int D, const double *X, long long ld
     if (e != cudaSuccess) return e;
     const long long ntiles = ((N + T::R - 1) / T::R) * T::NCT;
     const long long blocks = ntiles < 148LL * T::OCC ? ntiles : 148LL * T::OCC;
-    zstep_dmma_kernel<Q, ETA><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
+    zstep_dmma_kernel<Q, ETA><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles, nullptr);
     return cudaGetLastError();
 }
 
@@ -731,7 +732,7 @@ cudaError_t launch_zstep_eta_dmma(long long N, int D, int q, const double *X, lo
 template <int Q>
 static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long ldx, const double *Gw,
                                   const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                                  double *logdet, double *zsums, int k1_only, cudaStream_t st) {
+                                  double *logdet, double *zsums, int k1_only, cudaStream_t st, const double *cond) {
     using T = ZT<Q>;
     CUtensorMap tmX;
     cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, T::KC, T::R,
@@ -741,32 +742,33 @@ static cudaError_t launch_zstep_q(long long N, int D, const double *X, long long
     if (e != cudaSuccess) return e;
     const long long ntiles = ((N + T::R - 1) / T::R) * T::NCT;
     const long long blocks = ntiles < 148LL * ZC<Q>::OCC ? ntiles : 148LL * ZC<Q>::OCC;
-    zstep_dmma_kernel<Q, false><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles);
+    zstep_dmma_kernel<Q, false><<<(unsigned)blocks, T::NTHR, T::SMEM, st>>>(tmX, N, D, Gw, P0, h0, gl, MZ, ntiles, cond);
     e = cudaGetLastError();
     if (e != cudaSuccess || k1_only) return e;
-    return launch_zsolve(N, Q, MZ, Sig, logdet, gl, zsums, st);
+    return launch_zsolve(N, Q, MZ, Sig, logdet, gl, zsums, st, cond);
 }
 
 cudaError_t launch_zstep_dmma(long long N, int D, int q, const double *X, long long ldx, const double *Gw, int ldg,
                               const double *P0, const double *h0, double *gl, double *MZ, double *Sig,
-                              double *logdet, double *zsums, int k1_only, cudaStream_t st) {
+                              double *logdet, double *zsums, int k1_only, cudaStream_t st, const double *cond) {
     if (N <= 0) return cudaSuccess;
     if (ldg != c_gw_pitch(q)) return cudaErrorInvalidValue;
     switch (q) {
-        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
-        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
-        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
-        case 64: return launch_zstep_q<64>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st);
+        case 8: return launch_zstep_q<8>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st, cond);
+        case 16: return launch_zstep_q<16>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st, cond);
+        case 32: return launch_zstep_q<32>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st, cond);
+        case 64: return launch_zstep_q<64>(N, D, X, ldx, Gw, P0, h0, gl, MZ, Sig, logdet, zsums, k1_only, st, cond);
     }
     return cudaErrorNotSupported;
 }
 
 cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
-                          cudaStream_t st) {
+                          cudaStream_t st, const double *cond, I8Check chk) {
     if (N <= 0) return cudaSuccess;
     const int impl = k2_impl(q);
-    if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st);
-    if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st);
+    if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
+    if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
+    if (cond != nullptr || chk.gscale != nullptr) return cudaErrorNotSupported;   // the cross-check kernel has no guard
     switch (q) {
         case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);
         case 16: return launch_zsolve_q<16>(N, MZ, Sig, logdet, gl, zsums, st);
@@ -812,8 +814,10 @@ template <int Q, bool XO = false> struct STT {
 template <int Q, bool XO>
 __global__ void __launch_bounds__(STT<Q, XO>::NTHR, SC<Q>::OCC)
 stats_dmma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmV, long long N, int D,
-                  const double *__restrict__ MZ, double *__restrict__ ws, long long rows_per_chunk) {
+                  const double *__restrict__ MZ, double *__restrict__ ws, long long rows_per_chunk,
+                  const double *__restrict__ cond) {
     using T = STT<Q, XO>;
+    if (cond != nullptr && !(*cond > 0.0)) return;              // conditional (fall-back) launch of the INT8 statistics
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzled TMA tiles); pointer arithmetic on the __shared__ array keeps the
     // shared address space so that fragment loads compile to LDS, not generic LD
@@ -1011,7 +1015,7 @@ int stats_dmma_nchunks(long long N, int D, int q) {
 
 template <int Q, bool XO = false>
 static cudaError_t launch_stats_q(long long N, int D, const double *X, long long ldx, const double *MZ, double *ws,
-                                  int nchunks, cudaStream_t st) {
+                                  int nchunks, cudaStream_t st, const double *cond = nullptr) {
     using T = STT<Q, XO>;
     CUtensorMap tmX, tmV;
     cudaError_t e = make_map(&tmX, X, (uint64_t)D, (uint64_t)N, (uint64_t)ldx, 16, T::KC, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1032,7 +1036,7 @@ static cudaError_t launch_stats_q(long long N, int D, const double *X, long long
     if (rpc < T::KC) rpc = T::KC;
     const int ndt = ((D + T::DT - 1) / T::DT) * T::NCT;
     dim3 grid((unsigned)ndt, (unsigned)nchunks);
-    stats_dmma_kernel<Q, XO><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc);
+    stats_dmma_kernel<Q, XO><<<grid, T::NTHR, T::SMEM, st>>>(tmX, tmV, N, D, MZ, ws, rpc, cond);
     return cudaGetLastError();
 }
 
@@ -1049,13 +1053,13 @@ cudaError_t launch_stats_x_dmma(long long N, int D, int q, const double *X, long
 }
 
 cudaError_t launch_stats_dmma(long long N, int D, int q, const double *X, long long ldx, const double *MZ,
-                              double *ws_main, int nchunks, cudaStream_t st) {
+                              double *ws_main, int nchunks, cudaStream_t st, const double *cond) {
     if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 8: return launch_stats_q<8>(N, D, X, ldx, MZ, ws_main, nchunks, st);
-        case 16: return launch_stats_q<16>(N, D, X, ldx, MZ, ws_main, nchunks, st);
-        case 32: return launch_stats_q<32>(N, D, X, ldx, MZ, ws_main, nchunks, st);
-        case 64: return launch_stats_q<64>(N, D, X, ldx, MZ, ws_main, nchunks, st);
+        case 8: return launch_stats_q<8>(N, D, X, ldx, MZ, ws_main, nchunks, st, cond);
+        case 16: return launch_stats_q<16>(N, D, X, ldx, MZ, ws_main, nchunks, st, cond);
+        case 32: return launch_stats_q<32>(N, D, X, ldx, MZ, ws_main, nchunks, st, cond);
+        case 64: return launch_stats_q<64>(N, D, X, ldx, MZ, ws_main, nchunks, st, cond);
     }
     return cudaErrorNotSupported;
 }

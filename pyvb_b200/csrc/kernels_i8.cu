@@ -79,10 +79,11 @@ prepare_mask_i8_kernel(long long N, int D, const double *__restrict__ X, long lo
 // one contiguous [224 rows][64 bytes] block.
 __global__ void __launch_bounds__(256)
 pack_g_i8_kernel(int D, int q, const double *__restrict__ Wbar, const double *__restrict__ Wvar,
-                 signed char *__restrict__ GI, double *__restrict__ gscale) {
+                 signed char *__restrict__ GI, double *__restrict__ gscale, double *__restrict__ gl) {
     __shared__ double sh[33];
     const int P = i_tri(q);
     const int c = blockIdx.x;
+    if (c == 0 && threadIdx.x == 0) gl[PYVB_GL_I8BAD] = 0.0;           // guard counter of the Z step that follows (K2 adds to it)
     int i = 0, j = 0;
     if (c < P) unpack_p(c, i, j);
     double mx = 0.0;
@@ -597,11 +598,11 @@ colmax_kernel(long long N, int ldmz, const double *__restrict__ MZ, double *__re
 // a slice of 32 x 17 columns and every (8 / slices)-th row; the warps of a slice are combined in a fixed order.
 constexpr int MZP_KPL = 17;
 __global__ void __launch_bounds__(256)
-mzpart_kernel(long long N, int ldmz, const double *__restrict__ MZ, const double *__restrict__ logdet,
+mzpart_kernel(long long N, int ldmz, int orow, const double *__restrict__ MZ, const double *__restrict__ logdet,
               double *__restrict__ part, long long rows_per_blk) {
     extern __shared__ double mz_sh[];                       // [sums ldmz | maxima ldmz | 4 scalars]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int orow = ldmz - 4, kw = 2 * orow + 4;
+    const int kw = 2 * orow + 4;                            // orow = gw_woff(q) + q: the used columns of a row
     const int ns = (ldmz + 32 * MZP_KPL - 1) / (32 * MZP_KPL);         // column slices: 1, 2 or 4
     const int slice = warp % ns, rg = warp / ns, nrg = 8 / ns;
     const long long r0 = (long long)blockIdx.x * rows_per_blk;
@@ -751,6 +752,49 @@ prepare_maskT_kernel(long long N, int D, long long npad, const double *__restric
                 *reinterpret_cast<unsigned int *>(maskT + ((size_t)kb * D + d0 + row) * 64 + (w & 15) * 4) =
                     *reinterpret_cast<const unsigned int *>(&sh[row * PITCH + h * 64 + (w & 15) * 4]);
         }
+    }
+}
+
+constexpr int CHK_BLOCKS = 16;
+__global__ void __launch_bounds__(128)
+stats_i8_check_kernel(int D, int q, const double *__restrict__ ws, int nchunks, const double *__restrict__ cnt,
+                      const double *__restrict__ zscale, double *__restrict__ guard, double tol) {
+    __shared__ double sh[33];
+    __shared__ int last;
+    const StatLayout L(D, q);
+    const int P = i_tri(q);
+    double sz = 0.0;
+    for (int c = threadIdx.x; c < P; c += 128) sz = fmax(sz, zscale[c]);
+    for (int o = 16; o > 0; o >>= 1) sz = fmax(sz, __shfl_xor_sync(0xffffffffu, sz, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sz;
+    __syncthreads();
+    sz = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3])) * 2.7755575615628914e-17;      // max_c zscale_c * 2^-55
+    double bad = 0.0;
+    for (int d = blockIdx.x * 128 + threadIdx.x; d < D; d += gridDim.x * 128) {
+        double dm = 0.0;
+        for (int i = 0; i < q; ++i) {
+            double t = 0.0;
+            const size_t off = L.t1 + (size_t)d * P + i_tri(i) + i;
+            for (int ch = 0; ch < nchunks; ++ch) t += ws[(size_t)ch * L.len + off];
+            dm = fmax(dm, t);
+        }
+        if (cnt[d] * sz > tol * dm) bad += 1.0;
+    }
+    bad = block_sum(bad, sh);
+    if (threadIdx.x == 0) {
+        guard[8 + blockIdx.x] = bad;
+        __threadfence();
+        const unsigned int done = atomicAdd(reinterpret_cast<unsigned int *>(guard + 2), 1u);
+        last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double *>(guard)[8 + b];
+        guard[0] = t;
+        if (t > 0.0) guard[1] += 1.0;
+        *reinterpret_cast<unsigned int *>(guard + 2) = 0u;
     }
 }
 
@@ -1027,9 +1071,9 @@ cudaError_t launch_prepare_mask_i8(long long N, int D, const double *X, long lon
     return cudaGetLastError();
 }
 
-cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wvar, void *GI, double *gscale,
+cudaError_t launch_pack_g_i8(int D, int q, const double *Wbar, const double *Wvar, void *GI, double *gscale, double *gl,
                              cudaStream_t st) {
-    pack_g_i8_kernel<<<i_nc8(q), 256, 0, st>>>(D, q, Wbar, Wvar, static_cast<signed char *>(GI), gscale);
+    pack_g_i8_kernel<<<i_nc8(q), 256, 0, st>>>(D, q, Wbar, Wvar, static_cast<signed char *>(GI), gscale, gl);
     return cudaGetLastError();
 }
 
@@ -1105,7 +1149,20 @@ int stats_i8_ncols(int q) { return (i_tri(q) + q + 31) & ~31; }
 long long stats_i8_npad(long long N) { return (N + 127) / 128 * 128; }
 size_t stats_i8_digits_bytes(long long N, int q) { return (size_t)stats_i8_ncols(q) * NPL * (size_t)stats_i8_npad(N); }
 size_t stats_i8_maskt_bytes(long long N, int D) { return (size_t)D * (size_t)stats_i8_npad(N) + (size_t)BM * BKB; }
-size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * 2 * ldmz + stats_i8_ncols(q); }
+size_t stats_i8_scratch_len(int q, int ldmz) { return (size_t)CM_BLOCKS * 2 * ldmz + stats_i8_ncols(q) + 8 + CHK_BLOCKS; }
+double *stats_i8_guard(double *scratch, int q, int ldmz) { return scratch + (size_t)CM_BLOCKS * 2 * ldmz + stats_i8_ncols(q); }
+
+// Accuracy guard of the INT8 statistics: T1[d][c] carries at most cnt_d * zscale_c * 2^-55 of fixed-point rounding.  A data
+// dimension whose largest diagonal entry max_i T1[d][ii] (a sum of cnt_d non-negative terms) does not dominate that bound by
+// 1 / tol fails; guard[0] = number of failing dimensions (the conditional DMMA statistics redo the pass when it is > 0).
+// guard: [0] failing dimensions, [1] fall-backs so far, [2] block counter, [8 ...] per-block counts.
+cudaError_t launch_stats_i8_check(int D, int q, const double *ws, int nchunks, const double *xcache, double *scratch,
+                                  int ldmz, double tol, cudaStream_t st) {
+    const int blocks = (D + 127) / 128 < CHK_BLOCKS ? (D + 127) / 128 : CHK_BLOCKS;
+    stats_i8_check_kernel<<<blocks, 128, 0, st>>>(D, q, ws, nchunks, xcache, scratch + (size_t)CM_BLOCKS * 2 * ldmz,
+                                                  stats_i8_guard(scratch, q, ldmz), tol);
+    return cudaGetLastError();
+}
 
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
 // chunks: items = ndb * nct * nchunks a whole number of rounds over 148 CTAs, chunks of >= 32 K steps, <= 2^23 rows
@@ -1148,7 +1205,7 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
     if (N <= 0) return cudaSuccess;
     const int P = i_tri(q), NCZ = stats_i8_ncols(q), nct = NCZ / CT, ndb = (D + BM - 1) / BM;
     const long long npad = stats_i8_npad(N);
-    const int orow = ldmz - 4;
+    const int orow = gw_woff(q) + q;                        // [packed | pad | zbar] columns of an MZ row (K2's partial layout)
     double *pm = scratch, *zscale = scratch + (size_t)CM_BLOCKS * 2 * ldmz;
     if (!(zsums != nullptr && nzblk > 0 && trusted)) {
         if (logdet == nullptr) return cudaErrorInvalidValue;
@@ -1156,7 +1213,7 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
         long long rpb = (N + nblk - 1) / nblk;
         if (rpb < 64) rpb = 64;
         nblk = (int)((N + rpb - 1) / rpb);
-        mzpart_kernel<<<nblk, 256, (size_t)(2 * ldmz + 4) * sizeof(double), st>>>(N, ldmz, MZ, logdet, pm, rpb);
+        mzpart_kernel<<<nblk, 256, (size_t)(2 * ldmz + 4) * sizeof(double), st>>>(N, ldmz, orow, MZ, logdet, pm, rpb);
         zsums = pm;
         nzblk = nblk;
         zkw = 2 * orow + 4;

@@ -84,8 +84,10 @@ template <int Q, bool F32>
 __global__ void __launch_bounds__(32 * KB<Q>::WARPS, KB<Q>::OCC)
 zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, double *__restrict__ Sig,
                       double *__restrict__ logdet, double *gl, double *__restrict__ zsums,
-                      __nv_bfloat16 *__restrict__ MP) {
+                      __nv_bfloat16 *__restrict__ MP, const double *__restrict__ cond, const I8Check chk) {
     using T = KB<Q>;
+    if (cond != nullptr && !(*cond > 0.0)) return;               // conditional (fall-back) launch: nothing to redo
+    __shared__ double s_chk[T::WARPS + 1];
     using IO = KIO<Q, F32>;
     using io_t = typename IO::type;
     constexpr int NB = T::NB, MPW = T::MPW;
@@ -108,7 +110,21 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
     }
     if (T::ZS)
         for (int c = lane; c < T::OROW; c += 32) csum[c] = 0.0;
+    // INT8 guard (kernels.h: I8Check): a row whose largest diagonal entry is below `thr` carries too much fixed-point rounding
+    if (chk.gscale != nullptr) {                                 // kernel-uniform
+        double m = 0.0;
+        for (int c = tid; c < chk.ncols; c += 32 * T::WARPS) m = fmax(m, chk.gscale[c]);
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_chk[warp] = m;
+    }
     __syncthreads();
+    double thr = -1.0;
+    if (chk.gscale != nullptr) {
+        double m = s_chk[0];
+        for (int w = 1; w < T::WARPS; ++w) m = fmax(m, s_chk[w]);
+        thr = gl[PYVB_GL_TAU] * chk.fac * m;
+    }
+    if (cond != nullptr && blockIdx.x == 0 && tid == 0) gl[PYVB_GL_I8FALL] += 1.0;
 
     const int gid = lane >> 2, qd = lane & 3;
     const int oA0 = kb_sw(gid, qd), oA1 = kb_sw(gid, qd + 4);    // row-wise fragment   M[gid][qd + 4h]
@@ -160,6 +176,16 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
             if (Q > 32) eta[m][32 + lane] = e1;
         }
         __syncwarp();
+        if (thr >= 0.0) {                                        // diagonal of qprec, before the factorisation overwrites it
+#pragma unroll
+            for (int m = 0; m < MPW; ++m) {
+                double dm = 0.0;
+#pragma unroll
+                for (int i = lane; i < Q; i += 32) dm = fmax(dm, blk[m][kb_boff(i >> 3, i >> 3) + kb_sw(i & 7, i & 7)]);
+                for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, o));
+                if (lane == 0 && valid[m] && thr > dm) atomicAdd(&gl[PYVB_GL_I8BAD], 1.0);
+            }
+        }
 
         // ---- 1. left-looking block Cholesky; diagonal blocks are replaced by their inverses X_jj
         double mant[MPW];             // prod_k 1/l_kk = mant * 2^esum, renormalised after every diagonal block
@@ -425,7 +451,7 @@ zsolve_blocked_kernel(long long N, typename KIO<Q, F32>::type *__restrict__ MZ, 
 
 template <int Q, bool F32>
 cudaError_t launch_blocked_q(long long N, void *MZ, double *Sig, double *logdet, double *gl, double *zsums, void *MP,
-                             cudaStream_t st) {
+                             cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check()) {
     using T = KB<Q>;
     cudaError_t e = cudaFuncSetAttribute(zsolve_blocked_kernel<Q, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)T::SMEM);
@@ -433,7 +459,7 @@ cudaError_t launch_blocked_q(long long N, void *MZ, double *Sig, double *logdet,
     const int blocks = zsolve_blocked_blocks(N, Q);
     zsolve_blocked_kernel<Q, F32><<<blocks, 32 * T::WARPS, T::SMEM, st>>>(
         N, static_cast<typename KIO<Q, F32>::type *>(MZ), Sig, logdet, gl, T::ZS ? zsums : nullptr,
-        static_cast<__nv_bfloat16 *>(MP));
+        static_cast<__nv_bfloat16 *>(MP), cond, chk);
     return cudaGetLastError();
 }
 
@@ -464,13 +490,13 @@ int zsolve_blocked_kw(int q) {
 }
 
 cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl,
-                                  double *zsums, cudaStream_t st) {
+                                  double *zsums, cudaStream_t st, const double *cond, I8Check chk) {
     if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 8: return launch_blocked_q<8, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
-        case 16: return launch_blocked_q<16, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
-        case 32: return launch_blocked_q<32, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
-        case 64: return launch_blocked_q<64, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
+        case 8: return launch_blocked_q<8, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st, cond, chk);
+        case 16: return launch_blocked_q<16, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st, cond, chk);
+        case 32: return launch_blocked_q<32, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st, cond, chk);
+        case 64: return launch_blocked_q<64, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st, cond, chk);
     }
     return cudaErrorNotSupported;
 }

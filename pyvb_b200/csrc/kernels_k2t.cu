@@ -112,8 +112,11 @@ __device__ __forceinline__ void split3_store(__nv_bfloat16 *dst, size_t plane, f
 template <int Q, bool F32>
 __global__ void __launch_bounds__(32 * TK<Q>::WARPS, 1)
 zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, double *__restrict__ Sig,
-                  double *__restrict__ logdet, double *gl, double *__restrict__ zsums, __nv_bfloat16 *__restrict__ MP) {
+                  double *__restrict__ logdet, double *gl, double *__restrict__ zsums, __nv_bfloat16 *__restrict__ MP,
+                  const double *__restrict__ cond, const I8Check chk) {
     using T = TK<Q>;
+    if (cond != nullptr && !(*cond > 0.0)) return;                 // conditional (fall-back) launch: nothing to redo
+    __shared__ double s_chk[T::WARPS + 1];
     using IO = TIO<Q, F32>;
     using io_t = typename IO::type;
     constexpr int P = T::P, LP = T::LP;
@@ -122,6 +125,22 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
     double *sm = smem_t + (size_t)warp * T::WARP_D;
     double *wsum = smem_t + (size_t)T::WARPS * T::WARP_D + (size_t)warp * T::KW;
 #define EL(e) sm[(e) * LP + lane]
+    // INT8 guard (kernels.h: I8Check): a row whose largest diagonal entry is below `thr` carries too much fixed-point rounding
+    double thr = -1.0;
+    if (chk.gscale != nullptr) {                                   // kernel-uniform
+        double m = 0.0;
+        for (int c = threadIdx.x; c < chk.ncols; c += 32 * T::WARPS) m = fmax(m, chk.gscale[c]);
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) s_chk[warp] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < T::WARPS; ++w) m = fmax(m, s_chk[w]);
+            s_chk[T::WARPS] = gl[PYVB_GL_TAU] * chk.fac * m;
+        }
+        __syncthreads();
+        thr = s_chk[T::WARPS];
+    }
+    if (cond != nullptr && blockIdx.x == 0 && threadIdx.x == 0) gl[PYVB_GL_I8FALL] += 1.0;
     // column sums of the finished rows, kept in registers: packed element lane + 32 u, zbar element lane (if < Q)
     double cs[T::NU], cz = 0.0, s_qld = 0.0, s_ld = 0.0, s_n = 0.0;
     // ... and upper bounds on their maxima of |.| (the scales of the INT8 statistics): the maximum of the high words of
@@ -185,6 +204,12 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
         // ---- every lane factors / inverts ITS matrix.  Register budget: at most two 8 x 8 triangles (72 doubles) live
         //      at a time; PHASE() keeps the compiler from hoisting the next phase's loads over the current one
 #define PHASE() asm volatile("" ::: "memory")
+        if (thr >= 0.0) {
+            double dmax = 0.0;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) dmax = fmax(dmax, EL(t_idx(i, i)));
+            if (lane < nval && thr > dmax) atomicAdd(&gl[PYVB_GL_I8BAD], 1.0);
+        }
         double lp = 1.0;
         if (Q == 16) {
             {   // X00 = chol(A00)^-1 ; L10 = A10 X00^T, row by row, in place (block (1,0): rows 8..15, columns 0..7)
@@ -431,14 +456,15 @@ zsolve_tpm_kernel(long long N, typename TIO<Q, F32>::type *__restrict__ MZ, doub
 
 template <int Q, bool F32>
 cudaError_t launch_tpm_q(long long N, void *MZ, double *Sig, double *logdet, double *gl, double *zsums, void *MP,
-                         cudaStream_t st) {
+                         cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check()) {
     using T = TK<Q>;
     cudaError_t e =
         cudaFuncSetAttribute(zsolve_tpm_kernel<Q, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
     if (e != cudaSuccess) return e;
     const int blocks = zsolve_tpm_blocks(N, Q);
     zsolve_tpm_kernel<Q, F32><<<blocks, 32 * T::WARPS, T::SMEM, st>>>(N, static_cast<typename TIO<Q, F32>::type *>(MZ), Sig,
-                                                                    logdet, gl, zsums, static_cast<__nv_bfloat16 *>(MP));
+                                                                    logdet, gl, zsums, static_cast<__nv_bfloat16 *>(MP),
+                                                                    cond, chk);
     return cudaGetLastError();
 }
 
@@ -455,11 +481,11 @@ int zsolve_tpm_blocks(long long N, int q) {
 int zsolve_tpm_kw(int q) { return q == 8 ? TK<8>::KW : q == 16 ? TK<16>::KW : 0; }
 
 cudaError_t launch_zsolve_tpm(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
-                              cudaStream_t st) {
+                              cudaStream_t st, const double *cond, I8Check chk) {
     if (N <= 0) return cudaSuccess;
     switch (q) {
-        case 8: return launch_tpm_q<8, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
-        case 16: return launch_tpm_q<16, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st);
+        case 8: return launch_tpm_q<8, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st, cond, chk);
+        case 16: return launch_tpm_q<16, false>(N, MZ, Sig, logdet, gl, zsums, nullptr, st, cond, chk);
     }
     return cudaErrorNotSupported;
 }

@@ -26,8 +26,10 @@ from . import _cabi
 import os
 
 from .dist import PeerExchange, allreduce_stats
-from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_F32, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_LEN, GL_NONPD, GL_QA,
-                      GL_QB, GL_TAU, OP_ALPHA, OP_BETA, OP_ELBO, OP_MU, QMAX, StatLayout)
+import functools
+
+from ._layout import (ALGO_AUTO, ALGO_DMMA, ALGO_F32, ALGO_GENERIC, GL_ALPHA, GL_ALQB, GL_ELBO, GL_I8BAD, GL_I8FALL, GL_LEN,
+                      GL_NONPD, GL_QA, GL_QB, GL_TAU, OP_ALPHA, OP_BETA, OP_ELBO, OP_MU, QMAX, StatLayout)
 
 _ALGOS = {"auto": ALGO_AUTO, "generic": ALGO_GENERIC, "dmma": ALGO_DMMA}
 
@@ -38,6 +40,16 @@ def _digamma(x):
         return float(special.digamma(x))
     except Exception:  # pragma: no cover
         return float(torch.special.digamma(torch.tensor(x, dtype=torch.float64)))
+
+
+def _on_device(fn):
+    """Run a method with the engine's GPU as the current CUDA device: the C-ABI launches on the current device, while the
+    tensors and the stream belong to self.device."""
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 def tril_pack_index(q):
@@ -68,13 +80,21 @@ class PlateEngine(object):
         assert precision in ("f64", "f32")
         self.f32 = (precision == "f32")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            self._construct(X, q, mode, alpha0, alpha_mu, a0, b0, ard, ard_a0, ard_b0, P0, m0, algo, keep_sigma,
+                            distributed, row_offset, trace_len)
+
+    def _construct(self, X, q, mode, alpha0, alpha_mu, a0, b0, ard, ard_a0, ard_b0, P0, m0, algo, keep_sigma,
+                   distributed, row_offset, trace_len):
         self.mode, self.q, self.ard = mode, int(q), bool(ard)
         # algo "i8": the mask contraction of the Z step on the INT8 tensor cores (exact, kernels_i8.cu); the rest as "dmma".
         # "auto" picks it when the shape allows (PYVB_I8=0 keeps the all-DMMA path)
         self.use_i8 = (algo == "i8")
         if algo == "i8":
             algo = "dmma"
-        elif algo == "auto" and mode == "B" and precision == "f64" and os.environ.get("PYVB_I8", "1") != "0":
+        elif algo == "auto" and mode == "B" and not self.f32 and os.environ.get("PYVB_I8", "1") != "0":
             self.use_i8 = None                                  # decided below, once D is known
         self.algo = _ALGOS[algo] if isinstance(algo, str) else int(algo)
         self.distributed = bool(distributed)
@@ -231,6 +251,7 @@ class PlateEngine(object):
         self._stats_fresh = False
         self._gw_fresh = False
 
+    @_on_device
     def close(self):
         """Release the peer exchange buffers (collective: every rank must call it)."""
         if self.peers is not None:
@@ -254,6 +275,7 @@ class PlateEngine(object):
         return 0 if t is None else t.data_ptr()
 
     # ------------------------------------------------------------------ state io
+    @_on_device
     def set_state(self, st):
         """Inject state (numpy arrays in the oracle's layout: Sig is (N,q,q), qb scalar ...)."""
         f64, dev = torch.float64, self.device
@@ -287,6 +309,7 @@ class PlateEngine(object):
             self._resplit()
         gl = self.gl.cpu()
         gl[GL_QA] = self.qa
+        gl[GL_NONPD] = 0.0                      # a fresh state: earlier non-PD rows are history
         if "qb" in st:
             gl[GL_QB] = float(st["qb"])
         gl[GL_TAU] = gl[GL_QA] / gl[GL_QB]
@@ -325,6 +348,7 @@ class PlateEngine(object):
         z[0, pp + self.q + 2] = float(self.N)
         self._zsums_valid = True
 
+    @_on_device
     def init_random(self, seed=1234, rank=0):
         """Scale-run initialisation on the device: Wbar ~ N(0,1) (same on every rank),
         Zbar ~ N(0,1) (per-rank stream), Wvar = 1, Sigma = I, mu = 0, qb = 0.5."""
@@ -349,6 +373,7 @@ class PlateEngine(object):
         self.logdet.fill_(1.0)
         self.set_state({"qb": 0.5, "al_qb": np.ones(q)})
 
+    @_on_device
     def set_X(self, X):
         """Replace the (mode B) data shard, e.g. from pinned host memory; invalidates the cached X sums."""
         assert self.mode == "B" and not self.f32
@@ -392,11 +417,21 @@ class PlateEngine(object):
 
     def check(self):
         """Raise LinAlgError if any posterior precision was not positive definite (gaussian.py:118)."""
-        if float(self.gl[GL_NONPD].item()) > 0:
-            raise np.linalg.LinAlgError("posterior precision of %d row(s) is not positive definite"
-                                        % int(self.gl[GL_NONPD].item()))
+        bad = float(self.gl[GL_NONPD].item())
+        if bad > 0:
+            self.gl[GL_NONPD] = 0.0             # reported once; a state injected afterwards starts clean
+            raise np.linalg.LinAlgError("posterior precision of %d row(s) is not positive definite" % int(bad))
+
+    def i8_fallbacks(self):
+        """How often the accuracy guard of the INT8 path sent a step to the FP64 tensor cores: (Z steps, statistics passes)."""
+        z = float(self.gl[GL_I8FALL].item())
+        s = 0.0
+        if getattr(self, "i8_scratch", None) is not None:
+            s = float(self.i8_scratch[int(self.lib.pyvb_stats_i8_guard_offset(self.q)) + 1].item())
+        return int(z), int(s)
 
     # ------------------------------------------------------------------ operators
+    @_on_device
     def _ensure_gw(self):
         if not self._gw_fresh and self.f32:
             rc = self.lib.pyvb_pack_gw_f32(self.D, self.q, self.Wbar.data_ptr(), self.Wvar.data_ptr(),
@@ -409,6 +444,7 @@ class PlateEngine(object):
             _cabi.check(rc, "pyvb_pack_gw_f64")
             self._gw_fresh = True
 
+    @_on_device
     def _ensure_stats(self):
         if self._stats_fresh:
             return
@@ -456,6 +492,7 @@ class PlateEngine(object):
             allreduce_stats(self.stats)          # fallback exchange: NCCL all-reduce
         self._stats_fresh = True
 
+    @_on_device
     def update_W(self, col_lo=0, col_hi=None):
         col_hi = self.q if col_hi is None else col_hi
         self._ensure_stats()
@@ -465,6 +502,7 @@ class PlateEngine(object):
         _cabi.check(rc, "pyvb_wupdate_f64")
         self._gw_fresh = False
 
+    @_on_device
     def update_Z(self, lo=0, hi=None, _chunk_zsums=False):
         hi = self.N if hi is None else hi
         self._stats_fresh = False
@@ -489,6 +527,9 @@ class PlateEngine(object):
         full = (lo == 0 and hi == self.N and self.zsums is not None and self.algo in (ALGO_AUTO, ALGO_DMMA))
         # (_chunk_zsums: iterate_from_host takes the K2 partials of a row chunk for that chunk's statistics)
         zs = self.zsums.data_ptr() if ((full or _chunk_zsums) and self.zsums is not None) else 0
+        if zs and int(self.lib.pyvb_zsums_len(self.N, q)) > self.zsums.numel():
+            # (PYVB_K2 picks the batched-solve kernel per call; its partial layout must be the one this buffer was sized for)
+            raise RuntimeError("the K2 partial buffer was sized for another batched-solve kernel (PYVB_K2 changed?)")
         self._zsums_valid = False
         if self.use_i8 and lo % 128 == 0:                   # (the int8 mask is tiled by 128 rows: other offsets take the DMMA path)
             if not self._mask_valid:                        # the int8 mask follows X (static in mode B)
@@ -514,6 +555,7 @@ class PlateEngine(object):
         self._zsums_valid = full
         self._stats_fresh = False
 
+    @_on_device
     def update_X(self, lo=0, hi=None):
         """Mode A imputation of rows [lo,hi) that are not fully observed; no-op in mode B."""
         if self.mode != "A":
@@ -531,6 +573,7 @@ class PlateEngine(object):
         _cabi.check(rc, "pyvb_impute_f64")
         self._stats_fresh = False
 
+    @_on_device
     def _global(self, ops, elbo_out=0, col_lo=0, col_hi=None):
         self._ensure_stats()
         col_hi = self.q if col_hi is None else col_hi
@@ -584,6 +627,7 @@ class PlateEngine(object):
         self.trace_pos += 1
         return slot
 
+    @_on_device
     def iterate_from_host(self, Xh, nchunks=8):
         """One mode-B sweep whose data shard comes from (pinned) HOST memory: the upload is cut into row chunks on
         a copy stream and the Z step of chunk c (K1 + K2) runs while chunk c+1 is still on the PCIe bus.  The W
@@ -592,14 +636,17 @@ class PlateEngine(object):
         that only the last chunk's work is left when the upload ends.  Returns the trace slot of the bound (no host
         synchronisation)."""
         assert self.mode == "B"
+        assert not self.f32, "iterate_from_host: the FP32 variant keeps X as bf16 planes; use precision='f64'"
         N = self.N
         cur = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         cs = self._copy_stream
-        cs.wait_stream(cur)                      # the previous sweep has finished reading X
+        # first everything that may still read the resident X (stale statistics are rebuilt from it), THEN the copy
+        # stream waits: the upload must not overwrite rows a queued kernel has yet to read
         self.update_W()
         self._ensure_gw()
+        cs.wait_stream(cur)
         self._xcache_valid = False
         self._mask_valid = False
         self._maskT_valid = False
@@ -651,6 +698,8 @@ class PlateEngine(object):
             out.append(llb)
             if verbose:
                 print(niters - i, llb)
+            if not np.isfinite(llb):
+                self.check()                     # a non-PD row poisons the bound: raise at once (gaussian.py:118)
             if llb - old < tol:
                 if verbose:
                     print("Convergence!")

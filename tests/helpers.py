@@ -72,7 +72,7 @@ def w_update_from_stats(stats, D, q, Wbar, mu, tau, alpha):
     W = Wbar.copy()
     Wvar = np.zeros_like(W)
     for i in range(q):
-        prec = alpha + tau * T1[:, i, i]
+        prec = (alpha[i] if np.ndim(alpha) else alpha) + tau * T1[:, i, i]
         m2 = v["Ast"][:, i] - mu * v["Bst"][:, i]
         for j in range(q):
             if j != i:

@@ -10,8 +10,9 @@ from oracle.plate_oracle import PlateOracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def big():
+@pytest.fixture(scope="module", params=["dmma", "auto"])
+def big(request):
+    """The N = 1M engine on the all-DMMA path and on the default path (auto = the INT8 tensor-core path, what bench.py times)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import bench
@@ -19,9 +20,13 @@ def big():
     N, D, q = 1000000, 256, 16
     dev = torch.device("cuda", 0)
     X = bench.make_data(torch, N, D, q, 0.2, 1234, dev)
-    e = PlateEngine(X, q, mode="B", algo="dmma", keep_sigma=False, device=dev)
+    e = PlateEngine(X, q, mode="B", algo=request.param, keep_sigma=False, device=dev)
+    assert e.use_i8 == (request.param == "auto") and e.use_i8_stats == (request.param == "auto")
     e.init_random(seed=4321)
-    return e
+    yield e
+    assert e.i8_fallbacks() == (0, 0)          # normalised data: the accuracy guard never fires
+    del e
+    torch.cuda.empty_cache()
 
 
 def test_fullsize_sweeps_and_determinism(big):
@@ -98,9 +103,90 @@ def test_fullsize_rows_match_oracle_on_a_sample(big):
     # and the statistics layout, on the sample, against the numpy definition
     ref = numpy_stats(Xs, o.Zbar, o.Sig, e.q)
     from pyvb_b200 import PlateEngine
-    small = PlateEngine(Xs, e.q, mode="B", algo="dmma", device=e.X.device)
+    small = PlateEngine(Xs, e.q, mode="B", algo="dmma" if not e.use_i8 else "auto", device=e.X.device)
     small.set_state({"Zbar": o.Zbar, "Sig": o.Sig})
     small._ensure_stats()
+    if small.use_i8_stats:                      # (the first call fills the X-only cache on the DMMA kernels)
+        small._stats_fresh = False
+        small._ensure_stats()
+        assert small.i8_stats_calls == 1
     got = small.stats.cpu().numpy()
     L = small.L
     assert tensor_rel(got[:L.scal], ref[:L.scal]) < 1e-11
+
+
+def test_fullsize_T1_matches_float64_matmul_on_column_blocks(big):
+    """T1 / Bst / Ast of the full 1M rows (K3 of whichever path the fixture runs: its INT8 scales are global column maxima
+    over all N rows) against torch float64 matmuls accumulated over row blocks."""
+    e = big
+    e.update_Z()
+    e._stats_fresh = False
+    e._ensure_stats()
+    v = e.L.views(e.stats)
+    T1 = torch.zeros(e.D, e.P, dtype=torch.float64, device=e.X.device)
+    Bst = torch.zeros(e.D, e.q, dtype=torch.float64, device=e.X.device)
+    Ast = torch.zeros_like(Bst)
+    step = 1 << 17
+    for lo in range(0, e.N, step):
+        x = e.X[lo:lo + step]
+        o = (~torch.isnan(x)).to(torch.float64)
+        x0 = torch.nan_to_num(x, nan=0.0)
+        T1 += o.t() @ e.M2[lo:lo + step]
+        Bst += o.t() @ e.Zbar[lo:lo + step]
+        Ast += x0.t() @ e.Zbar[lo:lo + step]
+    for name, ref in (("T1", T1), ("Bst", Bst), ("Ast", Ast)):
+        got = v[name]
+        row = ((got - ref).abs().amax(1) / ref.abs().amax(1)).max().item()       # per data dimension
+        assert row < 1e-10, (name, row)
+
+
+# ---- the default path at the other two configurations' shapes: BASELINE.json config 3 (one GPU's share of its rows is
+# 1.25M; 160k here) and config 4 (ARD, q = 64), five sweeps against the oracle on a row sample + properties at full N
+@pytest.mark.parametrize("N,D,q,miss,ard", [(160000, 1024, 32, 0.3, False), (60000, 512, 64, 0.3, True)])
+def test_c3_c4_shapes_default_path_sample_rows_match_oracle(N, D, q, miss, ard):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import bench
+    from pyvb_b200 import PlateEngine
+    from oracle.plate_oracle import pack_sym
+    dev = torch.device("cuda", 0)
+    X = bench.make_data(torch, N, D, q, miss, 77, dev)
+    e = PlateEngine(X, q, mode="B", algo="auto", keep_sigma=False, device=dev, ard=ard)
+    assert e.use_i8 and e.use_i8_stats
+    e.init_random(seed=5)
+    for _ in range(3):
+        e.iterate()
+    e.check()
+    # (1) one Z step of the sampled rows against the oracle, from the engine's current globals
+    rng = np.random.RandomState(1)
+    idx = np.sort(rng.choice(N, 1200, replace=False))
+    it = torch.as_tensor(idx, device=dev)
+    Xs = e.X[it].cpu().numpy()
+    st = e.get_state_small()
+    o = PlateOracle(Xs, q, mode="B", ard=ard)
+    o.Wbar, o.Wvar, o.mu = st["Wbar"], st["Wvar"], st["mu"]
+    o.qa, o.qb = st["tau"], 1.0
+    o.update_Z()
+    e.update_Z()
+    z, m2 = e.Zbar[it].cpu().numpy(), e.M2[it].cpu().numpy()
+    ref_m2 = pack_sym(o.M2())
+    assert tensor_rel(z, o.Zbar) < 1e-9 and tensor_rel(m2, ref_m2) < 1e-9
+    rowerr = np.max(np.abs(m2 - ref_m2), axis=1) / np.max(np.abs(ref_m2), axis=1)
+    assert rowerr.max() < 1e-9, rowerr.max()                                       # per row, not only tensor-wise
+    assert tensor_rel(0.5 / e.logdet[it].cpu().numpy(), o.qldZ) < 1e-9
+    # (2) the statistics of ALL rows against float64 matmuls, per data dimension
+    e._stats_fresh = False
+    e._ensure_stats()
+    v = e.L.views(e.stats)
+    o_ = (~torch.isnan(e.X)).to(torch.float64)
+    T1 = o_.t() @ e.M2
+    Ast = torch.nan_to_num(e.X, nan=0.0).t() @ e.Zbar
+    assert ((v["T1"] - T1).abs().amax(1) / T1.abs().amax(1)).max().item() < 1e-10
+    assert ((v["Ast"] - Ast).abs().amax(1) / Ast.abs().amax(1)).max().item() < 1e-10
+    # (3) the W update from those statistics against its numpy definition
+    from helpers import w_update_from_stats
+    gl = e.get_state_small()
+    Wref, Wvref = w_update_from_stats(e.stats.cpu().numpy(), D, q, gl["Wbar"], gl["mu"], gl["tau"], gl["alpha"])
+    e.update_W()
+    assert tensor_rel(e.Wbar.cpu().numpy(), Wref) < 1e-9 and tensor_rel(e.Wvar.cpu().numpy(), Wvref) < 1e-9
+    assert e.i8_fallbacks() == (0, 0)

@@ -146,3 +146,101 @@ def test_i8_rejects_unsupported_shape(eng):
     X = synth_pca(40, 48, 16, 0.1, seed=1)
     with pytest.raises(ValueError):
         eng(X, 16, mode="B", algo="i8")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Dynamic range: the fixed point of the INT8 kernels is relative to the COLUMN maximum (of G over the data dimensions, of
+# the MZ columns over the rows).  An un-normalised feature (one ROW of W on another scale) or outlier data rows leave the
+# rows / dimensions that do not see them with an absolute error of scale * 2^-55 in a result of ordinary size.  The default
+# path (algo="auto") must stay within 1e-9 PER ROW there: the guard sends such steps to the FP64 tensor cores.
+def _per_row_rel(a, b):
+    a = np.asarray(a).reshape(a.shape[0], -1)
+    b = np.asarray(b).reshape(b.shape[0], -1)
+    return np.max(np.abs(a - b), axis=1) / np.maximum(np.max(np.abs(b), axis=1), 1e-300)
+
+
+@pytest.mark.parametrize("s", [1.0, 30.0, 1e4, 1e6])
+@pytest.mark.parametrize("shape", [(2000, 128, 16), (900, 192, 32)])
+def test_auto_path_is_row_accurate_with_an_unnormalised_feature(eng, shape, s):
+    N, D, q = shape
+    X = synth_pca(N, D, q, 0.3, seed=21)
+    X[:, 9] *= s                                   # feature 9 lives on another scale ...
+    init = rand_init(N, D, q, seed=4)
+    init["Wbar"][9] *= s                           # ... and so does its row of W
+    o = PlateOracle(X, q, mode="B")
+    o.load_state(init)
+    e = eng(X, q, mode="B", algo="auto")
+    assert e.use_i8 and e.use_i8_stats
+    e.set_state(init)
+    e._ensure_stats()
+    o.update_Z(); e.update_Z()
+    st = e.get_state()
+    assert _per_row_rel(st["Sig"], o.Sig).max() < 1e-9, (shape, s, _per_row_rel(st["Sig"], o.Sig).max())
+    assert _per_row_rel(st["Zbar"], o.Zbar).max() < 1e-9, (shape, s)
+    zf, _ = e.i8_fallbacks()
+    assert (zf >= 1) == (s >= 1e4), (s, zf)        # the guard fires exactly where the hazard is
+    for it in range(3):                            # and whole sweeps stay on the oracle
+        ref, got = o.iterate(), e.iterate()
+        assert abs(got - ref) <= TOL * abs(ref), (shape, s, it, got, ref)
+    st = e.get_state()
+    assert _per_row_rel(st["Wbar"], o.Wbar).max() < 1e-9 and _per_row_rel(st["Sig"], o.Sig).max() < 1e-9
+    e.check()
+
+
+@pytest.mark.parametrize("s", [1.0, 1e4])
+def test_auto_path_is_accurate_per_dimension_with_outlier_rows(eng, s):
+    N, D, q = 3000, 128, 16
+    X = synth_pca(N, D, q, 0.3, seed=8)
+    X[:6] *= s                                     # six outlier rows ...
+    X[:6, :20] = np.nan                            # ... which the first 20 data dimensions never see
+    init = rand_init(N, D, q, seed=9)
+    o = PlateOracle(X, q, mode="B")
+    o.load_state(init)
+    e = eng(X, q, mode="B", algo="auto")
+    e.set_state(init)
+    e._ensure_stats()
+    o.update_Z(); e.update_Z()
+    e._stats_fresh = False
+    e._ensure_stats()
+    from helpers import numpy_stats
+    ref = e.L.views(numpy_stats(X, o.Zbar, o.Sig, q))
+    got = e.L.views(e.stats.cpu().numpy())
+    for k in ("T1", "Bst", "Ast"):
+        assert _per_row_rel(got[k], ref[k]).max() < 1e-9, (k, s, _per_row_rel(got[k], ref[k]).max())
+    _, sf = e.i8_fallbacks()
+    assert (sf >= 1) == (s >= 1e4), (s, sf)
+    for it in range(3):
+        r, g = o.iterate(), e.iterate()
+        assert abs(g - r) <= TOL * abs(r), (s, it, g, r)
+    assert _per_row_rel(e.get_state()["Wbar"], o.Wbar).max() < 1e-9
+    e.check()
+
+
+def test_forced_fallback_reproduces_the_dmma_path(eng):
+    """PYVB_I8_GUARD=force (read once per process, hence the subprocess) makes every guard fire: the conditional launches must
+    then leave exactly what the all-DMMA path computes (up to the order of the chunk sums of the statistics)."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, torch, sys
+        sys.path.insert(0, %r)
+        from pyvb_b200 import PlateEngine
+        from oracle.plate_oracle import synth_pca
+        X = synth_pca(1500, 128, 32, 0.3, seed=1)
+        ed, ei = PlateEngine(X, 32, mode="B", algo="dmma"), PlateEngine(X, 32, mode="B", algo="auto")
+        for e in (ed, ei):
+            e.init_random(seed=3)
+            for _ in range(3):
+                e.iterate()
+        assert ei.i8_fallbacks() == (3, 3), ei.i8_fallbacks()
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        assert rel(ei.MZ, ed.MZ) < 1e-11 and rel(ei.Wbar, ed.Wbar) < 1e-11 and rel(ei.trace[:3], ed.trace[:3]) < 1e-11
+        e2 = PlateEngine(X, 32, mode="B", algo="auto")          # one Z step from the same state: the rows are bit-identical
+        e2.set_state(ed.get_state()); ed.set_state(ed.get_state())
+        e2._ensure_stats(); ed._ensure_stats()
+        e2.update_Z(); ed.update_Z()
+        assert torch.equal(e2.MZ, ed.MZ) and torch.equal(e2.logdet, ed.logdet)
+        print("forced ok")
+    """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, PYVB_I8_GUARD="force")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "forced ok" in r.stdout, r.stdout + r.stderr

@@ -77,3 +77,48 @@ def test_result_is_within_the_fixed_point_bound_of_the_true_product(shape):
     f64 = tau * (mask.astype(np.float64) @ G)
     assert np.max(np.abs(got - ref)) <= np.max(np.abs(f64 - ref)) + np.max(bound)
     assert np.all(got[0] == 0.0)                                        # an all-missing row contributes nothing
+
+
+@pytest.mark.parametrize("s", [1.0, 30.0, 1e3, 1e4, 1e6])
+def test_guard_flags_every_row_whose_fixed_point_error_matters(s):
+    """One data dimension of W scaled by s (an un-normalised feature): rows that do not observe it keep an absolute error of
+    ~ s^2 2^-55 in a qprec of size O(D).  The guard (restated in i8_oracle.zstep_guard_rows) must flag every row whose error
+    exceeds 1e-10 of its largest diagonal entry, and must leave normalised data (s = 1) alone."""
+    from oracle.i8_oracle import zstep_guard_rows
+    rng = np.random.RandomState(5)
+    N, D, q, tau = 300, 128, 6, 20.0
+    W, Wv = rng.randn(D, q), np.full((D, q), 1e-3)
+    W[7] *= s
+    ii, jj = np.tril_indices(q)
+    G = W[:, ii] * W[:, jj] + np.where(ii == jj, Wv[:, ii], 0.0)
+    mask = rng.rand(N, D) > 0.3
+    P0 = np.eye(q)[ii, jj][None, :]
+    got = mask_contract_i8(mask, G, tau=tau, add=P0)
+    ref = (P0 + tau * (mask.astype(np.longdouble) @ G.astype(np.longdouble))).astype(np.float64)
+    dmax = ref[:, ii == jj].max(1)
+    err = np.max(np.abs(got - ref), axis=1) / dmax                 # per row, max norm
+    flagged = zstep_guard_rows(dmax, G, tau, D)
+    assert np.all(flagged | (err <= 1e-10)), (s, float(err[~flagged].max()))
+    if s <= 30.0:
+        assert not flagged.any()                                     # moderate ranges stay on the INT8 path
+    if s >= 1e4:
+        assert flagged.any() and err.max() > (1e-9 if s >= 1e5 else 1e-10)   # the hazard is real: unguarded it breaks 1e-9 per row
+
+
+def test_stats_guard_flags_dimensions_hidden_from_outlier_rows():
+    from oracle.i8_oracle import stats_guard_dims
+    rng = np.random.RandomState(2)
+    N, D, q = 4000, 32, 4
+    Z = rng.randn(N, q)
+    Z[:5] *= 1e5                                                     # outlier rows
+    ii, jj = np.tril_indices(q)
+    M2 = Z[:, ii] * Z[:, jj] + np.where(ii == jj, 0.1, 0.0)
+    mask = rng.rand(N, D) > 0.3
+    mask[:5, :8] = False                                             # dimensions 0..7 do not see the outliers
+    got = mask_contract_i8(mask.T, M2)
+    ref = (mask.T.astype(np.longdouble) @ M2.astype(np.longdouble)).astype(np.float64)
+    dmax = ref[:, ii == jj].max(1)
+    err = np.max(np.abs(got - ref), axis=1) / dmax
+    flagged = stats_guard_dims(dmax, mask.sum(0), M2)
+    assert np.all(flagged | (err <= 1e-10))
+    assert flagged[:8].all() and not flagged[8:].any()
