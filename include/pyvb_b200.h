@@ -237,7 +237,8 @@ int pyvb_zstep_i8_f64(long long N, int D, int q, const double *X, long long ldx,
  * treats as optional: xcache (valid: the X-only sums of an earlier pyvb_stats_f64 call).  zsums: the K2 partials of the
  * Z step that produced these rows, or NULL (then logdet [N] is read and the MZ column sums take one more pass).
  *   maskT  pyvb_stats_i8_maskt_bytes(N, D) bytes, [n / 64][D][64] int8: pyvb_prepare_maskt_i8 (once per data set)
- *   ZI     pyvb_stats_i8_digits_bytes(N, q) bytes, scratch pyvb_stats_i8_scratch_len(q) doubles: per-call scratch
+ *   ZI     pyvb_stats_i8_digits_bytes(N, q) bytes, scratch pyvb_stats_i8_scratch_len(q) doubles: per-call scratch; the
+ *          caller ZEROES scratch once (its last 8 doubles are the guard's counters, kept from call to call)
  *   ws     pyvb_stats_i8_workspace_bytes(N, D, q)
  * Accuracy guard, as for pyvb_zstep_i8_f64: a data dimension d with cnt_d * max_c zscale_c * 2^-55 > 2^-38 * max_i T1[d][ii]
  * (outlier rows that d does not observe) sends the whole pass to the FP64 tensor cores, before the exchange. */

@@ -444,7 +444,7 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
         // FP64 tensor cores (one conditional launch that exits at once otherwise); both before the exchange
         double *guard = stats_i8_guard(scratch, q, (int)ldmz);
         e = launch_stats_i8_check(D, q, (const double *)ws, nch, xcache, scratch, (int)ldmz,
-                                  i8_guard_mode() == 2 ? 1e300 : I8_TOL, st);
+                                  i8_guard_mode() == 2 ? 0.0 : I8_TOL, st);      // (tol = 0: every observed dimension fails)
         if (e == cudaSuccess) e = launch_stats_dmma(N, D, q, X, ldx, MZ, (double *)ws, nch, st, guard);
         if (e != cudaSuccess) return cuda_fail(e, "stats_i8 (guard)");
     }

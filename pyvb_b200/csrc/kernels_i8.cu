@@ -755,46 +755,44 @@ prepare_maskT_kernel(long long N, int D, long long npad, const double *__restric
     }
 }
 
-constexpr int CHK_BLOCKS = 16;
+constexpr int CHK_BLOCKS = 0;                             // (the guard block needs no per-CTA storage)
+// one CTA per data dimension d: warp w sums T1[d][ii] over the chunks for i = w, w + 4, ... (lanes over chunks)
 __global__ void __launch_bounds__(128)
 stats_i8_check_kernel(int D, int q, const double *__restrict__ ws, int nchunks, const double *__restrict__ cnt,
                       const double *__restrict__ zscale, double *__restrict__ guard, double tol) {
-    __shared__ double sh[33];
-    __shared__ int last;
+    __shared__ double sh[8];
     const StatLayout L(D, q);
-    const int P = i_tri(q);
+    const int P = i_tri(q), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x;
     double sz = 0.0;
     for (int c = threadIdx.x; c < P; c += 128) sz = fmax(sz, zscale[c]);
-    for (int o = 16; o > 0; o >>= 1) sz = fmax(sz, __shfl_xor_sync(0xffffffffu, sz, o));
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sz;
-    __syncthreads();
-    sz = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3])) * 2.7755575615628914e-17;      // max_c zscale_c * 2^-55
-    double bad = 0.0;
-    for (int d = blockIdx.x * 128 + threadIdx.x; d < D; d += gridDim.x * 128) {
-        double dm = 0.0;
-        for (int i = 0; i < q; ++i) {
-            double t = 0.0;
-            const size_t off = L.t1 + (size_t)d * P + i_tri(i) + i;
-            for (int ch = 0; ch < nchunks; ++ch) t += ws[(size_t)ch * L.len + off];
-            dm = fmax(dm, t);
-        }
-        if (cnt[d] * sz > tol * dm) bad += 1.0;
+    double dm = 0.0;
+    for (int i = warp; i < q; i += 4) {
+        const size_t off = L.t1 + (size_t)d * P + i_tri(i) + i;
+        double t = 0.0;
+        for (int ch = lane; ch < nchunks; ch += 32) t += ws[(size_t)ch * L.len + off];
+        dm = fmax(dm, warp_sum(t));
     }
-    bad = block_sum(bad, sh);
+    for (int o = 16; o > 0; o >>= 1) sz = fmax(sz, __shfl_xor_sync(0xffffffffu, sz, o));
+    if (lane == 0) {
+        sh[warp] = sz;
+        sh[4 + warp] = dm;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        guard[8 + blockIdx.x] = bad;
+        sz = fmax(fmax(sh[0], sh[1]), fmax(sh[2], sh[3])) * 2.7755575615628914e-17;      // max_c zscale_c * 2^-55
+        dm = fmax(fmax(sh[4], sh[5]), fmax(sh[6], sh[7]));
+        if (cnt[d] * sz > tol * dm) atomicAdd(guard + 3, 1.0);
         __threadfence();
         const unsigned int done = atomicAdd(reinterpret_cast<unsigned int *>(guard + 2), 1u);
-        last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence();
-        double t = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) t += reinterpret_cast<volatile double *>(guard)[8 + b];
-        guard[0] = t;
-        if (t > 0.0) guard[1] += 1.0;
-        *reinterpret_cast<unsigned int *>(guard + 2) = 0u;
+        if (done == gridDim.x - 1) {           // the last CTA publishes the verdict and re-arms the counters
+            __threadfence();
+            const double t = *reinterpret_cast<volatile double *>(guard + 3);
+            guard[0] = t;
+            if (t > 0.0) guard[1] += 1.0;
+            guard[3] = 0.0;
+            *reinterpret_cast<unsigned int *>(guard + 2) = 0u;
+        }
     }
 }
 
@@ -1155,11 +1153,10 @@ double *stats_i8_guard(double *scratch, int q, int ldmz) { return scratch + (siz
 // Accuracy guard of the INT8 statistics: T1[d][c] carries at most cnt_d * zscale_c * 2^-55 of fixed-point rounding.  A data
 // dimension whose largest diagonal entry max_i T1[d][ii] (a sum of cnt_d non-negative terms) does not dominate that bound by
 // 1 / tol fails; guard[0] = number of failing dimensions (the conditional DMMA statistics redo the pass when it is > 0).
-// guard: [0] failing dimensions, [1] fall-backs so far, [2] block counter, [8 ...] per-block counts.
+// guard: [0] failing dimensions of the last call, [1] fall-backs so far, [2] CTA counter, [3] running count (all zero at first).
 cudaError_t launch_stats_i8_check(int D, int q, const double *ws, int nchunks, const double *xcache, double *scratch,
                                   int ldmz, double tol, cudaStream_t st) {
-    const int blocks = (D + 127) / 128 < CHK_BLOCKS ? (D + 127) / 128 : CHK_BLOCKS;
-    stats_i8_check_kernel<<<blocks, 128, 0, st>>>(D, q, ws, nchunks, xcache, scratch + (size_t)CM_BLOCKS * 2 * ldmz,
+    stats_i8_check_kernel<<<D, 128, 0, st>>>(D, q, ws, nchunks, xcache, scratch + (size_t)CM_BLOCKS * 2 * ldmz,
                                                   stats_i8_guard(scratch, q, ldmz), tol);
     return cudaGetLastError();
 }

@@ -199,7 +199,8 @@ class PlateEngine(object):
                 self.npad = int(self.lib.pyvb_stats_i8_npad(N))
                 self.maskT = torch.empty(int(self.lib.pyvb_stats_i8_maskt_bytes(N, D)), dtype=torch.int8, device=dev)
                 self.ZI = torch.empty(int(self.lib.pyvb_stats_i8_digits_bytes(N, q)), dtype=torch.int8, device=dev)
-                self.i8_scratch = torch.empty(int(self.lib.pyvb_stats_i8_scratch_len(q)), dtype=f64, device=dev)
+                # (zeros: the tail of the scratch is the guard block -- counters of the accuracy check -- see the header)
+                self.i8_scratch = torch.zeros(int(self.lib.pyvb_stats_i8_scratch_len(q)), dtype=f64, device=dev)
                 self.ws_bytes = max(self.ws_bytes, int(self.lib.pyvb_stats_i8_workspace_bytes(N, D, q)))
             except torch.cuda.OutOfMemoryError:          # the digit planes are 7 bytes per MZ entry: DMMA statistics instead
                 self.maskT = self.ZI = self.i8_scratch = None
