@@ -301,6 +301,13 @@ int pyvb_lds_max_len(void);
 int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A, double *Avar,
                          double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb, double alpha0,
                          double a0, double b0, int niters, double *status, void *stream);
+/* The same with KNOWN entries of A (examples/LDS_knowns_in_A.py:72-74: `As[i].observe(...)` with NaN = unknown makes the
+ * column a partially observed Gaussian, nodes/gaussian.py:125-134; with the diagonal posterior covariance of an hstack
+ * column that conditioning clamps the known entries to their values with zero variance after every column update).
+ *   Aknown [B][q][q] (row k, column i), NaN = free; NULL = nothing known (= pyvb_lds_iterate_f64). */
+int pyvb_lds_iterate_known_f64(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A, double *Avar,
+                               double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb, const double *Aknown,
+                               double alpha0, double a0, double b0, int niters, double *status, void *stream);
 
 /* Measurement utility (not part of the hot path): `iters` dependent rounds of 8 independent
  * DMMA.8x8x4 per warp on `blocks` x 256 threads; flops = blocks * 8 warps * iters * 8 * 512.

@@ -81,10 +81,16 @@ def snapshot(m, prefix, out):
     out[prefix + "max_offdiag"] = np.float64(offd)
 
 
-def run(pyvb, Y, q, seed, niters):
+def run(pyvb, Y, q, seed, niters, known=None):
     np.random.seed(seed)
     m = build(pyvb, Y, q)
+    if known is not None:              # examples/LDS_knowns_in_A.py:72-74: observe the known entries of A's columns
+        for i, a in enumerate(m["As"]):
+            if not np.all(np.isnan(known[:, i])):
+                a.observe(known[:, i].reshape(q, 1))
     out = {"Y": Y, "q": np.int64(q), "niters": np.int64(niters)}
+    if known is not None:
+        out["A_known"] = known
     snapshot(m, "init_", out)
     Xs = m["Xs"]
     for it in range(niters):
@@ -113,5 +119,24 @@ def main():
               "Qb", out["it%d_Qb" % (niters - 1)][:3])
 
 
+def main_known():
+    """lds_known.npz: q = 2 with A[0][0] = 1 and A[0][1] = dt known (the shipped LDS_knowns_in_A.py pattern), and
+    lds_known_b.npz: q = 3 with a known entry in every column, one column fully known but one entry."""
+    make_ref(quiet=True)
+    pyvb = import_ref()
+    assert pyvb is not None, "reference not available"
+    nan = np.nan
+    for name, (q, d, T), seed, known in [
+            ("lds_known", (2, 5, 25), 3, np.array([[1.0, 0.05], [nan, nan]])),
+            ("lds_known_b", (3, 4, 14), 4, np.array([[0.9, nan, 0.1], [nan, 0.8, nan], [nan, 0.2, nan]]))]:
+        Y = simulate(q, d, T, np.random.RandomState(200 + seed))
+        out = run(pyvb, Y, q, seed, 6, known=known)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+        print(name, "A after 6 iterations", out["it5_A"].round(4).tolist())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "known":
+        main_known()
+    else:
+        main()

@@ -80,18 +80,28 @@ def make_ref(src=DEFAULT_SRC, dst=DEFAULT_DST, quiet=False):
     return True
 
 
+REF_MODULE = "pyvb_literal_reference"
+
+
 def import_ref():
-    """Import the translated reference as module ``pyvb`` (or return None)."""
-    root = os.path.join(HERE, "_ref")
-    if not os.path.isfile(os.path.join(root, "pyvb", "__init__.py")):
+    """Import the translated reference (or return None).  It is loaded under the module name ``pyvb_literal_reference`` --
+    NOT ``pyvb``: the repo's own top-level ``pyvb`` package is the drop-in alias of pyvb_b200, and the two must be able to
+    live in one process (the parity tests build the same graph with both)."""
+    pkg = os.path.join(HERE, "_ref", "pyvb")
+    if not os.path.isfile(os.path.join(pkg, "__init__.py")):
         return None
-    import importlib
+    if REF_MODULE in sys.modules:
+        return sys.modules[REF_MODULE]
+    import importlib.util
     import warnings
 
     warnings.simplefilter("ignore")
-    if root not in sys.path:
-        sys.path.insert(0, root)
-    return importlib.import_module("pyvb")
+    spec = importlib.util.spec_from_file_location(REF_MODULE, os.path.join(pkg, "__init__.py"),
+                                                  submodule_search_locations=[pkg])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[REF_MODULE] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
 if __name__ == "__main__":

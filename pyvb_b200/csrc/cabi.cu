@@ -544,6 +544,18 @@ int pyvb_lds_iterate_f64(int B, int T, int q, int d, const double *Y, double *X,
     return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "lds_iterate");
 }
 
+int pyvb_lds_iterate_known_f64(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A, double *Avar,
+                               double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb, const double *Aknown,
+                               double alpha0, double a0, double b0, int niters, double *status, void *stream) {
+    ARG(B >= 0 && q >= 1 && q <= 8 && d >= 1 && d <= 8 && niters >= 0, "B, q (<= 8), d (<= 8), niters");
+    ARG(T >= 3 && T <= pyvb_lds_max_len(), "T (3 .. pyvb_lds_max_len())");
+    if (B == 0) return PYVB_OK;
+    ARG(Y && X && Xcov3 && A && Avar && C && Cvar && Qa && Qb && Ra && Rb && status, "null pointer");
+    cudaError_t e = launch_lds_iterate(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb, alpha0, a0, b0, niters,
+                                       status, (cudaStream_t)stream, Aknown);
+    return e == cudaSuccess ? PYVB_OK : cuda_fail(e, "lds_iterate");
+}
+
 int pyvb_bench_umma(int blocks, int iters, int n, int kind, int mode, const void *src, long long *clk_out, void *stream) {
     ARG(blocks >= 1 && blocks <= 148 && iters >= 1 && n >= 16 && n <= 256 && (n % 16) == 0 && (kind == 0 || kind == 1) && clk_out,
         "arguments");

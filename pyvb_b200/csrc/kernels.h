@@ -140,7 +140,8 @@ cudaError_t launch_stats_x_dmma(long long N, int D, int q, const double *X, long
 size_t lds_smem_bytes(int T, int d);
 cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
                                double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
-                               double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st);
+                               double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st,
+                               const double *Aknown = nullptr);
 
 cudaError_t launch_bench_dmma(int blocks, int iters, double *scratch, cudaStream_t st);
 cudaError_t launch_bench_umma(int blocks, int iters, int n, int kind, int mode, const void *src, long long *clk_out,

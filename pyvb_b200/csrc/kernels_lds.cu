@@ -27,14 +27,15 @@ constexpr int LW = 4;                       // warps (sequences) per CTA
 // per-warp shared memory (doubles): xs [(T + 2)][8] (one zero row before and after), ys [T][d] (+ 8: the padded
 // columns of the last row are read with zero coefficients), then the small arrays
 __host__ __device__ inline size_t lds_warp_doubles(int T, int d) {
-    return (size_t)(T + 2) * 8 + (((size_t)T * d + 8 + 1) & ~(size_t)1) + 64 * 13;
+    return (size_t)(T + 2) * 8 + (((size_t)T * d + 8 + 1) & ~(size_t)1) + 64 * 14;
 }
 
 __global__ void __launch_bounds__(32 * LW)
 lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, double *__restrict__ X,
                    double *__restrict__ Xcov3, double *__restrict__ A, double *__restrict__ Avar, double *__restrict__ C,
                    double *__restrict__ Cvar, double *__restrict__ Qa, double *__restrict__ Qb, double *__restrict__ Ra,
-                   double *__restrict__ Rb, double alpha0, double a0, double b0, int niters, double *status) {
+                   double *__restrict__ Rb, double alpha0, double a0, double b0, int niters, double *status,
+                   const double *__restrict__ Aknown) {
     extern __shared__ __align__(16) double smem_l[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, qd = lane & 3;
@@ -47,6 +48,7 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
     double *tmp = Sg + 192;                                 // [64]
     double *sSA = tmp + 64, *sSC = sSA + 64, *sXX1 = sSC + 64, *sYX = sXX1 + 64;
     double *qbar = sYX + 64, *rbar = qbar + 8, *yy = rbar + 8, *xx0 = yy + 8;   // [8] each
+    double *pK = xx0 + 8;                                   // [k][i]: known entries of A (NaN = free), examples/LDS_knowns_in_A.py:72-74
 
     for (int b = blockIdx.x * LW + warp; b < B; b += gridDim.x * LW) {
         // ---- load the sequence and its parameters (padded to 8 x 8)
@@ -66,6 +68,10 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
             pC[(i / q) * 8 + (i % q)] = C[(size_t)b * d * q + i];
             pCv[(i / q) * 8 + (i % q)] = Cvar[(size_t)b * d * q + i];
         }
+        for (int i = lane; i < 64; i += 32) pK[i] = __longlong_as_double(0x7ff8000000000000LL);
+        __syncwarp();
+        if (Aknown != nullptr)
+            for (int i = lane; i < q * q; i += 32) pK[(i / q) * 8 + (i % q)] = Aknown[(size_t)b * q * q + i];
         double qb_l = (lane < q) ? Qb[(size_t)b * q + lane] : 1.0;            // lane k: Q row k; lane 8 + k: R row k
         double qa_l = (lane < q) ? Qa[(size_t)b * q + lane] : 1.0;
         if (lane >= 8 && lane < 8 + d) {
@@ -221,6 +227,13 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
                                 if (j != i) m2 = fma(-S[i * 8 + j], a[j], m2);
                             a[i] = lam * m2 / prec;
                             pv[k * 8 + i] = 1.0 / prec;
+                            // a partially observed column (Gaussian.update, gaussian.py:125-134) with a diagonal posterior
+                            // covariance: the known entries are clamped (value, zero variance), the others are untouched
+                            const double kv = isA ? pK[k * 8 + i] : __longlong_as_double(0x7ff8000000000000LL);
+                            if (kv == kv) {
+                                a[i] = kv;
+                                pv[k * 8 + i] = 0.0;
+                            }
                         }
                     }
                     double quad = 0.0, lin = 0.0;
@@ -277,7 +290,8 @@ size_t lds_smem_bytes(int T, int d) { return (size_t)LW * lds_warp_doubles(T, d)
 
 cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
                                double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
-                               double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st) {
+                               double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st,
+                               const double *Aknown) {
     if (B <= 0 || niters <= 0) return cudaSuccess;
     const size_t smem = lds_smem_bytes(T, d);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
@@ -289,7 +303,7 @@ cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, doub
     long long blocks = ((long long)B + LW - 1) / LW;
     if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
     lds_iterate_kernel<<<(unsigned)blocks, 32 * LW, smem, st>>>(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb,
-                                                               alpha0, a0, b0, niters, status);
+                                                               alpha0, a0, b0, niters, status, Aknown);
     return cudaGetLastError();
 }
 

@@ -15,7 +15,7 @@ from . import _cabi
 class LDSEngine(object):
     KEYS = ("A", "Avar", "C", "Cvar", "Qa", "Qb", "Ra", "Rb", "X")
 
-    def __init__(self, Y, q, alpha0=1e-3, a0=1e-3, b0=1e-3, device=None):
+    def __init__(self, Y, q, alpha0=1e-3, a0=1e-3, b0=1e-3, device=None, A_known=None):
         if not torch.cuda.is_available():
             raise RuntimeError("pyvb_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _cabi.lib()
@@ -43,6 +43,14 @@ class LDSEngine(object):
         self.X = torch.zeros(B, T, q, dtype=f64, device=dev)
         self.Xcov3 = torch.zeros(B, 3, q, q, dtype=f64, device=dev)
         self.status = torch.zeros(1, dtype=f64, device=dev)
+        # known entries of A (examples/LDS_knowns_in_A.py:72-74), NaN = free; (q, q) is shared by all sequences
+        self.A_known = None
+        if A_known is not None:
+            ak = torch.as_tensor(np.asarray(A_known, dtype=np.float64))
+            if ak.dim() == 2:
+                ak = ak[None].expand(B, q, q)
+            assert tuple(ak.shape) == (B, q, q)
+            self.A_known = ak.to(device=dev, dtype=f64).contiguous()
 
     def init_random(self, seed=0):
         g = torch.Generator(device=self.device)
@@ -72,12 +80,14 @@ class LDSEngine(object):
 
     def iterate(self, niters=1):
         """`niters` iterations of the reference's sweep (Linear_Dynamic_System.py:69-76) for every sequence."""
-        p = lambda t: t.data_ptr()
-        rc = self.lib.pyvb_lds_iterate_f64(self.B, self.T, self.q, self.d, p(self.Y), p(self.X), p(self.Xcov3), p(self.A),
-                                           p(self.Avar), p(self.C), p(self.Cvar), p(self.Qa), p(self.Qb), p(self.Ra),
-                                           p(self.Rb), self.alpha0, self.a0, self.b0, int(niters), p(self.status),
-                                           torch.cuda.current_stream(self.device).cuda_stream)
-        _cabi.check(rc, "pyvb_lds_iterate_f64")
+        p = lambda t: 0 if t is None else t.data_ptr()
+        with torch.cuda.device(self.device):
+            rc = self.lib.pyvb_lds_iterate_known_f64(self.B, self.T, self.q, self.d, p(self.Y), p(self.X), p(self.Xcov3),
+                                                     p(self.A), p(self.Avar), p(self.C), p(self.Cvar), p(self.Qa), p(self.Qb),
+                                                     p(self.Ra), p(self.Rb), p(self.A_known), self.alpha0, self.a0, self.b0,
+                                                     int(niters), p(self.status),
+                                                     torch.cuda.current_stream(self.device).cuda_stream)
+        _cabi.check(rc, "pyvb_lds_iterate_known_f64")
 
     def check(self):
         n = float(self.status.item())

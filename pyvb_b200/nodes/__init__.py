@@ -3,11 +3,16 @@
 Same names, constructor signatures, attributes and error conventions as the reference, so that
 examples/PCA_missing_data.py:31-45 runs unmodified.  The objects only *describe* the graph and hold
 the random initial state (drawn from the global numpy stream in the reference's order, so a seeded
-script gets the reference's initialisation).  All arithmetic runs on the GPU: the first
+script gets the reference's initialisation).  All updates run on the GPU: the first
 ``update()`` / ``log_lower_bound()`` / ``Network.learn()`` compiles the graph into a plate
 (``pyvb_b200.plate``) backed by the CUDA engine, after which ``qmu``/``qcov``/``qa``/``qb`` are
-views of device state.  Graphs outside the VB-PCA pattern raise NotImplementedError -- there is
-no CPU message-passing fallback.
+views of device state.  Graphs outside the compiled patterns raise NotImplementedError -- there is
+no CPU message-passing fallback for ``update()``.
+
+The message getters (``pass_up_m1_m2``, ``pass_down_Ex/ExxT``) are an *inspection* API: they evaluate
+ONE node's message on the host from the device-backed state, with the reference's semantics
+(node.py:95-129, 182-276; nodes_todo.py:43-62; gaussian.py:179-183).  The update kernels never call
+them -- inside the plate the same quantities are fused sums over all rows.
 """
 import numpy as np
 
@@ -83,6 +88,22 @@ class Addition(Node):
     def pass_down_Ex(self):
         return self.A.pass_down_Ex() + self.B.pass_down_Ex()
 
+    def pass_down_ExxT(self):
+        """<(A+B)(A+B)^T> for independent A, B (node.py:120-129)"""
+        cross = np.dot(self.A.pass_down_Ex(), self.B.pass_down_Ex().T)
+        return self.A.pass_down_ExxT() + self.B.pass_down_ExxT() + cross + cross.T
+
+    def pass_up_m1_m2(self, requester):
+        """Children's (m1, m2) with the co-parent's mean taken out of m2 (node.py:95-110)."""
+        m1, m2 = _sum_child_messages(self)
+        other = self.B if requester is self.A else self.A
+        return m1, m2 - np.dot(m1, other.pass_down_Ex())
+
+
+def _sum_child_messages(node):
+    msgs = [c.pass_up_m1_m2(node) for c in node.children]
+    return sum(m[0] for m in msgs), sum(m[1] for m in msgs)
+
 
 class Multiplication(Node):
     """node.py:131-276 (graph description only)"""
@@ -100,6 +121,45 @@ class Multiplication(Node):
 
     def pass_down_Ex(self):
         return np.dot(self.A.pass_down_Ex(), self.B.pass_down_Ex())
+
+    def _second_moment_of_A(self):
+        """<a_i a_j^T> for the columns of an hstack A as a (q, q, d, d) array: outer products of the column means plus the
+        column covariances on the i == j blocks (node.py:213-224)."""
+        Abar = self.A.pass_down_Ex()
+        G = np.einsum("ai,bj->ijab", Abar, Abar)
+        for i, col in enumerate(self.A.parents):
+            G[i, i] += col.qcov
+        return G
+
+    def pass_down_ExxT(self):
+        """<(AB)(AB)^T> (node.py:244-276): column A times scalar B, Constant matrix A, or hstack A."""
+        BBt = self.B.pass_down_ExxT()
+        if self.A.shape[1] == 1:
+            return self.A.pass_down_ExxT() * float(BBt[0, 0])
+        if isinstance(self.A, Constant):
+            return np.dot(self.A.value, np.dot(BBt, self.A.value.T))
+        if hasattr(self.A, "parents"):
+            return np.einsum("ijab,ij->ab", self._second_moment_of_A(), BBt)
+        raise NotImplementedError("pass_down_ExxT for this left operand")
+
+    def pass_up_m1_m2(self, requester):
+        """node.py:182-232.  To an hstack A the raw 4-tuple (sum m1, sum m2, <B>, <BB^T>) is forwarded; to B the contraction
+        m1 = tr(<a_i a_j^T> sum m1), m2 = <A>^T sum m2 -- the quantity K1 evaluates for all rows at once."""
+        m1s, m2s = _sum_child_messages(self)
+        if requester is self.A:
+            if self.A.shape[1] == 1:
+                return m1s * float(self.B.pass_down_ExxT()[0, 0]), float(self.B.pass_down_Ex()[0, 0]) * m2s
+            if hasattr(self.A, "parents"):
+                return m1s, m2s, self.B.pass_down_Ex(), self.B.pass_down_ExxT()
+            raise NotImplementedError("messages to this left operand")
+        m2 = np.dot(self.A.pass_down_Ex().T, m2s)
+        if self.A.shape[1] == 1:
+            return np.trace(np.dot(self.A.pass_down_ExxT(), m1s)), m2
+        if isinstance(self.A, Constant):
+            return np.dot(self.A.value.T, np.dot(m1s, self.A.value)), m2
+        if hasattr(self.A, "parents"):
+            return np.einsum("ijab,ba->ij", self._second_moment_of_A(), m1s), m2
+        raise NotImplementedError("messages through this left operand")
 
 
 class hstack(Node):
@@ -123,6 +183,20 @@ class hstack(Node):
 
     def pass_down_ExTx(self):
         raise NotImplementedError
+
+    def pass_up_m1_m2(self, requester):
+        """Message to column i (nodes_todo.py:43-62): m1 = sum_n m1_n <b b^T>_n[i, i],
+        m2 = sum_n (m2_n <b_i>_n - sum_{j != i} m1_n <b b^T>_n[i, j] <a_j>) -- what K3 + the W update evaluate."""
+        msgs = [c.pass_up_m1_m2(self) for c in self.children]
+        if self.shape[1] == 1:
+            return sum(m[0] for m in msgs), sum(m[1] for m in msgs)
+        i = self.parents.index(requester)
+        m1 = sum(m[0] * float(m[3][i, i]) for m in msgs)
+        m2 = sum(m[1] * float(m[2][i, 0]) for m in msgs)
+        for j, col in enumerate(self.parents):
+            if j != i:
+                m2 = m2 - np.dot(sum(m[0] * float(m[3][i, j]) for m in msgs), col.pass_down_Ex())
+        return m1, m2
 
 
 class Gamma(object):
@@ -265,7 +339,9 @@ class Gaussian(Node):
         return np.trace(self.pass_down_ExxT())
 
     def pass_up_m1_m2(self, requester):
-        raise NotImplementedError("messages are fused into the CUDA kernels (see DESIGN.md)")
+        """(<Lambda>, <Lambda> qmu), unmasked even for a partially observed node (gaussian.py:179-183)."""
+        pp = self.precision_parent.pass_down_Ex()
+        return pp, np.dot(pp, self.qmu)
 
 
 def _out_of_scope(name, ref):
@@ -274,7 +350,57 @@ def _out_of_scope(name, ref):
     return type(name, (object,), {"__init__": __init__, "__doc__": "out of scope: " + ref})
 
 
+class DiagonalGamma(object):
+    """nodes_todo.py:159-204: independent Gamma precisions for the entries of a Gaussian (Q and R of the LDS scripts)."""
+
+    def __init__(self, dim, a0s, b0s):
+        self.shape = (dim, dim)
+        assert a0s.size == self.shape[0]
+        assert b0s.size == self.shape[0]
+        self.a0s = a0s.flatten()
+        self.b0s = b0s.flatten()
+        self.children = []
+        self._binding = None
+        self.update_a()
+        self._qb = np.random.rand()          # ONE scalar, the same draw as nodes_todo.py:176
+
+    def addChild(self, child):
+        assert child.shape == (self.shape[0], 1)
+        self.children.append(child)
+        self.update_a()
+
+    def update_a(self):
+        self._qa = self.a0s + 0.5 * len(self.children)
+
+    @property
+    def qa(self):
+        return self._qa
+
+    @property
+    def qb(self):
+        if self._binding is not None:
+            return self._binding.get(self, "qb")
+        return self._qb
+
+    def update(self):
+        _plate.bind(self).update(self)
+
+    def pass_down_Ex(self):
+        return np.diag(self.qa / self.qb)
+
+    def pass_down_lndet(self):
+        return np.log(np.prod(self.qa / self.qb))
+
+    def log_lower_bound(self):
+        """Sum over the entries of the Gamma terms (nodes_todo.py:198-203); host arithmetic on 2 dim device-backed scalars."""
+        from scipy import special
+        qa, qb = self.qa, self.qb * np.ones(self.shape[0])
+        elnx = special.digamma(qa) - np.log(qb)
+        prior = (self.a0s - 1) * elnx - special.gammaln(self.a0s) + self.a0s * np.log(self.b0s) - self.b0s * qa / qb
+        entropy = (qa - 1) * elnx - special.gammaln(qa) + qa * np.log(qb) - qa
+        return float(np.sum(prior - entropy))
+
+
 DiagonalGaussian = _out_of_scope("DiagonalGaussian", "gaussian.py:185-203")
-DiagonalGamma = _out_of_scope("DiagonalGamma", "nodes_todo.py:159-204")
 Wishart = _out_of_scope("Wishart", "nodes_todo.py:205-234")
 Transpose = _out_of_scope("Transpose", "nodes_todo.py:65-82")

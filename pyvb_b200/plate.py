@@ -66,14 +66,24 @@ class PCAPlate(object):
         algo = DEFAULT_ALGO if algo is None else algo
         allnodes = _crawl(any_node)
         hs = [n for n in allnodes if isinstance(n, nd.hstack)]
-        if len(hs) != 1:
+        if len(hs) == 1:
+            W = hs[0]
+            Ws = list(W.parents)
+        elif len(hs) == 0:
+            # q = 1 without an hstack (src/tests.py:176-202, simple_PCA): W is ONE Gaussian column, every product is
+            # Multiplication(W, z_n) with a scalar z_n (node.py:195-197, 205-207) -- the same plate with q = 1
+            cols = [n for n in allnodes if isinstance(n, nd.Gaussian) and n.children
+                    and all(isinstance(c, nd.Multiplication) and c.A is n for c in n.children)]
+            if len(cols) != 1:
+                raise NotImplementedError("expected one hstack (W) or one Gaussian column multiplied by scalar z_n")
+            W = cols[0]
+            Ws = [W]
+        else:
             raise NotImplementedError("expected exactly one hstack (W) in the graph, found %d" % len(hs))
-        W = hs[0]
-        Ws = list(W.parents)
         q = len(Ws)
         mults = list(W.children)
         if not mults or not all(isinstance(m, nd.Multiplication) and m.A is W for m in mults):
-            raise NotImplementedError("children of the hstack must be Multiplication(W, z_n) nodes")
+            raise NotImplementedError("children of W must be Multiplication(W, z_n) nodes")
         Zs, Xs, Mu, Beta = [], [], None, None
         for m in mults:
             z = m.B
@@ -281,8 +291,17 @@ class PCAPlate(object):
 
 
 def bind(node, mode=None, algo=None):
-    """Return the plate `node` belongs to, compiling the graph on first use."""
+    """Return the plate `node` belongs to, compiling the graph on first use: the VB-PCA pattern (PCAPlate) or the
+    linear-dynamic-system pattern of the reference's LDS scripts (lds_plate.LDSPlate)."""
     b = getattr(node, "_binding", None)
     if b is None:
-        b = PCAPlate(node, mode=mode, algo=algo)
+        try:
+            b = PCAPlate(node, mode=mode, algo=algo)
+        except NotImplementedError as pca_err:
+            from .lds_plate import LDSPlate
+            try:
+                b = LDSPlate(node)
+            except NotImplementedError as lds_err:
+                raise NotImplementedError("the graph matches no compiled pattern -- VB-PCA: %s; LDS: %s (there is no CPU "
+                                          "message passing)" % (pca_err, lds_err))
     return b

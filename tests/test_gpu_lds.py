@@ -61,3 +61,20 @@ def test_lds_empty_batch_is_a_noop():
     e.iterate(2)
     e.check()
     assert e.get_state()["X"].shape == (0, 10, 2)
+
+
+@pytest.mark.parametrize("name", ["lds_known.npz", "lds_known_b.npz"])
+def test_lds_known_entries_of_A_match_literal_reference(name):
+    """examples/LDS_knowns_in_A.py:72-74: columns of A observed with NaN = unknown."""
+    from pyvb_b200 import LDSEngine
+    g = load_golden(name)
+    e = LDSEngine(g["Y"], int(g["q"]), device="cuda:0", A_known=g["A_known"])
+    e.set_state({k: g["init_" + k] for k in LDSEngine.KEYS})
+    for it in range(int(g["niters"])):
+        e.iterate()
+        st = e.get_state()
+        for k in KEYS:
+            assert tensor_rel(st[k][0], g["it%d_%s" % (it, k)]) < TOL, (name, it, k)
+        kn = g["A_known"]
+        assert np.array_equal(st["A"][0][~np.isnan(kn)], kn[~np.isnan(kn)]) and np.all(st["Avar"][0][~np.isnan(kn)] == 0)
+    e.check()
