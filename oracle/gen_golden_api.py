@@ -7,6 +7,7 @@ TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
 Fixtures:
   simple_pca.npz   src/tests.py:176-202 (simple_PCA): q = 1, W is ONE Gaussian column (no hstack), products are
                    Multiplication(W, z_n) with scalar z_n; manual order W, Z rows, Mu, noise; 10 iterations
+  simple_regression.npz  src/tests.py:100-128: y_n ~ N(x_n * A + B, noise) with constant scalar regressors; A, B, noise x 10
   messages.npz     the per-node messages of the shipped graph (examples/PCA_missing_data.py:31-37, N = 6, d = 4, q = 2,
                    one NaN) at its random initial state: pass_up_m1_m2 of X_n, Addition, Multiplication (to W: the
                    4-tuple, to z), hstack (to every column), and pass_down_ExxT of Addition / Multiplication
@@ -64,6 +65,36 @@ def simple_pca(pyvb, seed=7, niters=10):
     return out
 
 
+def build_regression(nodes, x, y):
+    """src/tests.py:108-123"""
+    N = x.shape[0]
+    B = nodes.Gaussian(1, np.array([[0.]]), np.array([[1e-2]]))
+    A = nodes.Gaussian(1, np.array([[0.]]), np.array([[1e-2]]))
+    noise = nodes.Gamma(1, 1e-3, 1e-3)
+    Xs = [nodes.Constant(xx.reshape(1, 1)) for xx in x]
+    Ys = [nodes.Gaussian(1, Xnode * A + B, noise) for Xnode in Xs]
+    for n, yy in zip(Ys, y):
+        n.observe(yy.reshape(1, 1))
+    return A, B, noise, Ys
+
+
+def simple_regression(pyvb, seed=11, niters=10):
+    np.random.seed(seed)
+    N = 200
+    x = np.linspace(-1, 1, N).reshape(N, 1)
+    y = 0.7 * x + 0.3 + np.random.randn(N, 1) * np.sqrt(1. / 10.)
+    A, B, noise, Ys = build_regression(pyvb.nodes, x, y)
+    out = {"x": x, "y": y, "niters": np.int64(niters), "seed": np.int64(seed),
+           "init": np.array([float(A.qmu[0, 0]), float(A.qcov[0, 0]), float(B.qmu[0, 0]), float(B.qcov[0, 0]), float(noise.qb)])}
+    for it in range(niters):
+        A.update()
+        B.update()
+        noise.update()
+        out["it%d" % it] = np.array([float(A.qmu[0, 0]), float(A.qcov[0, 0]), float(B.qmu[0, 0]), float(B.qcov[0, 0]),
+                                     float(noise.qb), float(noise.pass_down_Ex()[0, 0])])
+    return out
+
+
 def build_shipped(nodes, X, q):
     N, d = X.shape
     Ws = [nodes.Gaussian(d, np.zeros((d, 1)), np.eye(d) * 1e-3) for i in range(q)]
@@ -118,7 +149,8 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     np.savez_compressed(os.path.join(GOLD, "simple_pca.npz"), **simple_pca(pyvb))
     np.savez_compressed(os.path.join(GOLD, "messages.npz"), **messages(pyvb.nodes))
-    for f in ("simple_pca.npz", "messages.npz"):
+    np.savez_compressed(os.path.join(GOLD, "simple_regression.npz"), **simple_regression(pyvb))
+    for f in ("simple_pca.npz", "messages.npz", "simple_regression.npz"):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 
 

@@ -66,6 +66,7 @@ class PCAPlate(object):
         algo = DEFAULT_ALGO if algo is None else algo
         allnodes = _crawl(any_node)
         hs = [n for n in allnodes if isinstance(n, nd.hstack)]
+        fixed_z = False
         if len(hs) == 1:
             W = hs[0]
             Ws = list(W.parents)
@@ -74,20 +75,33 @@ class PCAPlate(object):
             # Multiplication(W, z_n) with a scalar z_n (node.py:195-197, 205-207) -- the same plate with q = 1
             cols = [n for n in allnodes if isinstance(n, nd.Gaussian) and n.children
                     and all(isinstance(c, nd.Multiplication) and c.A is n for c in n.children)]
-            if len(cols) != 1:
-                raise NotImplementedError("expected one hstack (W) or one Gaussian column multiplied by scalar z_n")
-            W = cols[0]
+            # scalar regression (src/tests.py:100-128, simple_regression): y_n ~ N(x_n * A + B, noise) with CONSTANT 1 x 1
+            # regressors x_n on the left: the same plate with d = q = 1, W := A, z_n := x_n fixed (never updated)
+            regs = [n for n in allnodes if isinstance(n, nd.Gaussian) and n.shape == (1, 1) and n.children
+                    and all(isinstance(c, nd.Multiplication) and c.B is n and isinstance(c.A, nd.Constant)
+                            and c.A.shape == (1, 1) for c in n.children)]
+            if len(cols) == 1:
+                W = cols[0]
+            elif len(regs) == 1 and not cols:
+                W = regs[0]
+                fixed_z = True
+            else:
+                raise NotImplementedError("expected one hstack (W), one Gaussian column multiplied by scalar z_n, or one "
+                                          "scalar Gaussian multiplied by constant regressors")
             Ws = [W]
         else:
             raise NotImplementedError("expected exactly one hstack (W) in the graph, found %d" % len(hs))
         q = len(Ws)
         mults = list(W.children)
-        if not mults or not all(isinstance(m, nd.Multiplication) and m.A is W for m in mults):
+        if not mults or not all(isinstance(m, nd.Multiplication) and (m.B if fixed_z else m.A) is W for m in mults):
             raise NotImplementedError("children of W must be Multiplication(W, z_n) nodes")
         Zs, Xs, Mu, Beta = [], [], None, None
         for m in mults:
-            z = m.B
-            if not isinstance(z, nd.Gaussian) or len(z.children) != 1 or len(m.children) != 1:
+            z = m.A if fixed_z else m.B
+            if fixed_z:
+                if len(m.children) != 1:
+                    raise NotImplementedError("each product x_n * A must have a single child")
+            elif not isinstance(z, nd.Gaussian) or len(z.children) != 1 or len(m.children) != 1:
                 raise NotImplementedError("each z_n must be a Gaussian with the single child W*z_n")
             add = m.children[0]
             if not isinstance(add, nd.Addition) or len(add.children) != 1:
@@ -126,12 +140,17 @@ class PCAPlate(object):
             raise NotImplementedError("Mu needs a constant zero prior mean")
         alpha_mu = _scalar_times_eye(Mu.precision_parent.value)
         z0 = Zs[0]
-        if not isinstance(z0.mean_parent, nd.Constant) or not isinstance(z0.precision_parent, nd.Constant):
-            raise NotImplementedError("z_n needs constant prior mean and precision")
-        m0, P0 = z0.mean_parent.value, z0.precision_parent.value
-        for z in Zs:
-            if not (np.array_equal(z.mean_parent.value, m0) and np.array_equal(z.precision_parent.value, P0)):
-                raise NotImplementedError("all z_n must share one prior")
+        if fixed_z:
+            m0, P0 = np.zeros((q, 1)), np.eye(q)          # (unused: the regressors are never updated)
+            if not all(x.observed for x in Xs):
+                raise NotImplementedError("regression pattern: every y_n must be observed")
+        else:
+            if not isinstance(z0.mean_parent, nd.Constant) or not isinstance(z0.precision_parent, nd.Constant):
+                raise NotImplementedError("z_n needs constant prior mean and precision")
+            m0, P0 = z0.mean_parent.value, z0.precision_parent.value
+            for z in Zs:
+                if not (np.array_equal(z.mean_parent.value, m0) and np.array_equal(z.precision_parent.value, P0)):
+                    raise NotImplementedError("all z_n must share one prior")
 
         # data + initial state from the nodes (the reference's random init, gaussian.py:70-72)
         X = np.full((N, d), np.nan)
@@ -144,8 +163,8 @@ class PCAPlate(object):
             "Wbar": np.hstack([w._qmu for w in Ws]),
             "Wvar": np.stack([np.diag(w._qcov) for w in Ws], 1),
             "mu": Mu._qmu[:, 0], "muvar": np.diag(Mu._qcov),
-            "Zbar": np.stack([z._qmu[:, 0] for z in Zs]),
-            "Sig": np.stack([z._qcov for z in Zs]),
+            "Zbar": np.stack([(z.value if fixed_z else z._qmu)[:, 0] for z in Zs]),
+            "Sig": np.stack([np.zeros((q, q)) if fixed_z else z._qcov for z in Zs]),
             "Xhat": np.stack([x._qmu[:, 0] for x in Xs]),
             "V": np.stack([np.diag(x._qcov) for x in Xs]),
             "qb": Beta._qb,
@@ -163,15 +182,17 @@ class PCAPlate(object):
         self.index = {}
         for i, w in enumerate(Ws):
             self.index[id(w)] = ("W", i)
+        self.fixed_z = fixed_z
         for n, z in enumerate(Zs):
-            self.index[id(z)] = ("Z", n)
+            if not fixed_z:
+                self.index[id(z)] = ("Z", n)
         for n, x in enumerate(Xs):
             self.index[id(x)] = ("X", n)
         self.index[id(Mu)] = ("M", 0)
         self.index[id(Beta)] = ("B", 0)
         for i, a in enumerate(Alphas):
             self.index[id(a)] = ("L", i)
-        for n in Ws + Zs + Xs + [Mu, Beta] + Alphas:
+        for n in Ws + ([] if fixed_z else Zs) + Xs + [Mu, Beta] + Alphas:
             n._binding = self
         self._host = None
         self._elbo_terms = None
@@ -220,6 +241,8 @@ class PCAPlate(object):
             self.run(kind, lo, hi)
 
     def elbo(self):
+        if self.fixed_z:
+            raise NotImplementedError("the bound of the regression pattern is not evaluated (its regressors are constants)")
         v = self.engine.elbo()
         self._elbo_terms = None
         return v

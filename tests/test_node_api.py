@@ -63,8 +63,8 @@ def test_simple_pca_q1_without_hstack_matches_literal_reference():
         p = "it%d_" % it
         assert tensor_rel(W.qmu[:, 0], g[p + "W"]) < 1e-9 and tensor_rel(W.qcov, g[p + "Wcov"]) < 1e-9
         assert tensor_rel(Mu.qmu[:, 0], g[p + "mu"]) < 1e-9 and tensor_rel(Mu.qcov, g[p + "mucov"]) < 1e-9
-        assert tensor_rel(np.array([float(z.qmu) for z in Zs]), g[p + "Z"]) < 1e-9
-        assert tensor_rel(np.array([float(z.qcov) for z in Zs]), g[p + "Zvar"]) < 1e-9
+        assert tensor_rel(np.array([z.qmu[0, 0] for z in Zs]), g[p + "Z"]) < 1e-9
+        assert tensor_rel(np.array([z.qcov[0, 0] for z in Zs]), g[p + "Zvar"]) < 1e-9
         assert abs(noise.qb - float(g[p + "qb"])) <= 1e-9 * float(g[p + "qb"])
     assert abs(noise.qa / noise.qb - float(g["it9_qa"]) / float(g["it9_qb"])) < 1e-9 * noise.qa / noise.qb
 
@@ -189,3 +189,27 @@ def test_lds_scripts_through_the_node_api_match_literal_reference(name, seed):
         assert tensor_rel(np.diag(m["Q"].pass_down_Ex()), g[p + "Qa"] / g[p + "Qb"]) < 1e-9
     b = m["Q"]._binding
     assert b.iterations == int(g["niters"]) and b.launches == int(g["niters"]) // 2
+
+
+@pytest.mark.gpu
+def test_simple_regression_matches_literal_reference():
+    """src/tests.py:100-128: constant scalar regressors on the left of the product, manual order A, B, noise."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from gen_golden_api import build_regression
+    from pyvb import nodes
+    g = load_golden("simple_regression.npz")
+    np.random.seed(int(g["seed"]))
+    np.random.randn(g["x"].shape[0], 1)                                 # the data draw
+    A, B, noise, Ys = build_regression(nodes, g["x"], g["y"])
+    got = np.array([A.qmu[0, 0], A.qcov[0, 0], B.qmu[0, 0], B.qcov[0, 0], noise.qb])
+    assert np.array_equal(got, g["init"])                                # the reference's random initialisation
+    for it in range(int(g["niters"])):
+        A.update()
+        B.update()
+        noise.update()
+        got = np.array([A.qmu[0, 0], A.qcov[0, 0], B.qmu[0, 0], B.qcov[0, 0], noise.qb, noise.pass_down_Ex()[0, 0]])
+        assert np.max(np.abs(got - g["it%d" % it]) / np.abs(g["it%d" % it])) < 1e-9, (it, got, g["it%d" % it])
