@@ -410,14 +410,14 @@ int pyvb_stats_i8_f64(long long N, int D, int q, const double *X, long long ldx,
     }
     ARG(X && maskT && MZ && ZI && scratch && xcache, "null pointer (xcache is required)");
     ARG(zsums || logdet, "zsums or logdet");
-    ARG(logdet || (k2_impl(q) == 1 || k2_impl(q) == 2), "logdet is needed when the K2 partials carry no column maxima");
+    ARG(logdet || k2_impl(q) >= 1, "logdet is needed when the K2 partials carry no column maxima");
     ARG(ldx >= D && (ldx % 2) == 0 && ldmz == pyvb_mz_pitch(q), "ldx, ldmz");
     ARG(ws_bytes >= pyvb_stats_i8_workspace_bytes(N, D, q), "workspace too small");
     int nzblk = 0, zkw = 0;
     if (zsums) zsolve_partials(N, q, nzblk, zkw);
     const int nch = stats_i8_nchunks(N, D, q);
     // the default K2 kernels leave bounds on the column maxima behind their column sums: [sums OROW | 4 | maxima OROW]
-    const bool kmax = nzblk > 0 && (k2_impl(q) == 1 || k2_impl(q) == 2);
+    const bool kmax = nzblk > 0 && k2_impl(q) >= 1;
     AuxStream *aux = aux_stream();                              // Ast (FP64 tensor cores on X) next to digitize + the INT8 kernel
     cudaStream_t st2 = st;
     cudaError_t e = cudaSuccess;

@@ -656,11 +656,12 @@ static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double 
 // blocked / tpm overrides the default (measured per 1M rows, FP64: q = 16: 1.62 / 2.0 / see DESIGN ms; q = 32: 9.0 / 5.8).
 int k2_impl(int q) {
     const char *e = getenv("PYVB_K2");               // read per call (tests flip it); callers size zsums with pyvb_zsums_len
-    int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : -1;
-    if (q == 64) return 1;
+    int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : (e && e[0] == 'l') ? 3 : -1;
+    if (q == 64 && (mode == 0 || mode == 2)) mode = -1;  // q = 64 only exists blocked
     if (mode == 2 && q > 16) mode = -1;
+    if (mode == 3 && q < 16) mode = -1;
     if (mode >= 0) return mode;
-    return q >= 32 ? 1 : 2;
+    return q >= 32 ? 1 : 2;      // (the lane-parallel-diagonal kernel, 3, is not faster: 7.7 vs 7.4 ms at q = 32)
 }
 
 void zsolve_partials(long long N, int q, int &nblk, int &kw) {
@@ -676,6 +677,11 @@ void zsolve_partials(long long N, int q, int &nblk, int &kw) {
     if (impl == 2) {
         kw = zsolve_tpm_kw(q);
         nblk = zsolve_tpm_blocks(N, q);
+        return;
+    }
+    if (impl == 3) {
+        kw = zsolve_lanediag_kw(q);
+        nblk = kw > 0 ? zsolve_lanediag_blocks(N, q) : 0;
         return;
     }
     switch (q) {
@@ -768,6 +774,7 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
     const int impl = k2_impl(q);
     if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
+    if (impl == 3) return launch_zsolve_lanediag(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (cond != nullptr || chk.gscale != nullptr) return cudaErrorNotSupported;   // the cross-check kernel has no guard
     switch (q) {
         case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);

@@ -37,7 +37,7 @@ namespace {
 __host__ __device__ constexpr int i_tri(int i) { return i * (i + 1) / 2; }
 __host__ __device__ constexpr int i_nc8(int q) { return (i_tri(q) + 31) & ~31; }          // packed columns rounded to 32
 constexpr int NPL = 7;                                                                    // digit planes
-constexpr int BM = 128, BKB = 64, ST = 8, CT = 32;       // rows per tile, K bytes per chunk, max digit stages, columns per tile
+constexpr int BM = 128, BKB = 64, ST = 16, CT = 32;      // rows per tile, K bytes per chunk, max digit stages, columns per tile
 constexpr int A_B = BM * BKB, B_B = NPL * CT * BKB;      // 8192, 14336
 constexpr int NTHR = 10 * 32;
 
@@ -171,6 +171,15 @@ __device__ __forceinline__ void tma_load_3d_i8_mc(void *dst_smem, const void *tm
         "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "h"(mask)
         : "memory");
 }
+// CTA pair: the box lands in THIS CTA's shared memory, the transaction bytes are signalled on a barrier of the LEADER CTA
+// (`bar_cluster` = shared::cluster address, umma::map_to_cta)
+__device__ __forceinline__ void tma_load_3d_i8_pair(void *dst_smem, const void *tmap, int c0, int c1, int c2, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster)
+        : "memory");
+}
 // tcgen05.commit that arrives on the barrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void mma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -224,16 +233,25 @@ struct I8Geom {
 };
 constexpr int OUT_B = 8 * 32 * 16 * 8;                  // epilogue staging: 8 warps x (32 rows x 16 columns) doubles
 // hstage: the epilogue stages (and stores) 8 columns at a time: half the staging memory, one more digit stage at D = 1024
-size_t i8_smem_bytes(int D, int q, int nst, int hstage) {
+// pair: cta_group::2 -- a CTA holds HALF of every digit tile (7 KB per stage)
+size_t i8_smem_bytes(int D, int q, int nst, int hstage, int pair = 0) {
     const I8Geom g(q);
     const int nk = D / BKB;
-    return 1024 + (size_t)nk * A_B + (size_t)nst * B_B + (hstage ? OUT_B / 2 : OUT_B) + (size_t)(2 * g.NC8) * 8 +
+    return 1024 + (size_t)nk * A_B + (size_t)nst * (pair ? B_B / 2 : B_B) + (hstage ? OUT_B / 2 : OUT_B) + (size_t)(2 * g.NC8) * 8 +
            (size_t)(2 * nk + 2 * nst + 4) * 8 + 16;
 }
-int i8_stages(int D, int q, int hstage) {                // digit-tile stages that fit next to the resident mask block
-    for (int nst = ST; nst >= 2; --nst)
-        if (i8_smem_bytes(D, q, nst, hstage) <= 227 * 1024) return nst;
+int i8_stages(int D, int q, int hstage, int pair = 0) {  // digit-tile stages that fit next to the resident mask block
+    for (int nst = pair ? ST : ST / 2; nst >= 2; --nst)
+        if (i8_smem_bytes(D, q, nst, hstage, pair) <= 227 * 1024) return nst;
     return 0;
+}
+int i8_pair_mode() {                                     // PYVB_I8_PAIR = 0 | 1 (default 1): tcgen05.mma.cta_group::2 in K1-i8 / K3-i8
+    static int m = -1;
+    if (m < 0) {
+        const char *e = getenv("PYVB_I8_PAIR");
+        m = (e && e[0] == '0') ? 0 : 1;
+    }
+    return m;
 }
 int i8_hstage(int D, int q) {                            // half staging only where it buys a stage and stages are scarce
     static int force = -2;
@@ -250,7 +268,10 @@ int i8_hstage(int D, int q) {                            // half staging only wh
 // CL > 1: clusters of CL CTAs (consecutive row blocks) share every digit tile: each CTA fetches 1 / CL of it and the
 // copy is multicast to all of them (the digit tiles come from L2 and their traffic, not the MMAs, bounds the kernel);
 // a stage is released by the MMA commits of ALL the CTAs (multicast tcgen05.commit on every CTA's `empty` barrier).
-template <int CL>
+// PAIR (with CL = 2): tcgen05.mma.cta_group::2 -- the CTA pair is ONE 256-row MMA; a CTA holds its own 128 x D mask block and
+// HALF of every digit tile (7 KB instead of 14: twice the ring depth next to the resident mask block), the leader CTA issues
+// the MMAs for both, every CTA drains its own 128 TMEM lanes.  No multicast: each CTA fetches only its half.
+template <int CL, bool PAIR = false>
 __global__ void __launch_bounds__(NTHR, 1)
 zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO8, long long N, int D, int q,
@@ -271,10 +292,12 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } while (0)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+    constexpr int BSZ = PAIR ? B_B / 2 : B_B;                                  // bytes of a digit stage in THIS CTA
     const int nk = D / BKB;
     unsigned char *a_base = smem;                                              // [nk][128 x 64 B] resident mask block
-    unsigned char *b_base = smem + (size_t)nk * A_B;                           // [nst][224 x 64 B] digit tiles
-    unsigned char *o_base = b_base + (size_t)nst * B_B;                        // [8 warps][32 rows x 128 B] output staging (swizzled)
+    unsigned char *b_base = smem + (size_t)nk * A_B;                           // [nst][224 (PAIR: 112) x 64 B] digit tiles
+    unsigned char *o_base = b_base + (size_t)nst * BSZ;                        // [8 warps][32 rows x 128 B] output staging (swizzled)
     double *p0v = reinterpret_cast<double *>(o_base + (hstage ? OUT_B / 2 : OUT_B));   // [NC8]: packed P0, zero pad
     double *fcol = p0v + G.NC8;                                                // [NC8]: tau * scale_c * 2^-54
     uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nk]
@@ -291,6 +314,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // every CTA of a cluster runs the same number of row blocks (a CTA past the last block works on zero-filled rows)
     const int first = (int)blockIdx.x - crank;
     const int niter = (first < nrb) ? (nrb - first + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    int niter_mma = niter;                                     // (PAIR: zero in the non-leader CTA)
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
     // every cluster walks the (column tile, K chunk) grid from its own starting point: 148 CTAs stepping through the
     // same few MB of digit tiles in lockstep would all hit the same L2 lines at the same time
@@ -318,15 +342,18 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL);
+            mbar_init(&empty[s], PAIR ? 1 : CL);                   // PAIR: one multicast commit of the leader per use
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 8);
+            mbar_init(&tempty[b], PAIR ? 16 : 8);                  // PAIR: the epilogue warps of BOTH CTAs release the leader's buffer
         }
         mbar_fence_init();
     }
-    if (warp == 1) umma::tmem_alloc(tbase, 512);
+    if (warp == 1) {
+        if (PAIR) umma::tmem_alloc2(tbase, 512);
+        else umma::tmem_alloc(tbase, 512);
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();                            // the peers' barriers are initialised before anyone signals them
@@ -336,6 +363,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0) {
         // ===================== TMA producer (whole warp, one elected lane issues) =====================
         const bool leader = elect_one();
+        const uint32_t afull_l = PAIR ? umma::map_to_cta(afull, 0) : 0u, full_l = PAIR ? umma::map_to_cta(full, 0) : 0u;
         int s = 0;
         uint32_t ph = 0;
         for (int rl = 0; rl < niter; ++rl) {
@@ -347,18 +375,29 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (ci == 0) {      // the mask chunk of the previous row block has been consumed by its last column tile
                         PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[kb], (uint32_t)((rl & 1) ^ 1)));
                         if (leader) {
-                            mbar_arrive_expect_tx(&afull[kb], (uint32_t)A_B);
-                            tma_load_3d_i8(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, &afull[kb]);   // past the end: zero fill
+                            if (PAIR) {        // both CTAs' chunks complete on the LEADER's barrier (armed by the leader for both)
+                                if (crank == 0) mbar_arrive_expect_tx(&afull[kb], (uint32_t)(2 * A_B));
+                                tma_load_3d_i8_pair(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, afull_l + (uint32_t)kb * 8u);
+                            } else {
+                                mbar_arrive_expect_tx(&afull[kb], (uint32_t)A_B);
+                                tma_load_3d_i8(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, &afull[kb]);   // past the end: zero fill
+                            }
                         }
                     }
                     PROF_WAIT(w0, umma::mbar_wait_bounded(&empty[s], ph ^ 1));
                     if (leader) {
-                        mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
-                        if (CL == 1)
-                            tma_load_3d_i8(b_base + s * B_B, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT), 0, &full[s]);   // 7 planes x 32 columns
-                        else                                                                               // this CTA's slice, to everybody
-                            tma_load_3d_i8_mc(b_base + s * B_B + crank * (B_B / CL), &tmB, 0,
-                                              (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / CL), 0, &full[s], CMASK);
+                        if (PAIR) {            // this CTA's half of the tile (rows crank * 112 ...) into its own stage
+                            if (crank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
+                            tma_load_3d_i8_pair(b_base + s * BSZ, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / 2), 0,
+                                                full_l + (uint32_t)s * 8u);
+                        } else {
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
+                            if (CL == 1)
+                                tma_load_3d_i8(b_base + s * B_B, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT), 0, &full[s]);   // 7 planes x 32 columns
+                            else                                                                               // this CTA's slice, to everybody
+                                tma_load_3d_i8_mc(b_base + s * B_B + crank * (B_B / CL), &tmB, 0,
+                                                  (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / CL), 0, &full[s], CMASK);
+                        }
                     }
                     __syncwarp();
                     if (++s == nst) {
@@ -369,14 +408,15 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (whole warp, one elected lane issues) =====================
-        const bool leader = elect_one();
-        const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
+        // ===================== MMA issuer (whole warp, one elected lane issues; PAIR: the leader CTA alone) ============
+        const bool leader = elect_one() && (!PAIR || crank == 0);
+        if (PAIR && crank != 0) niter_mma = 0;
+        const uint32_t idesc = umma::idesc_s8_s32(PAIR ? 2 * BM : BM, NPL * CT);
         // descriptors: the start-address field counts 16-byte units, so stage / chunk / K-step offsets are plain adds
         const uint64_t adesc0 = umma::desc_kmajor_sw64(smem_u32(a_base), 0), bdesc0 = umma::desc_kmajor_sw64(smem_u32(b_base), 0);
         int s = 0, tl = 0;
         uint32_t ph = 0;
-        for (int rl = 0; rl < niter; ++rl) {
+        for (int rl = 0; rl < niter_mma; ++rl) {
             for (int ci = 0; ci < G.NCT; ++ci, ++tl) {
                 const int buf = tl & 1;
                 PROF_WAIT(w1, umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1)));
@@ -388,12 +428,19 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     PROF_WAIT(w0, umma::mbar_wait_bounded(&full[s], ph));
                     umma::fence_after_sync();
                     if (leader) {
-                        const uint64_t ad = adesc0 + (uint64_t)(kb * (A_B >> 4)), bd = bdesc0 + (uint64_t)(s * (B_B >> 4));
-                        umma::mma_i8(dacc, ad, bd, idesc, ki ? 1u : 0u);
-                        umma::mma_i8(dacc, ad + 2, bd + 2, idesc, 1u);
-                        if (CL == 1) umma::mma_commit(&empty[s]);
-                        else mma_commit_mc(&empty[s], CMASK);
-                        if (ci == G.NCT - 1) umma::mma_commit(&aempty[kb]);
+                        const uint64_t ad = adesc0 + (uint64_t)(kb * (A_B >> 4)), bd = bdesc0 + (uint64_t)(s * (BSZ >> 4));
+                        if (PAIR) {
+                            umma::mma_i8_pair(dacc, ad, bd, idesc, ki ? 1u : 0u);
+                            umma::mma_i8_pair(dacc, ad + 2, bd + 2, idesc, 1u);
+                            umma::mma_commit_pair(&empty[s]);                            // frees the stage in both CTAs
+                            if (ci == G.NCT - 1) umma::mma_commit_pair(&aempty[kb]);
+                        } else {
+                            umma::mma_i8(dacc, ad, bd, idesc, ki ? 1u : 0u);
+                            umma::mma_i8(dacc, ad + 2, bd + 2, idesc, 1u);
+                            if (CL == 1) umma::mma_commit(&empty[s]);
+                            else mma_commit_mc(&empty[s], CMASK);
+                            if (ci == G.NCT - 1) umma::mma_commit(&aempty[kb]);
+                        }
                     }
                     __syncwarp();
                     if (++s == nst) {
@@ -401,7 +448,10 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         ph ^= 1;
                     }
                 }
-                if (leader) umma::mma_commit(&tfull[buf]);
+                if (leader) {
+                    if (PAIR) umma::mma_commit_pair(&tfull[buf]);            // the accumulators of both CTAs are complete
+                    else umma::mma_commit(&tfull[buf]);
+                }
                 __syncwarp();
             }
         }
@@ -409,6 +459,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== epilogue: 7 INT32 planes -> FP64 -> P0 + f_c * v -> MZ row ========
         const int wq = warp & 3;                               // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;                      // which 16 of the tile's 32 columns
+        const uint32_t tempty_l = PAIR ? umma::map_to_cta(tempty, 0) : 0u;
         int tl = 0;
         for (int rl = 0; rl < niter; ++rl) {
             const long long rowbase = ((long long)blockIdx.x + (long long)rl * gridDim.x) * BM + wq * 32;
@@ -427,7 +478,10 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 umma::tmem_ld_wait();
                 umma::fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);       // the accumulator buffer is free again
+                if (lane == 0) {                                // the accumulator buffer is free again
+                    if (PAIR) umma::mbar_arrive_cluster(tempty_l + (uint32_t)buf * 8u);   // (the leader's barrier counts both CTAs)
+                    else mbar_arrive(&tempty[buf]);
+                }
                 // lane = row: 16 outputs per lane, staged in this warp's [32 rows][128 B] tile (16-byte chunks XOR-swizzled
                 // with the row, the SWIZZLE_128B pattern of the store map: conflict-free 16-byte shared-memory stores)
                 // and written by ONE TMA tensor store (rows >= N and columns >= PP are clipped by the map).  Per-lane
@@ -511,7 +565,10 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     umma::fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();        // no CTA leaves while a peer may still multicast into it or signal its barriers
-    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+    if (warp == 1) {
+        if (PAIR) umma::tmem_dealloc2(tmem, 512);
+        else umma::tmem_dealloc(tmem, 512);
+    }
 }
 
 // launch with a cluster dimension (cl = 1: plain launch)
@@ -556,6 +613,7 @@ int i8_cluster_size() {                     // PYVB_I8_CLUSTER = 1 | 2 | 4 (defa
 // second stage, stats_reduce_kernel, adds the chunks).  Items are dealt round-robin to 148 persistent CTAs, chunk-major,
 // so that the CTAs running at the same time share their operand tiles through L2.
 constexpr int SST = 9;                                   // stages of the K3-i8 ring (22 KB each)
+constexpr int SST_PAIR = 13;                             // ... with cta_group::2 (15 KB each: half of the digit tile per CTA)
 constexpr int CM_BLOCKS = 148 * 4;                       // partial column maxima
 
 // column maxima of |MZ| over a block of rows: pm[blk][ldmz].  Warp per row, lane l owns the columns l, l + 32, ...
@@ -796,25 +854,30 @@ stats_i8_check_kernel(int D, int q, const double *__restrict__ ws, int nchunks, 
     }
 }
 
-size_t si8_smem_bytes(int q) {
-    return 1024 + (size_t)SST * (A_B + B_B) + (size_t)((i_tri(q) + q + 31) & ~31) * 8 + (size_t)(2 * SST + 4) * 8 + 16;
+size_t si8_smem_bytes(int q, int pair = 0) {
+    const int ns = pair ? SST_PAIR : SST;
+    return 1024 + (size_t)ns * (A_B + (pair ? B_B / 2 : B_B)) + (size_t)((i_tri(q) + q + 31) & ~31) * 8 + (size_t)(2 * ns + 4) * 8 + 16;
 }
 
 // CL > 1: the CTAs of a cluster take CL consecutive blocks of data dimensions of the same (column tile, chunk) item and
 // share its digit tiles by multicast, as in K1-i8.
-template <int CL>
+// PAIR (CL = 2): tcgen05.mma.cta_group::2 -- the two blocks of data dimensions are ONE 256-row MMA, each CTA stages its own
+// maskT tile and HALF of the digit tile (15 KB per stage instead of 22: more stages, half the L2 traffic of the digits).
+template <int CL, bool PAIR = false>
 __global__ void __launch_bounds__(NTHR, 1)
 stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long N, int D, int q,
                 const double *__restrict__ zscale, double *__restrict__ ws, long long rows_per_chunk, int nchunks, int ndb,
                 int nct) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+    constexpr int BSZ = PAIR ? B_B / 2 : B_B, STG = A_B + BSZ, NS = PAIR ? SST_PAIR : SST;
     const int P = i_tri(q), NCZ = (P + q + 31) & ~31;
-    unsigned char *st_base = smem;                                             // [SST][A 8 KB | B 14 KB]
-    double *fcol = reinterpret_cast<double *>(smem + (size_t)SST * (A_B + B_B));   // [NCZ]: zscale_c * 2^-54
+    unsigned char *st_base = smem;                                             // [NS][A 8 KB | B 14 KB (PAIR: 7 KB)]
+    double *fcol = reinterpret_cast<double *>(smem + (size_t)NS * STG);         // [NCZ]: zscale_c * 2^-54
     uint64_t *full = reinterpret_cast<uint64_t *>(fcol + NCZ);
-    uint64_t *empty = full + SST;
-    uint64_t *tfull = empty + SST;
+    uint64_t *empty = full + NS;
+    uint64_t *tfull = empty + NS;
     uint64_t *tempty = tfull + 2;
     uint32_t *tbase = reinterpret_cast<uint32_t *>(tempty + 2);
 
@@ -828,17 +891,20 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < SST; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CL);
+            mbar_init(&empty[s], PAIR ? 1 : CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 8);
+            mbar_init(&tempty[b], PAIR ? 16 : 8);
         }
         mbar_fence_init();
     }
-    if (warp == 1) umma::tmem_alloc(tbase, 512);
+    if (warp == 1) {
+        if (PAIR) umma::tmem_alloc2(tbase, 512);
+        else umma::tmem_alloc(tbase, 512);
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();
@@ -861,6 +927,7 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0) {
         // TMA producer: whole warp, one elected lane issues (see elect_one)
         const bool leader = elect_one();
+        const uint32_t full_l = PAIR ? umma::map_to_cta(full, 0) : 0u;
         int s = 0;
         uint32_t ph = 0;
         for (int item = cid; item < nitems; item += ncl) {
@@ -870,31 +937,38 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int k = 0; k < nsteps; ++k) {
                 umma::mbar_wait_bounded(&empty[s], ph ^ 1);
                 if (leader) {
-                    unsigned char *st = st_base + (size_t)s * (A_B + B_B);
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
+                    unsigned char *st = st_base + (size_t)s * STG;
                     const long long kb = r0 / BKB + k;
-                    tma_load_3d_i8(st, &tmA, 0, (int)(kb * D + db * BM), 0, &full[s]);               // 128 data dimensions x 64 rows
-                    if (CL == 1)
-                        tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
-                    else
-                        tma_load_3d_i8_mc(st + A_B + crank * (B_B / CL), &tmB, 0,
-                                          (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / CL)), 0, &full[s], CMASK);
+                    if (PAIR) {                // both CTAs' tiles complete on the LEADER's barrier (armed by the leader for both)
+                        if (crank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * STG));
+                        tma_load_3d_i8_pair(st, &tmA, 0, (int)(kb * D + db * BM), 0, full_l + (uint32_t)s * 8u);
+                        tma_load_3d_i8_pair(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / 2)), 0,
+                                            full_l + (uint32_t)s * 8u);
+                    } else {
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
+                        tma_load_3d_i8(st, &tmA, 0, (int)(kb * D + db * BM), 0, &full[s]);               // 128 data dimensions x 64 rows
+                        if (CL == 1)
+                            tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
+                        else
+                            tma_load_3d_i8_mc(st + A_B + crank * (B_B / CL), &tmB, 0,
+                                              (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / CL)), 0, &full[s], CMASK);
+                    }
                 }
                 __syncwarp();
-                if (++s == SST) {
+                if (++s == NS) {
                     s = 0;
                     ph ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        // MMA issuer: whole warp, one elected lane issues
-        const bool leader = elect_one();
-        const uint32_t idesc = umma::idesc_s8_s32(BM, NPL * CT);
+        // MMA issuer: whole warp, one elected lane issues (PAIR: the leader CTA alone, for both)
+        const bool leader = elect_one() && (!PAIR || crank == 0);
+        const uint32_t idesc = umma::idesc_s8_s32(PAIR ? 2 * BM : BM, NPL * CT);
         const uint64_t adesc0 = umma::desc_kmajor_sw64(smem_u32(st_base), 0), bdesc0 = umma::desc_kmajor_sw64(smem_u32(st_base + A_B), 0);
         int s = 0, tl = 0;
         uint32_t ph = 0;
-        for (int item = cid; item < nitems; item += ncl, ++tl) {
+        for (int item = (PAIR && crank != 0) ? nitems : cid; item < nitems; item += ncl, ++tl) {
             int chunk, db, ct, nsteps;
             long long r0;
             item_geom(item, chunk, db, ct, r0, nsteps);
@@ -906,24 +980,34 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 umma::mbar_wait_bounded(&full[s], ph);
                 umma::fence_after_sync();
                 if (leader) {
-                    const uint64_t off = (uint64_t)(s * ((A_B + B_B) >> 4));
-                    umma::mma_i8(dacc, adesc0 + off, bdesc0 + off, idesc, k ? 1u : 0u);
-                    umma::mma_i8(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
-                    if (CL == 1) umma::mma_commit(&empty[s]);
-                    else mma_commit_mc(&empty[s], CMASK);
+                    const uint64_t off = (uint64_t)(s * (STG >> 4));
+                    if (PAIR) {
+                        umma::mma_i8_pair(dacc, adesc0 + off, bdesc0 + off, idesc, k ? 1u : 0u);
+                        umma::mma_i8_pair(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
+                        umma::mma_commit_pair(&empty[s]);
+                    } else {
+                        umma::mma_i8(dacc, adesc0 + off, bdesc0 + off, idesc, k ? 1u : 0u);
+                        umma::mma_i8(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
+                        if (CL == 1) umma::mma_commit(&empty[s]);
+                        else mma_commit_mc(&empty[s], CMASK);
+                    }
                 }
                 __syncwarp();
-                if (++s == SST) {
+                if (++s == NS) {
                     s = 0;
                     ph ^= 1;
                 }
             }
-            if (leader) umma::mma_commit(&tfull[buf]);
+            if (leader) {
+                if (PAIR) umma::mma_commit_pair(&tfull[buf]);
+                else umma::mma_commit(&tfull[buf]);
+            }
             __syncwarp();
         }
     } else {
         const StatLayout L(D, q);
         const int wq = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t tempty_l = PAIR ? umma::map_to_cta(tempty, 0) : 0u;
         int tl = 0;
         for (int item = cid; item < nitems; item += ncl, ++tl) {
             int chunk, db, ct, nsteps;
@@ -960,13 +1044,19 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             umma::fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[buf]);
+            if (lane == 0) {
+                if (PAIR) umma::mbar_arrive_cluster(tempty_l + (uint32_t)buf * 8u);
+                else mbar_arrive(&tempty[buf]);
+            }
         }
     }
     umma::fence_before_sync();
     __syncthreads();
     if (CL > 1) cluster_sync_all();
-    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+    if (warp == 1) {
+        if (PAIR) umma::tmem_dealloc2(tmem, 512);
+        else umma::tmem_dealloc(tmem, 512);
+    }
 }
 
 
@@ -1101,10 +1191,14 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     }
-    const int hstage = i8_hstage(D, q);
-    const int nst = i8_stages(D, q, hstage);
+    // tcgen05.mma.cta_group::2 where digit stages are scarce (D = 1024: 5 stages of 14 KB next to the 128 KB mask block -> 10 of
+    // 7 KB; K1 4.49 -> 4.19 ms on the config-3 shard).  Where eight full stages fit anyway (D <= 512) the pair only couples the
+    // two CTAs' epilogues (D = 256: 0.43 -> 0.54 ms): plain clusters with multicast there.
+    const int pair = (cl == 2 && i8_pair_mode() && i8_stages(D, q, i8_hstage(D, q), 0) < 8) ? 1 : 0;
+    const int hstage = pair ? ((i8_stages(D, q, 0, 1) < 12 && i8_stages(D, q, 1, 1) > i8_stages(D, q, 0, 1)) ? 1 : 0) : i8_hstage(D, q);
+    const int nst = i8_stages(D, q, hstage, pair);
     if (nst < 2) return cudaErrorNotSupported;
-    const size_t smem = i8_smem_bytes(D, q, nst, hstage);
+    const size_t smem = i8_smem_bytes(D, q, nst, hstage, pair);
     CUtensorMap tmO8;
     {   // the same rows as 8-column x 32-row boxes (64-byte rows, SWIZZLE_64B) for the half-staging epilogue
         EncodeTiledFn enc = get_encode_i8();
@@ -1117,7 +1211,7 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
     }
     long long gl_ = (nrb + cl - 1) / cl * cl;
     const int grid = (int)(gl_ < 148 ? gl_ : 148 / cl * cl);
-    auto kern = cl == 4 ? zstep_i8_kernel<4> : cl == 2 ? zstep_i8_kernel<2> : zstep_i8_kernel<1>;
+    auto kern = cl == 4 ? zstep_i8_kernel<4> : cl == 2 ? (pair ? zstep_i8_kernel<2, true> : zstep_i8_kernel<2>) : zstep_i8_kernel<1>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     static long long *prof = nullptr;
@@ -1161,6 +1255,14 @@ cudaError_t launch_stats_i8_check(int D, int q, const double *ws, int nchunks, c
     return cudaGetLastError();
 }
 
+static int stats_pair_min_d() {                          // PYVB_I8_STATS_PAIR_D: smallest D that uses the CTA-pair MMA in K3-i8
+    static int d = -1;
+    if (d < 0) {
+        const char *e = getenv("PYVB_I8_STATS_PAIR_D");
+        d = e ? atoi(e) : 512;
+    }
+    return d;
+}
 static long long gcd_ll(long long a, long long b) { return b ? gcd_ll(b, a % b) : a; }
 // chunks: items = ndb * nct * nchunks a whole number of rounds over 148 CTAs, chunks of >= 32 K steps, <= 2^23 rows
 int stats_i8_nchunks(long long N, int D, int q) {
@@ -1242,9 +1344,10 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
     }
-    const size_t smem = si8_smem_bytes(q);
     const int cl = i8_cluster_size();
-    auto kern = cl == 4 ? stats_i8_kernel<4> : cl == 2 ? stats_i8_kernel<2> : stats_i8_kernel<1>;
+    const int pair = (cl == 2 && i8_pair_mode() && ndb >= 2 && D >= stats_pair_min_d()) ? 1 : 0;   // tcgen05.mma.cta_group::2
+    const size_t smem = si8_smem_bytes(q, pair);
+    auto kern = cl == 4 ? stats_i8_kernel<4> : cl == 2 ? (pair ? stats_i8_kernel<2, true> : stats_i8_kernel<2>) : stats_i8_kernel<1>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long nitems = (long long)((ndb + cl - 1) / cl) * nct * nchunks;
