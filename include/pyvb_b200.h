@@ -101,7 +101,7 @@ extern "C" {
 /* algorithm selector for zstep / stats */
 #define PYVB_ALGO_AUTO 0
 #define PYVB_ALGO_GENERIC 1  /* any D, q <= 64; FP64 FMA */
-#define PYVB_ALGO_DMMA 2     /* FP64 tensor-core (DMMA) + TMA staging; q in {8,16,32}, D % 16 == 0 */
+#define PYVB_ALGO_DMMA 2     /* FP64 tensor-core (DMMA) + TMA staging; q in {8,16,32,64}, D % 16 == 0 */
 #define PYVB_ALGO_F32 4      /* FP32 variant (tcgen05): only for pyvb_stats_workspace_bytes */
 #define PYVB_ALGO_DMMA_K1 3  /* measurement only (zstep): the tensor-core contraction alone; the MZ rows are
                                 left as [qprec packed | eta] for pyvb_zsolve_f64 */

@@ -177,7 +177,7 @@ int pyvb_zstep_f64(long long N, int D, int q, const double *X, long long ldx, co
     const int a = pick_algo(algo, D, q);
     cudaError_t e;
     if (a == PYVB_ALGO_DMMA) {
-        if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32}, D % 16 == 0");
+        if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32,64}, D % 16 == 0");
         ARG(ldg == pyvb_gw_pitch(q), "ldg must equal pyvb_gw_pitch(q) for the DMMA path");
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
         ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
@@ -234,7 +234,7 @@ int pyvb_stats_f64(long long N, int D, int q, const double *X, long long ldx, co
     cudaError_t e;
     double *ws_main = (double *)ws;
     if (a == PYVB_ALGO_DMMA) {
-        if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32}, D % 16 == 0");
+        if (!dmma_supported(D, q)) return fail(PYVB_ENOSUP, "%s", "DMMA path needs q in {8,16,32,64}, D % 16 == 0");
         ARG((ldx % 2) == 0, "ldx must be even for the DMMA path");
         ARG(ldz == pyvb_mz_pitch(q) && ldm == ldz && Zbar == M2 + gw_woff(q),
             "the DMMA path needs the interleaved MZ layout (see pyvb_mz_pitch)");

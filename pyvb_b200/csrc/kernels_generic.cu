@@ -532,7 +532,13 @@ stats_reduce_kernel(int D, int q, const double *__restrict__ ws_main, int nchunk
     if ((int)threadIdx.x < world && (int)threadIdx.x != rank) {
         const unsigned long long *pf = static_cast<const unsigned long long *>(peer_bufs[threadIdx.x]) +
                                        (size_t)par * PYVB_PEER_MAXBLK + blockIdx.x;
-        while (ld_acquire_sys(pf) < epoch) __nanosleep(64);
+        // bounded: a dead or failed peer must not hang this GPU forever (~5 s, then the kernel traps: a CUDA error on the
+        // next synchronisation instead of a wedged device)
+        unsigned int spins = 0;
+        while (ld_acquire_sys(pf) < epoch) {
+            __nanosleep(256);
+            if (++spins > (1u << 24)) __trap();
+        }
     }
     __syncthreads();
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < L.len; o += (size_t)gridDim.x * blockDim.x) {
@@ -554,8 +560,20 @@ cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks
                                 cudaStream_t st) {
     const StatLayout L(D, q);
     size_t b = (L.len + 255) / 256;
-    // all CTAs must be co-resident when they wait for their peers: at most 2 per SM (and <= PYVB_PEER_MAXBLK)
-    if (b > 148 * 2) b = 148 * 2;
+    // all CTAs must be co-resident when they wait for their peers: what the occupancy calculator says fits on THIS device
+    // (SM count queried, not assumed), at most 2 per SM and <= PYVB_PEER_MAXBLK
+    static int cap[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cap[dev] == 0) {
+        int sms = 0, per = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, stats_reduce_kernel, 256, 0) != cudaSuccess || per <= 0) per = 1;
+        if (per > 2) per = 2;
+        cap[dev] = sms * per < PYVB_PEER_MAXBLK ? sms * per : PYVB_PEER_MAXBLK;
+    }
+    const size_t bmax = (dev >= 0 && dev < 64) ? (size_t)cap[dev] : 148;
+    if (b > bmax) b = bmax;
     stats_reduce_kernel<<<(unsigned)b, 256, 0, st>>>(D, q, ws_main, nchunks, ws_sc, nblk, stats, xcache, use_xcache,
                                                      zsums, nzblk, zkw, peer_bufs, world, rank, epoch);
     return cudaGetLastError();

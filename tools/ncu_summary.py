@@ -23,7 +23,10 @@ KEYS = [
 
 def main():
     for rep in sys.argv[1:]:
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if rep.endswith(".csv"):                 # a raw page exported on the GPU box (ncu -i rep --page raw --csv)
+            out = open(rep).read()
+        else:
+            out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(out)))
         if len(rows) < 3:
             print(rep, "no data"); continue
