@@ -234,15 +234,16 @@ struct I8Geom {
 constexpr int OUT_B = 8 * 32 * 16 * 8;                  // epilogue staging: 8 warps x (32 rows x 16 columns) doubles
 // hstage: the epilogue stages (and stores) 8 columns at a time: half the staging memory, one more digit stage at D = 1024
 // pair: cta_group::2 -- a CTA holds HALF of every digit tile (7 KB per stage)
-size_t i8_smem_bytes(int D, int q, int nst, int hstage, int pair = 0) {
+// adbl: TWO mask blocks (the next row block's is fetched while the current one is multiplied)
+size_t i8_smem_bytes(int D, int q, int nst, int hstage, int pair = 0, int adbl = 0) {
     const I8Geom g(q);
-    const int nk = D / BKB;
+    const int nk = D / BKB * (adbl ? 2 : 1);
     return 1024 + (size_t)nk * A_B + (size_t)nst * (pair ? B_B / 2 : B_B) + (hstage ? OUT_B / 2 : OUT_B) + (size_t)(2 * g.NC8) * 8 +
            (size_t)(2 * nk + 2 * nst + 4) * 8 + 16;
 }
-int i8_stages(int D, int q, int hstage, int pair = 0) {  // digit-tile stages that fit next to the resident mask block
+int i8_stages(int D, int q, int hstage, int pair = 0, int adbl = 0) {  // digit-tile stages that fit next to the resident mask block(s)
     for (int nst = pair ? ST : ST / 2; nst >= 2; --nst)
-        if (i8_smem_bytes(D, q, nst, hstage, pair) <= 227 * 1024) return nst;
+        if (i8_smem_bytes(D, q, nst, hstage, pair, adbl) <= 227 * 1024) return nst;
     return 0;
 }
 int i8_pair_mode() {                                     // PYVB_I8_PAIR = 0 | 1 (default 1): tcgen05.mma.cta_group::2 in K1-i8 / K3-i8
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NTHR, 1)
 zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO8, long long N, int D, int q,
                 const double *__restrict__ P0, const double *__restrict__ gscale, const double *__restrict__ gl, int nrb,
-                int nst, int hstage, long long *prof) {
+                int nst, int hstage, int adbl, long long *prof) {
     const I8Geom G(q);
     long long w0 = 0, w1 = 0, w2 = 0;                          // PYVB_I8_PROF: clocks spent waiting, per role
     const long long tstart = clock64();
@@ -295,14 +296,17 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
     constexpr int BSZ = PAIR ? B_B / 2 : B_B;                                  // bytes of a digit stage in THIS CTA
     const int nk = D / BKB;
-    unsigned char *a_base = smem;                                              // [nk][128 x 64 B] resident mask block
-    unsigned char *b_base = smem + (size_t)nk * A_B;                           // [nst][224 (PAIR: 112) x 64 B] digit tiles
+    // adbl: two mask blocks -- the block of row block rl + 1 is fetched while row block rl is multiplied (without it every
+    // row block starts with the latency of its 128 x D mask load: a quarter of the kernel at D = 256)
+    const int nab = adbl ? 2 : 1;
+    unsigned char *a_base = smem;                                              // [nab][nk][128 x 64 B] resident mask block(s)
+    unsigned char *b_base = smem + (size_t)nab * nk * A_B;                     // [nst][224 (PAIR: 112) x 64 B] digit tiles
     unsigned char *o_base = b_base + (size_t)nst * BSZ;                        // [8 warps][32 rows x 128 B] output staging (swizzled)
     double *p0v = reinterpret_cast<double *>(o_base + (hstage ? OUT_B / 2 : OUT_B));   // [NC8]: packed P0, zero pad
     double *fcol = p0v + G.NC8;                                                // [NC8]: tau * scale_c * 2^-54
-    uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nk]
-    uint64_t *aempty = afull + nk;                                             // [nk]
-    uint64_t *full = aempty + nk;                                              // [nst]
+    uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nab][nk]
+    uint64_t *aempty = afull + nab * nk;                                       // [nab][nk]
+    uint64_t *full = aempty + nab * nk;                                        // [nst]
     uint64_t *empty = full + nst;                                              // [nst]
     uint64_t *tfull = empty + nst;                                             // [2]
     uint64_t *tempty = tfull + 2;                                              // [2]
@@ -336,7 +340,7 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO);
         tma_prefetch_desc(&tmO8);
-        for (int k = 0; k < nk; ++k) {
+        for (int k = 0; k < nab * nk; ++k) {
             mbar_init(&afull[k], 1);
             mbar_init(&aempty[k], 1);
         }
@@ -367,20 +371,26 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int s = 0;
         uint32_t ph = 0;
         for (int rl = 0; rl < niter; ++rl) {
-            const int rb = (int)blockIdx.x + rl * (int)gridDim.x;
             for (int ci = 0; ci < G.NCT; ++ci) {
                 const int ct = (ci + ct0 < G.NCT) ? ci + ct0 : ci + ct0 - G.NCT;
                 for (int ki = 0; ki < nk; ++ki) {
                     const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
-                    if (ci == 0) {      // the mask chunk of the previous row block has been consumed by its last column tile
-                        PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[kb], (uint32_t)((rl & 1) ^ 1)));
-                        if (leader) {
-                            if (PAIR) {        // both CTAs' chunks complete on the LEADER's barrier (armed by the leader for both)
-                                if (crank == 0) mbar_arrive_expect_tx(&afull[kb], (uint32_t)(2 * A_B));
-                                tma_load_3d_i8_pair(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, afull_l + (uint32_t)kb * 8u);
-                            } else {
-                                mbar_arrive_expect_tx(&afull[kb], (uint32_t)A_B);
-                                tma_load_3d_i8(a_base + (size_t)kb * A_B, &tmA, 0, (rb * nk + kb) * BM, 0, &afull[kb]);   // past the end: zero fill
+                    if (ci == 0) {
+                        // mask chunk kb of row block r into buffer r % nab, once that buffer's previous user (row block r - nab)
+                        // has been consumed by its last column tile.  Two buffers: row block rl + 1 is fetched NOW, a whole
+                        // row block ahead of its use (and row block 0 with it).
+                        for (int r = (nab == 2 && rl > 0) ? rl + 1 : rl; r <= rl + nab - 1 && r < niter; ++r) {
+                            const int ab = (r & (nab - 1)) * nk + kb;
+                            const int rbr = (int)blockIdx.x + r * (int)gridDim.x;
+                            PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[ab], (uint32_t)(((r / nab) & 1) ^ 1)));
+                            if (leader) {
+                                if (PAIR) {    // both CTAs' chunks complete on the LEADER's barrier (armed by the leader for both)
+                                    if (crank == 0) mbar_arrive_expect_tx(&afull[ab], (uint32_t)(2 * A_B));
+                                    tma_load_3d_i8_pair(a_base + (size_t)ab * A_B, &tmA, 0, (rbr * nk + kb) * BM, 0, afull_l + (uint32_t)ab * 8u);
+                                } else {
+                                    mbar_arrive_expect_tx(&afull[ab], (uint32_t)A_B);
+                                    tma_load_3d_i8(a_base + (size_t)ab * A_B, &tmA, 0, (rbr * nk + kb) * BM, 0, &afull[ab]);   // past the end: zero fill
+                                }
                             }
                         }
                     }
@@ -424,22 +434,23 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const uint32_t dacc = tmem + (uint32_t)(buf * 256);
                 for (int ki = 0; ki < nk; ++ki) {
                     const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
-                    if (ci == 0) PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[kb], (uint32_t)(rl & 1)));
+                    const int ab = (rl & (nab - 1)) * nk + kb;               // mask chunk kb of this row block's buffer
+                    if (ci == 0) PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[ab], (uint32_t)((rl / nab) & 1)));
                     PROF_WAIT(w0, umma::mbar_wait_bounded(&full[s], ph));
                     umma::fence_after_sync();
                     if (leader) {
-                        const uint64_t ad = adesc0 + (uint64_t)(kb * (A_B >> 4)), bd = bdesc0 + (uint64_t)(s * (BSZ >> 4));
+                        const uint64_t ad = adesc0 + (uint64_t)(ab * (A_B >> 4)), bd = bdesc0 + (uint64_t)(s * (BSZ >> 4));
                         if (PAIR) {
                             umma::mma_i8_pair(dacc, ad, bd, idesc, ki ? 1u : 0u);
                             umma::mma_i8_pair(dacc, ad + 2, bd + 2, idesc, 1u);
                             umma::mma_commit_pair(&empty[s]);                            // frees the stage in both CTAs
-                            if (ci == G.NCT - 1) umma::mma_commit_pair(&aempty[kb]);
+                            if (ci == G.NCT - 1) umma::mma_commit_pair(&aempty[ab]);
                         } else {
                             umma::mma_i8(dacc, ad, bd, idesc, ki ? 1u : 0u);
                             umma::mma_i8(dacc, ad + 2, bd + 2, idesc, 1u);
                             if (CL == 1) umma::mma_commit(&empty[s]);
                             else mma_commit_mc(&empty[s], CMASK);
-                            if (ci == G.NCT - 1) umma::mma_commit(&aempty[kb]);
+                            if (ci == G.NCT - 1) umma::mma_commit(&aempty[ab]);
                         }
                     }
                     __syncwarp();
@@ -1196,9 +1207,16 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
     // two CTAs' epilogues (D = 256: 0.43 -> 0.54 ms): plain clusters with multicast there.
     const int pair = (cl == 2 && i8_pair_mode() && i8_stages(D, q, i8_hstage(D, q), 0) < 8) ? 1 : 0;
     const int hstage = pair ? ((i8_stages(D, q, 0, 1) < 12 && i8_stages(D, q, 1, 1) > i8_stages(D, q, 0, 1)) ? 1 : 0) : i8_hstage(D, q);
-    const int nst = i8_stages(D, q, hstage, pair);
+    // a second mask block where it costs no digit stage (D <= 256): PYVB_I8_ADBL=0 switches it off
+    static int adbl_on = -1;
+    if (adbl_on < 0) {
+        const char *ev = getenv("PYVB_I8_ADBL");
+        adbl_on = (ev && ev[0] == '0') ? 0 : 1;
+    }
+    const int adbl = (adbl_on && !pair && i8_stages(D, q, hstage, 0, 1) >= ST / 2) ? 1 : 0;
+    const int nst = i8_stages(D, q, hstage, pair, adbl);
     if (nst < 2) return cudaErrorNotSupported;
-    const size_t smem = i8_smem_bytes(D, q, nst, hstage, pair);
+    const size_t smem = i8_smem_bytes(D, q, nst, hstage, pair, adbl);
     CUtensorMap tmO8;
     {   // the same rows as 8-column x 32-row boxes (64-byte rows, SWIZZLE_64B) for the half-staging epilogue
         EncodeTiledFn enc = get_encode_i8();
@@ -1220,7 +1238,7 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
         prof_on = getenv("PYVB_I8_PROF") ? 1 : 0;
         if (prof_on && cudaMalloc(&prof, 148 * 10 * sizeof(long long)) != cudaSuccess) prof_on = 0;
     }
-    e = launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, tmO, tmO8, N, D, q, P0, gscale, gl, (int)nrb, nst, hstage,
+    e = launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, tmO, tmO8, N, D, q, P0, gscale, gl, (int)nrb, nst, hstage, adbl,
                        prof_on ? prof : (long long *)nullptr);
     if (prof_on && e == cudaSuccess) {      // diagnosis only: synchronises
         long long h[148 * 10];
