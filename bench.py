@@ -323,12 +323,12 @@ def rooflines(eng, kt, rows, ms_sweep, hbm, peak_tf, traffic_json):
         ncz = (P + q + 31) // 32 * 32
         by = {"zstep_i8_kernel (INT8 mask contraction -> qprec)": (rows * (1.0 * D + 8.0 * P), kt["zstep_k1_i8_ms"]),
               "zstep_dmma_kernel<ETA> (eta = O.(X-mu) @ W, FP64 tensor cores)": (rows * (8.0 * D + 8.0 * q), kt["zstep_k1_eta_ms"]),
-              "zsolve (K2: batched q x q Cholesky / inverse / solve)": (rows * (16.0 * (P + q) + 8.0), kt["zsolve_k2_ms"]),
+              "zsolve (K2: batched q x q SPD inverse / solve)": (rows * (16.0 * (P + q) + 8.0), kt["zsolve_k2_ms"]),
               "statistics (digitize + INT8 T1/Bst + DMMA Ast + guard + reduce)":
                   (rows * (8.0 * (P + q) + 7.0 * ncz + 1.0 * D + 7.0 * ncz + 8.0 * D + 8.0 * q), kt["stats_ms"])}
         table = {k: {"ms": v[1], "algorithmic_GB": v[0] * 1e-9, "GBps": v[0] / (v[1] * 1e-3) * 1e-9,
                      "frac_of_hbm_peak": v[0] / (v[1] * 1e-3) * 1e-9 / hbm} for k, v in by.items()}
-        kname = "zsolve (K2: batched q x q Cholesky / inverse / solve, in place on the MZ rows)"
+        kname = "zsolve (K2: batched q x q SPD inverse / solve, in place on the MZ rows; Gauss-Jordan in registers at q = 16, 32)"
         by_dom, ms_dom = rows * (16.0 * (P + q) + 8.0), kt["zsolve_k2_ms"]
         traffic = None
         t = traffic_json.get("zsolve%d_dram_bytes_per_row" % q)

@@ -656,12 +656,19 @@ static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double 
 // blocked / tpm overrides the default (measured per 1M rows, FP64: q = 16: 1.62 / 2.0 / see DESIGN ms; q = 32: 9.0 / 5.8).
 int k2_impl(int q) {
     const char *e = getenv("PYVB_K2");               // read per call (tests flip it); callers size zsums with pyvb_zsums_len
-    int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : (e && e[0] == 'l') ? 3 : -1;
+    int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : (e && e[0] == 'l') ? 3
+               : (e && e[0] == 'g') ? 4 : -1;
     if (q == 64 && (mode == 0 || mode == 2)) mode = -1;  // q = 64 only exists blocked
     if (mode == 2 && q > 16) mode = -1;
     if (mode == 3 && q < 16) mode = -1;
+    if (mode == 4 && q != 16 && q != 32) mode = -1;
     if (mode >= 0) return mode;
+    if (q == 16 || q == 32) return 4;
     return q >= 32 ? 1 : 2;      // (the lane-parallel-diagonal kernel, 3, is not faster: 7.7 vs 7.4 ms at q = 32)
+}
+int k2_impl_f32(int q) {
+    const int impl = k2_impl(q);
+    return impl == 4 ? (q >= 32 ? 1 : 2) : impl;
 }
 
 void zsolve_partials(long long N, int q, int &nblk, int &kw) {
@@ -682,6 +689,11 @@ void zsolve_partials(long long N, int q, int &nblk, int &kw) {
     if (impl == 3) {
         kw = zsolve_lanediag_kw(q);
         nblk = kw > 0 ? zsolve_lanediag_blocks(N, q) : 0;
+        return;
+    }
+    if (impl == 4) {
+        kw = zsolve_gj_kw(q);
+        nblk = kw > 0 ? zsolve_gj_blocks(N, q) : 0;
         return;
     }
     switch (q) {
@@ -775,6 +787,7 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
     if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 3) return launch_zsolve_lanediag(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
+    if (impl == 4) return launch_zsolve_gj(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (cond != nullptr || chk.gscale != nullptr) return cudaErrorNotSupported;   // the cross-check kernel has no guard
     switch (q) {
         case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);

@@ -502,7 +502,7 @@ cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, d
 }
 
 void zsolve_partials_f32(long long N, int q, int &nblk, int &kw) {
-    if (q == 16 && k2_impl(q) == 2) {
+    if (q == 16 && k2_impl_f32(q) == 2) {
         kw = zsolve_tpm_kw(q);
         nblk = N > 0 ? zsolve_tpm_blocks(N, q) : 0;
         return;
@@ -515,7 +515,7 @@ void zsolve_partials_f32(long long N, int q, int &nblk, int &kw) {
 cudaError_t launch_zsolve_f32(long long N, int q, float *MZ32, void *MP, double *Sig, double *logdet, double *gl,
                               double *zsums, cudaStream_t st) {
     if (N <= 0) return cudaSuccess;
-    if (q == 16 && k2_impl(q) == 2) return launch_zsolve_tpm_f32(N, q, MZ32, MP, Sig, logdet, gl, zsums, st);
+    if (q == 16 && k2_impl_f32(q) == 2) return launch_zsolve_tpm_f32(N, q, MZ32, MP, Sig, logdet, gl, zsums, st);
     switch (q) {
         case 16: return launch_blocked_q<16, true>(N, MZ32, Sig, logdet, gl, zsums, MP, st);
         case 32: return launch_blocked_q<32, true>(N, MZ32, Sig, logdet, gl, zsums, MP, st);

@@ -10,7 +10,7 @@ dev = torch.device("cuda", 0)
 cases = [(16, 1000000), (32, 1000000), (64, 400000), (8, 1000000)]
 if len(sys.argv) > 2:
     cases = [(int(sys.argv[1]), int(sys.argv[2]))]
-impls = ["reg", "blocked", "tpm", "lanediag"] if len(sys.argv) <= 3 else [sys.argv[3]]
+impls = ["reg", "blocked", "tpm", "lanediag", "gj"] if len(sys.argv) <= 3 else [sys.argv[3]]
 for q, N in cases:
     P = q * (q + 1) // 2
     ld, zoff = int(lib.pyvb_mz_pitch(q)), int(lib.pyvb_gw_woff(q))
@@ -23,7 +23,8 @@ for q, N in cases:
     logdet = torch.zeros(N, dtype=torch.float64, device=dev)
     gl = torch.zeros(144, dtype=torch.float64, device=dev)
     for impl in impls:
-        if (impl == "reg" and q == 64) or (impl == "tpm" and q > 16) or (impl == "lanediag" and q < 16):
+        if (impl == "reg" and q == 64) or (impl == "tpm" and q > 16) or (impl == "lanediag" and q < 16) or \
+                (impl == "gj" and q not in (16, 32)):
             continue
         os.environ["PYVB_K2"] = impl
         nz = int(lib.pyvb_zsums_len(N, q))
