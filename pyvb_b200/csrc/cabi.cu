@@ -118,9 +118,13 @@ size_t pyvb_zsums_len_f32(long long N, int q) {
 int pyvb_zsums_kw(int q) { return 2 * (gw_woff(q) + q) + PYVB_ZS_EXTRA; }
 
 size_t pyvb_zsums_len(long long N, int q) {
-    int nblk, kw;
-    zsolve_partials(N, q, nblk, kw);
-    return (size_t)nblk * kw;
+    size_t len = 0;                                     // the largest over the K2 implementations (PYVB_K2 is read per call)
+    for (int impl = 0; impl <= 4; ++impl) {
+        int nblk, kw;
+        zsolve_partials_of(impl, N, q, nblk, kw);
+        if ((size_t)nblk * kw > len) len = (size_t)nblk * kw;
+    }
+    return len;
 }
 
 size_t pyvb_peer_bytes(size_t stats_len) { return peer_buffer_bytes(stats_len); }

@@ -67,6 +67,7 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
                           cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
 // K2 leaves nblk partials of kw doubles each in zsums (0, 0: no fast K2 for this q)
 void zsolve_partials(long long N, int q, int &nblk, int &kw);
+void zsolve_partials_of(int impl, long long N, int q, int &nblk, int &kw);
 // blocked tensor-core K2 (kernels_k2.cu): q in {8, 16, 32, 64}
 int zsolve_blocked_blocks(long long N, int q);
 int zsolve_blocked_kw(int q);

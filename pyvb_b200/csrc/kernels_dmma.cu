@@ -671,11 +671,14 @@ int k2_impl_f32(int q) {
     return impl == 4 ? (q >= 32 ? 1 : 2) : impl;
 }
 
-void zsolve_partials(long long N, int q, int &nblk, int &kw) {
+void zsolve_partials(long long N, int q, int &nblk, int &kw) { zsolve_partials_of(k2_impl(q), N, q, nblk, kw); }
+
+// the partials implementation `impl` leaves (pyvb_zsums_len sizes the buffer for the largest of them: PYVB_K2 may change
+// between the allocation and a later call)
+void zsolve_partials_of(int impl, long long N, int q, int &nblk, int &kw) {
     long long b = 0, r = 0;
     nblk = kw = 0;
     if (N <= 0) return;
-    const int impl = k2_impl(q);
     if (impl == 1) {
         kw = zsolve_blocked_kw(q);
         nblk = kw > 0 ? zsolve_blocked_blocks(N, q) : 0;

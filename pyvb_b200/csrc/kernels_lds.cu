@@ -13,6 +13,20 @@
 // (chol8.cuh), the smoother gain K_s = Sigma_s [Qbar A | A^T Qbar | C^T Rbar] (8 x 24) is spread over the lanes
 // (lane = row i, quarter p: 6 coefficients), and one Gauss-Seidel step is 6 FMAs + two shuffle reductions per lane.
 // State and observation dimensions are padded to 8 inside the kernel (q, d <= 8).
+//
+// The sweep over t (SCAN = true, the default).  A forward sweep is the recurrence  x_t = K1 x_{t-1} + u_t  with
+// u_t = K2 x_{t+1} + K3 y_t  made of values the sweep does not change, and K1 the same matrix for every interior t (the
+// backward sweep: x_t = K2 x_{t+1} + u'_t,  u'_t = K1 x_{t-1} + K3 y_t).  Done one step after the other -- SCAN = false, the
+// first version, kept as the cross-check -- it is a chain of 2T dependent steps of ~180 clocks each (6 % of the HBM roof).  Here:
+//   A. u_t for all t in parallel, four time steps per instruction (lane = (t mod 4, row)), written over x_t in place;
+//   B. the interior range is cut into <= 32 chunks of L steps, lane = chunk, K1 in the lane's registers:
+//      pass 1 runs every chunk from a zero start (its end value e_c), the chunk starts follow from
+//      E_c = e_c + K1^L E_{c-1}  (K1^L by binary powering, a short serial loop over the chunks), pass 2 reruns every chunk
+//      from its true start and stores x_t.
+// Same arithmetic as the step-by-step sweep up to the rounding of the chunk starts (1e-16 relative; the recurrence is a
+// contraction), 2 x 8 matrix-vector steps deep instead of 2T.
+#include <stdlib.h>
+
 #include "chol8.cuh"
 #include "common.cuh"
 #include "kernels.h"
@@ -22,15 +36,32 @@ namespace pyvb {
 
 namespace {
 
-constexpr int LW = 4;                       // warps (sequences) per CTA
+template <bool SCAN> struct LWC { static constexpr int LW = SCAN ? 1 : 4; };    // warps (sequences) per CTA (SCAN: as many one-warp CTAs as fit)
 
 // per-warp shared memory (doubles): xs [(T + 2)][8] (one zero row before and after), ys [T][d] (+ 8: the padded
-// columns of the last row are read with zero coefficients), then the small arrays
-__host__ __device__ inline size_t lds_warp_doubles(int T, int d) {
-    return (size_t)(T + 2) * 8 + (((size_t)T * d + 8 + 1) & ~(size_t)1) + 64 * 14;
+// columns of the last row are read with zero coefficients), then the small arrays; SCAN: + the interior gain [8][24] and the
+// chunk ends [32][8]
+__host__ __device__ inline size_t lds_warp_doubles(int T, int d, bool scan) {
+    return (size_t)(T + 2) * 8 + (((size_t)T * d + 8 + 1) & ~(size_t)1) + 64 * 14 + (scan ? 192 + 256 : 0);
 }
 
-__global__ void __launch_bounds__(32 * LW)
+// dst = A B (8 x 8, row-major, shared memory; dst distinct from A and B); lane (gid, qd) owns dst[gid][2qd], [2qd + 1]
+__device__ __forceinline__ void mat8_mul(double *dst, const double *A, const double *B, int gid, int qd) {
+    double r0 = 0.0, r1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double a = A[gid * 8 + k];
+        const double2 b = *reinterpret_cast<const double2 *>(B + k * 8 + 2 * qd);
+        r0 = fma(a, b.x, r0);
+        r1 = fma(a, b.y, r1);
+    }
+    __syncwarp();
+    *reinterpret_cast<double2 *>(dst + gid * 8 + 2 * qd) = make_double2(r0, r1);
+    __syncwarp();
+}
+
+template <bool SCAN>
+__global__ void __launch_bounds__(32 * LWC<SCAN>::LW)
 lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, double *__restrict__ X,
                    double *__restrict__ Xcov3, double *__restrict__ A, double *__restrict__ Avar, double *__restrict__ C,
                    double *__restrict__ Cvar, double *__restrict__ Qa, double *__restrict__ Qb, double *__restrict__ Ra,
@@ -39,7 +70,8 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
     extern __shared__ __align__(16) double smem_l[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gid = lane >> 2, qd = lane & 3;
-    double *base = smem_l + (size_t)warp * lds_warp_doubles(T, d);
+    constexpr int LW = LWC<SCAN>::LW;
+    double *base = smem_l + (size_t)warp * lds_warp_doubles(T, d, SCAN);
     double *xs = base + 8;                                  // xs[t * 8 + i], t = -1 .. T valid (zero rows at the ends)
     double *ys = base + (size_t)(T + 2) * 8;
     double *pA = ys + (((size_t)T * d + 8 + 1) & ~(size_t)1);   // [k][i]
@@ -49,6 +81,8 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
     double *sSA = tmp + 64, *sSC = sSA + 64, *sXX1 = sSC + 64, *sYX = sXX1 + 64;
     double *qbar = sYX + 64, *rbar = qbar + 8, *yy = rbar + 8, *xx0 = yy + 8;   // [8] each
     double *pK = xx0 + 8;                                   // [k][i]: known entries of A (NaN = free), examples/LDS_knowns_in_A.py:72-74
+    double *Kf = pK + 64;                                   // SCAN: [8][24] the interior smoother gain
+    double *ce = Kf + 192;                                  // SCAN: [32][8] chunk ends
 
     for (int b = blockIdx.x * LW + warp; b < B; b += gridDim.x * LW) {
         // ---- load the sequence and its parameters (padded to 8 x 8)
@@ -58,16 +92,21 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
         __syncwarp();
         const double *Yb = Y + (size_t)b * T * d;
         double *Xb = X + (size_t)b * T * q;
-        for (int i = lane; i < T * d; i += 32) ys[i] = Yb[i];
-        for (int i = lane; i < T * q; i += 32) xs[(i / q) * 8 + (i % q)] = Xb[i];
+        // (asynchronous copies, all in flight at once: with ~7 warps per SM a register-staged loop is a chain of HBM latencies)
+        for (int i = lane; i < T * d; i += 32) ldgsts8(ys + i, Yb + i);
+        for (int t0 = 0; t0 < T; t0 += 4) {                     // four rows per instruction: lane = (row mod 4, column)
+            const int t = t0 + (lane >> 3), i = lane & 7;
+            if (t < T && i < q) ldgsts8(xs + t * 8 + i, Xb + t * q + i);
+        }
         for (int i = lane; i < q * q; i += 32) {
-            pA[(i / q) * 8 + (i % q)] = A[(size_t)b * q * q + i];
-            pAv[(i / q) * 8 + (i % q)] = Avar[(size_t)b * q * q + i];
+            ldgsts8(pA + (i / q) * 8 + (i % q), A + (size_t)b * q * q + i);
+            ldgsts8(pAv + (i / q) * 8 + (i % q), Avar + (size_t)b * q * q + i);
         }
         for (int i = lane; i < d * q; i += 32) {
-            pC[(i / q) * 8 + (i % q)] = C[(size_t)b * d * q + i];
-            pCv[(i / q) * 8 + (i % q)] = Cvar[(size_t)b * d * q + i];
+            ldgsts8(pC + (i / q) * 8 + (i % q), C + (size_t)b * d * q + i);
+            ldgsts8(pCv + (i / q) * 8 + (i % q), Cvar + (size_t)b * d * q + i);
         }
+        ldgsts_wait_all();
         for (int i = lane; i < 64; i += 32) pK[i] = __longlong_as_double(0x7ff8000000000000LL);
         __syncwarp();
         if (Aknown != nullptr)
@@ -166,12 +205,169 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
                 if (qd == 0) xs[t * 8 + gid] = a;                   // row t is not an input of step t
                 __syncwarp();
             };
-            step(0, kc[0]);
-            for (int t = 1; t < T - 1; ++t) step(t, kc[1]);
-            step(T - 1, kc[2]);
-            step(T - 1, kc[2]);
-            for (int t = T - 2; t >= 1; --t) step(t, kc[1]);
-            step(0, kc[0]);
+            if (!SCAN) {
+                step(0, kc[0]);
+                for (int t = 1; t < T - 1; ++t) step(t, kc[1]);
+                step(T - 1, kc[2]);
+                step(T - 1, kc[2]);
+                for (int t = T - 2; t >= 1; --t) step(t, kc[1]);
+                step(0, kc[0]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 6; ++m) Kf[gid * 24 + qd * 6 + m] = kc[1][m];
+                __syncwarp();
+                const int n = T - 2;                                // interior steps t = 1 .. T-2 (T >= 3)
+                const int L = (n + 31) / 32, nch = (n + L - 1) / L;
+                // one sweep over the interior: fwd: t = 1 .. T-2 from x_0;  !fwd: t = T-2 .. 1 from x_{T-1}
+                auto sweep = [&](const bool fwd) {
+                    {   // A. u_t = [K2 | K3] [x_{t+1} | y_t]  (fwd)  /  [K1 | K3] [x_{t-1} | y_t]: lane = (t mod 4, row)
+                        const int tt = lane >> 3, i = lane & 7;
+                        double F[16];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            F[c] = Kf[i * 24 + (fwd ? 8 : 0) + c];
+                            F[8 + c] = Kf[i * 24 + 16 + c];
+                        }
+                        for (int g0 = 0; g0 < n; g0 += 8) {             // two groups of four time steps in flight
+                            double acc[2];
+                            int tw[2];
+                            bool act[2];
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                int idx = g0 + 4 * h + tt;
+                                act[h] = idx < n;
+                                if (!act[h]) idx = n - 1;
+                                const int t = fwd ? 1 + idx : T - 2 - idx;
+                                tw[h] = t;
+                                const double *xr = xs + (fwd ? t + 1 : t - 1) * 8, *yr = ys + t * d;
+                                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+                                for (int c = 0; c < 8; c += 4) {
+                                    const double2 xv = *reinterpret_cast<const double2 *>(xr + c);
+                                    const double2 xw = *reinterpret_cast<const double2 *>(xr + c + 2);
+                                    a0 = fma(F[c], xv.x, a0);
+                                    a1 = fma(F[c + 1], xv.y, a1);
+                                    a2 = fma(F[c + 2], xw.x, a2);
+                                    a3 = fma(F[c + 3], xw.y, a3);
+                                }
+#pragma unroll
+                                for (int c = 0; c < 8; c += 4) {        // (padded observation columns: zero gain, finite data)
+                                    a0 = fma(F[8 + c], yr[c], a0);
+                                    a1 = fma(F[9 + c], yr[c + 1], a1);
+                                    a2 = fma(F[10 + c], yr[c + 2], a2);
+                                    a3 = fma(F[11 + c], yr[c + 3], a3);
+                                }
+                                acc[h] = (a0 + a1) + (a2 + a3);
+                            }
+                            __syncwarp();                               // a row written here is an input of a neighbouring lane group
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                                if (act[h]) xs[tw[h] * 8 + i] = acc[h];
+                        }
+                        __syncwarp();
+                    }
+                    // B. the recurrence matrix, row-major in `tmp`, and its L-th power in Mr (binary powering; the statistics
+                    //    arrays are free until the sweeps are over)
+                    for (int e = lane; e < 64; e += 32) tmp[e] = Kf[(e >> 3) * 24 + (fwd ? 0 : 8) + (e & 7)];
+                    __syncwarp();
+                    double *Mr = sSA, *Mt = sSC, *Mb = sXX1, *Mt2 = sYX;
+                    if (nch > 1) {
+                        bool have = false;
+                        const double *bs = tmp;
+                        for (int e = L; e; e >>= 1) {
+                            if (e & 1) {
+                                if (!have) {
+                                    for (int k = lane; k < 64; k += 32) Mr[k] = bs[k];
+                                    __syncwarp();
+                                    have = true;
+                                } else {
+                                    mat8_mul(Mt, Mr, bs, gid, qd);
+                                    double *sw = Mr; Mr = Mt; Mt = sw;
+                                }
+                            }
+                            if (e >> 1) {
+                                double *dst = (bs == Mb) ? Mt2 : Mb;
+                                mat8_mul(dst, bs, bs, gid, qd);
+                                bs = dst;
+                            }
+                        }
+                    }
+                    double Kr[8][8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int j = 0; j < 8; j += 2) {
+                            const double2 v = *reinterpret_cast<const double2 *>(tmp + r * 8 + j);
+                            Kr[r][j] = v.x;
+                            Kr[r][j + 1] = v.y;
+                        }
+                    const double *start0 = fwd ? xs : xs + (T - 1) * 8;   // the row the first chunk starts from
+                    // one chunk, from the start value x[]; STORE: x_t replaces u_t
+                    auto chunk = [&](double (&x)[8], const bool store) {
+                        for (int sidx = 0; sidx < L; ++sidx) {
+                            const int idx = lane * L + sidx;
+                            if (idx < n) {
+                                double *row = xs + (fwd ? 1 + idx : T - 2 - idx) * 8;
+                                double xn[8];
+#pragma unroll
+                                for (int r = 0; r < 8; r += 2) {
+                                    const double2 u = *reinterpret_cast<const double2 *>(row + r);
+                                    xn[r] = u.x;
+                                    xn[r + 1] = u.y;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                                    for (int r = 0; r < 8; ++r) xn[r] = fma(Kr[r][j], x[j], xn[r]);
+#pragma unroll
+                                for (int r = 0; r < 8; ++r) x[r] = xn[r];
+                                if (store) {
+#pragma unroll
+                                    for (int r = 0; r < 8; r += 2)
+                                        *reinterpret_cast<double2 *>(row + r) = make_double2(xn[r], xn[r + 1]);
+                                }
+                            }
+                        }
+                    };
+                    double x[8];
+                    if (nch > 1) {
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) x[r] = 0.0;
+                        chunk(x, false);                                 // pass 1: e_c
+#pragma unroll
+                        for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2 *>(ce + lane * 8 + r) = make_double2(x[r], x[r + 1]);
+                        __syncwarp();
+                        double Pr[8];                                    // lane i < 8: row i of K^L
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) Pr[j] = Mr[(lane & 7) * 8 + j];
+                        for (int cc = 0; cc + 1 < nch; ++cc) {           // E_c = e_c + K^L E_{c-1}
+                            const double *Ep = cc ? ce + (cc - 1) * 8 : start0;
+                            double v = ce[cc * 8 + (lane & 7)], w = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                v = fma(Pr[j], Ep[j], v);
+                                w = fma(Pr[j + 1], Ep[j + 1], w);
+                            }
+                            __syncwarp();
+                            if (lane < 8) ce[cc * 8 + lane] = v + w;
+                            __syncwarp();
+                        }
+                    }
+                    {   // pass 2 from the true chunk starts
+                        const double *sp = (lane == 0 || nch == 1) ? start0 : ce + (lane - 1) * 8;
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) x[r] = sp[r];
+                        chunk(x, true);
+                    }
+                    __syncwarp();
+                };
+                step(0, kc[0]);
+                sweep(true);
+                step(T - 1, kc[2]);
+                step(T - 1, kc[2]);
+                sweep(false);
+                step(0, kc[0]);
+            }
 
             // ---- sufficient statistics of the sequence; lane owns entries (gid, 2qd), (gid, 2qd + 1)
             double sxx0 = 0.0, sxx1 = 0.0, sx10 = 0.0, sx11 = 0.0, syx0 = 0.0, syx1 = 0.0, syy = 0.0;
@@ -258,7 +454,10 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
         }
 
         // ---- write back
-        for (int i = lane; i < T * q; i += 32) Xb[i] = xs[(i / q) * 8 + (i % q)];
+        for (int t0 = 0; t0 < T; t0 += 4) {
+            const int t = t0 + (lane >> 3), i = lane & 7;
+            if (t < T && i < q) Xb[t * q + i] = xs[t * 8 + i];
+        }
         for (int i = lane; i < q * q; i += 32) {
             A[(size_t)b * q * q + i] = pA[(i / q) * 8 + (i % q)];
             Avar[(size_t)b * q * q + i] = pAv[(i / q) * 8 + (i % q)];
@@ -286,25 +485,46 @@ lds_iterate_kernel(int B, int T, int q, int d, const double *__restrict__ Y, dou
 
 }  // namespace
 
-size_t lds_smem_bytes(int T, int d) { return (size_t)LW * lds_warp_doubles(T, d) * sizeof(double); }
+// PYVB_LDS = serial: the step-by-step sweep (cross-check)
+static bool lds_scan() {
+    const char *e = getenv("PYVB_LDS");
+    return !(e && e[0] == 's' && e[1] == 'e');
+}
+
+size_t lds_smem_bytes(int T, int d) {
+    const bool scan = lds_scan();
+    return (size_t)(scan ? LWC<true>::LW : LWC<false>::LW) * lds_warp_doubles(T, d, scan) * sizeof(double);
+}
+
+template <bool SCAN>
+static cudaError_t launch_lds_t(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A, double *Avar,
+                                double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb, double alpha0,
+                                double a0, double b0, int niters, double *status, cudaStream_t st, const double *Aknown) {
+    constexpr int LW = LWC<SCAN>::LW;
+    const size_t smem = (size_t)LW * lds_warp_doubles(T, d, SCAN) * sizeof(double);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(lds_iterate_kernel<SCAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = (int)((227 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    long long blocks = ((long long)B + LW - 1) / LW;
+    if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
+    lds_iterate_kernel<SCAN><<<(unsigned)blocks, 32 * LW, smem, st>>>(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra,
+                                                                     Rb, alpha0, a0, b0, niters, status, Aknown);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_lds_iterate(int B, int T, int q, int d, const double *Y, double *X, double *Xcov3, double *A,
                                double *Avar, double *C, double *Cvar, double *Qa, double *Qb, double *Ra, double *Rb,
                                double alpha0, double a0, double b0, int niters, double *status, cudaStream_t st,
                                const double *Aknown) {
     if (B <= 0 || niters <= 0) return cudaSuccess;
-    const size_t smem = lds_smem_bytes(T, d);
-    if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(lds_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = (int)((227 * 1024) / smem);
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
-    long long blocks = ((long long)B + LW - 1) / LW;
-    if (blocks > 148LL * per_sm) blocks = 148LL * per_sm;
-    lds_iterate_kernel<<<(unsigned)blocks, 32 * LW, smem, st>>>(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb,
-                                                               alpha0, a0, b0, niters, status, Aknown);
-    return cudaGetLastError();
+    if (lds_scan())
+        return launch_lds_t<true>(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb, alpha0, a0, b0, niters, status, st,
+                                  Aknown);
+    return launch_lds_t<false>(B, T, q, d, Y, X, Xcov3, A, Avar, C, Cvar, Qa, Qb, Ra, Rb, alpha0, a0, b0, niters, status, st,
+                               Aknown);
 }
 
 }  // namespace pyvb

@@ -69,6 +69,15 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 // make generic-proxy shared-memory writes visible to the async proxy (before a bulk store reads them)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, so a lane can have dozens in flight
+__device__ __forceinline__ void ldgsts8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // One lane of the (converged) warp.  The producer and MMA warps run their loops with ALL lanes (uniform control flow, so
 // that addresses and descriptors live in uniform registers) and only issue under this predicate: a loop entered by
 // `lane == 0` alone made the compiler wrap every TMA / tcgen05 instruction in an election loop with register ->
