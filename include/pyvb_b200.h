@@ -140,7 +140,8 @@ int pyvb_gw_woff(int q);                               /* first <w_d> column of 
 int pyvb_mz_pitch(int q);                              /* doubles per row of the interleaved [M2 | zbar] array */
 size_t pyvb_stats_len(int D, int q);                   /* doubles */
 size_t pyvb_stats_workspace_bytes(long long N, int D, int q, int algo);
-size_t pyvb_zsums_len(long long N, int q);             /* doubles; 0 when K2 has no fast path for q */
+size_t pyvb_zsums_len(long long N, int q);             /* doubles to allocate (the largest over the K2 kernels); 0 when K2 has no fast path for q */
+int pyvb_zsums_blocks(long long N, int q);             /* partials the K2 kernel in use writes: the first pyvb_zsums_blocks * pyvb_zsums_kw doubles */
 
 /* peer exchange buffers: cudaMalloc'd (zeroed) so that the CUDA IPC handle (64 bytes) names exactly this buffer */
 size_t pyvb_peer_bytes(size_t stats_len);

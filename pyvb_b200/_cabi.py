@@ -36,6 +36,7 @@ SIGNATURES = {
     "pyvb_pack_gw_f64": (c_int, [c_int, c_int, c_dp, c_dp, c_dp, c_dp, c_int, c_dp]),
     "pyvb_zsums_len": (c_sz, [c_ll, c_int]),
     "pyvb_zsums_kw": (c_int, [c_int]),
+    "pyvb_zsums_blocks": (c_int, [c_ll, c_int]),
     "pyvb_zstep_f64": (c_int, [c_ll, c_int, c_int, c_dp, c_ll, c_dp, c_int, c_dp, c_dp, c_dp,
                                c_dp, c_ll, c_dp, c_ll, c_dp, c_dp, c_dp, c_int, c_dp]),
     "pyvb_zsolve_f64": (c_int, [c_ll, c_int, c_dp, c_ll, c_dp, c_dp, c_dp, c_dp, c_dp]),

@@ -127,6 +127,12 @@ size_t pyvb_zsums_len(long long N, int q) {
     return len;
 }
 
+int pyvb_zsums_blocks(long long N, int q) {
+    int nblk, kw;
+    zsolve_partials(N, q, nblk, kw);
+    return nblk;
+}
+
 size_t pyvb_peer_bytes(size_t stats_len) { return peer_buffer_bytes(stats_len); }
 
 int pyvb_peer_alloc(size_t bytes, void **dptr) {

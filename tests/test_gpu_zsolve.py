@@ -43,7 +43,8 @@ def _run(impl, q, A, eta, want_sig=True):
     old = os.environ.get("PYVB_K2")
     os.environ["PYVB_K2"] = impl
     try:
-        nz = int(lib.pyvb_zsums_len(N, q))
+        nz = int(lib.pyvb_zsums_len(N, q))                 # what to allocate: the largest over the K2 kernels
+        nblk = int(lib.pyvb_zsums_blocks(N, q))            # what the kernel in use writes
         zs = torch.full((max(nz, 1),), float("nan"), dtype=torch.float64, device=dev)
         _cabi.check(lib.pyvb_zsolve_f64(N, q, mz.data_ptr(), ld, sig.data_ptr() if want_sig else 0,
                                         logdet.data_ptr(), gl.data_ptr(), zs.data_ptr() if nz else 0,
@@ -54,8 +55,9 @@ def _run(impl, q, A, eta, want_sig=True):
             os.environ.pop("PYVB_K2")
         else:
             os.environ["PYVB_K2"] = old
+    kw = int(lib.pyvb_zsums_kw(q))
     return (mz.cpu().numpy(), sig.cpu().numpy(), logdet.cpu().numpy(), gl.cpu().numpy(),
-            zs.cpu().numpy() if nz else None, zoff)
+            zs.cpu().numpy()[:nblk * kw] if nblk else None, zoff)
 
 
 @pytest.mark.parametrize("impl", ["reg", "blocked", "tpm", "lanediag", "gj"])

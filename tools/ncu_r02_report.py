@@ -13,7 +13,7 @@ def tobytes(v, u):
     return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 
 
-KEY = {"zsolve_tpm_kernel": "zsolve", "zsolve_blocked_kernel": "zsolve", "zstep_i8_kernel": "zstep_i8", "zstep_dmma_kernel": "zstep_eta",
+KEY = {"zsolve_gj_kernel": "zsolve", "zsolve_tpm_kernel": "zsolve", "zsolve_blocked_kernel": "zsolve", "zstep_i8_kernel": "zstep_i8", "zstep_dmma_kernel": "zstep_eta",
        "digitize_kernel": "digitize", "stats_i8_kernel": "stats_i8", "stats_dmma_kernel": "stats_x"}
 out, table = {}, []
 for rep, (name, rows, D, q) in zip(raw.split("== ")[1:], CFG):
