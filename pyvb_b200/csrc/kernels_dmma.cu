@@ -787,6 +787,8 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
                           cudaStream_t st, const double *cond, I8Check chk) {
     if (N <= 0) return cudaSuccess;
     const int impl = k2_impl(q);
+    // the Gauss-Jordan kernel moves the rows with bulk copies: 16-byte aligned rows (the pitch is a multiple of 32 bytes)
+    if (impl == 4 && (reinterpret_cast<uintptr_t>(MZ) & 15) != 0) return cudaErrorMisalignedAddress;
     if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 3) return launch_zsolve_lanediag(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);

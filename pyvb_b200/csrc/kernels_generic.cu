@@ -580,21 +580,45 @@ cudaError_t launch_stats_reduce(int D, int q, const double *ws_main, int nchunks
 }
 
 // =============================================================== W columns (Gauss-Seidel), thread per d
+// QT > 0: q known at compile time -- the loops unroll and w[] lives in registers (with a run-time q the array is indexed
+// dynamically, i.e. it sits in local memory, and every FMA of the q^2-long dependent chain waits for a local load: 36 us at
+// D = 256, q = 16); QT = 0: any q.
+template <int QT>
 __global__ void __launch_bounds__(128)
-wupdate_kernel(int D, int q, int col_lo, int col_hi, const double *__restrict__ stats,
+wupdate_kernel(int D, int q_rt, int col_lo, int col_hi, const double *__restrict__ stats,
                const double *__restrict__ mu, const double *__restrict__ gl, double *__restrict__ Wbar,
                double *__restrict__ Wvar) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
+    const int q = QT > 0 ? QT : q_rt;
     const StatLayout L(D, q);
     const int P = L.P;
     const double tau = gl[PYVB_GL_TAU];
     const double *T1 = stats + L.t1 + (size_t)d * P;
     const double *Bst = stats + L.bst + (size_t)d * q;
     const double *Ast = stats + L.ast + (size_t)d * q;
-    double w[PYVB_QMAX];
-    for (int i = 0; i < q; ++i) w[i] = Wbar[(size_t)d * q + i];
+    double w[QT > 0 ? QT : PYVB_QMAX];
     const double m = mu[d];
+    if (QT > 0) {
+#pragma unroll
+        for (int i = 0; i < QT; ++i) w[i] = Wbar[(size_t)d * QT + i];
+#pragma unroll
+        for (int i = 0; i < QT; ++i) {
+            if (i < col_lo || i >= col_hi) continue;                 // (kernel-uniform)
+            const double prec = gl[PYVB_GL_ALPHA + i] + tau * T1[tri(i) + i];
+            double m2 = Ast[i] - m * Bst[i];
+#pragma unroll
+            for (int j = 0; j < QT; ++j) {
+                if (j < i) m2 = fma(-T1[tri(i) + j], w[j], m2);
+                if (j > i) m2 = fma(-T1[tri(j) + i], w[j], m2);
+            }
+            w[i] = tau * m2 / prec;
+            Wvar[(size_t)d * QT + i] = 1.0 / prec;
+            Wbar[(size_t)d * QT + i] = w[i];
+        }
+        return;
+    }
+    for (int i = 0; i < q; ++i) w[i] = Wbar[(size_t)d * q + i];
     for (int i = col_lo; i < col_hi; ++i) {
         const double prec = gl[PYVB_GL_ALPHA + i] + tau * T1[tri(i) + i];
         double m2 = Ast[i] - m * Bst[i];
@@ -608,7 +632,13 @@ wupdate_kernel(int D, int q, int col_lo, int col_hi, const double *__restrict__ 
 
 cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *stats, const double *mu,
                            const double *gl, double *Wbar, double *Wvar, cudaStream_t st) {
-    wupdate_kernel<<<(D + 127) / 128, 128, 0, st>>>(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar);
+    const int blocks = (D + 63) / 64;
+    switch (q) {
+        case 16: wupdate_kernel<16><<<blocks, 64, 0, st>>>(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar); break;
+        case 32: wupdate_kernel<32><<<blocks, 64, 0, st>>>(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar); break;
+        case 64: wupdate_kernel<64><<<blocks, 64, 0, st>>>(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar); break;
+        default: wupdate_kernel<0><<<(D + 127) / 128, 128, 0, st>>>(D, q, col_lo, col_hi, stats, mu, gl, Wbar, Wvar);
+    }
     return cudaGetLastError();
 }
 
@@ -647,20 +677,25 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
         }
         __syncthreads();
     }
+    // per-column sums over d: one WARP per column (lanes stride over d, fixed order), no block-wide reduction per column
+    // (2 q block sums with three barriers each were most of this kernel's 65 us at D = 256, q = 16)
+    __shared__ double s_ww[PYVB_QMAX], s_lv[PYVB_QMAX];
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
     if ((ops & PYVB_OP_ALPHA) && c.ard) {
-        for (int i = col_lo; i < col_hi; ++i) {
+        for (int i = col_lo + warp; i < col_hi; i += nwarp) {
             double part = 0.0;
-            for (int d = tid; d < D; d += nt) {
+            for (int d = lane; d < D; d += 32) {
                 const double w = Wbar[(size_t)d * q + i];
                 part += fma(w, w, Wvar[(size_t)d * q + i]);
             }
-            const double tot = block_sum(part, sh);
-            if (tid == 0) {
+            const double tot = warp_sum(part);
+            if (lane == 0) {
                 const double b = c.ard_b0 + 0.5 * tot;
                 gl[PYVB_GL_ALQB + i] = b;
                 gl[PYVB_GL_ALPHA + i] = c.al_qa / b;
             }
         }
+        __threadfence_block();
         __syncthreads();
     }
     double resid2 = 0.0;
@@ -712,15 +747,23 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
         __syncthreads();
         // ---- W columns (gaussian.py:141-147; q_ln_det = .5/ln prod diag chol is a division)
         double eW = 0.0;
-        for (int i = 0; i < q; ++i) {
+        for (int i = warp; i < q; i += nwarp) {
             double pw = 0.0, pl = 0.0;
-            for (int d = tid; d < D; d += nt) {
+            for (int d = lane; d < D; d += 32) {
                 const double w = Wbar[(size_t)d * q + i], v = Wvar[(size_t)d * q + i];
                 pw += fma(w, w, v);
                 pl += log(v);
             }
-            const double ww = block_sum(pw, sh);
-            const double lv = block_sum(pl, sh);
+            pw = warp_sum(pw);
+            pl = warp_sum(pl);
+            if (lane == 0) {
+                s_ww[i] = pw;
+                s_lv[i] = pl;
+            }
+        }
+        __syncthreads();
+        for (int i = 0; i < q; ++i) {
+            const double ww = s_ww[i], lv = s_lv[i];
             const double qld = 0.5 / (-0.5 * lv);
             const double al = gl[PYVB_GL_ALPHA + i];
             const double lndet = c.ard ? D * (log(c.al_qa) - log(gl[PYVB_GL_ALQB + i])) : D * log(al);
