@@ -642,17 +642,45 @@ cudaError_t launch_wupdate(int D, int q, int col_lo, int col_hi, const double *s
     return cudaGetLastError();
 }
 
-// =============================================================== Mu, Gamma(s), ELBO: one CTA
+// =============================================================== Mu, Gamma(s), ELBO: one CTA (+ helpers of its cluster)
+// The kernel is launched as ONE thread-block cluster: rank 0 does everything below; the other CTAs only take their share of the
+// D x P contraction  sum_d sum_p g_dp T1[d][p]  of the residual (0.3 of the kernel's 0.35 ms at D = 1024, q = 32 on a single SM),
+// hand their partial sums to rank 0 through distributed shared memory (fixed order: deterministic, replicas stay bit-identical)
+// and leave.
+__device__ __forceinline__ uint32_t gk_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t gk_cluster_size() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void gk_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void gk_store_remote(const double *local_smem, uint32_t rank, double v) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(r), "d"(v) : "memory");
+}
+constexpr int GK_CLUSTER = 8;
+
 __global__ void __launch_bounds__(1024)
 global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__restrict__ stats, const double *__restrict__ Wbar,
               const double *__restrict__ Wvar, double *mu, double *muvar, double *gl,
               const double *__restrict__ P0, const double *__restrict__ h0, const pyvb_consts c,
               double *elbo_out) {
     __shared__ double sh[33];
+    __shared__ double cl_part[GK_CLUSTER];                              // the cluster's partial sums of the D x P contraction
     __shared__ unsigned short ijtab[PYVB_QMAX * (PYVB_QMAX + 1) / 2];   // packed index -> (i << 8) | j
     const StatLayout L(D, q);
     const int P = L.P;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int crank = (int)gk_cluster_rank(), csize = (int)gk_cluster_size();
+    if (crank != 0 && !(ops & (PYVB_OP_BETA | PYVB_OP_ELBO))) return;   // (kernel-uniform: nobody waits for the helpers)
     for (int p = tid; p < P; p += nt) {
         int i, j;
         unpack_p(p, i, j);
@@ -667,7 +695,7 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
     double tau = gl[PYVB_GL_TAU];
     __syncthreads();
 
-    if (ops & PYVB_OP_MU) {
+    if ((ops & PYVB_OP_MU) && crank == 0) {
         for (int d = tid; d < D; d += nt) {
             const double prec = c.alpha_mu + tau * cnt[d];
             double s = colx[d];
@@ -681,7 +709,7 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
     // (2 q block sums with three barriers each were most of this kernel's 65 us at D = 256, q = 16)
     __shared__ double s_ww[PYVB_QMAX], s_lv[PYVB_QMAX];
     const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
-    if ((ops & PYVB_OP_ALPHA) && c.ard) {
+    if ((ops & PYVB_OP_ALPHA) && c.ard && crank == 0) {
         for (int i = col_lo + warp; i < col_hi; i += nwarp) {
             double part = 0.0;
             for (int d = lane; d < D; d += 32) {
@@ -700,6 +728,38 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
     }
     double resid2 = 0.0;
     if (ops & (PYVB_OP_BETA | PYVB_OP_ELBO)) {
+        // (d, p) advance incrementally and (i, j) come from a table: a 64-bit division and a square root per element made
+        //  this loop 0.5 ms at D = 1024, q = 32); the cluster's CTAs take contiguous slices of the D x P index range
+        double dot = 0.0;
+        {
+            const long long tot = (long long)D * P;
+            const long long per = (tot + csize - 1) / csize;
+            const long long lo = per * crank, hi = (lo + per < tot) ? lo + per : tot;
+            const long long i0 = lo + tid;
+            int d = (int)(i0 / P), pp = (int)(i0 - (long long)d * P);
+            const int dstep = nt / P, pstep = nt - (nt / P) * P;
+            for (long long idx = i0; idx < hi; idx += nt) {
+                const int ij = ijtab[pp], i = ij >> 8, j = ij & 255;
+                double g = Wbar[(size_t)d * q + i] * Wbar[(size_t)d * q + j];
+                if (i == j) g += Wvar[(size_t)d * q + i];
+                else g *= 2.0;
+                dot = fma(g, T1[idx], dot);
+                d += dstep;
+                pp += pstep;
+                if (pp >= P) {
+                    pp -= P;
+                    ++d;
+                }
+            }
+        }
+        dot = block_sum(dot, sh);
+        if (csize > 1) {
+            if (tid == 0) gk_store_remote(cl_part + crank, 0, dot);
+            gk_cluster_sync();
+            if (crank != 0) return;
+            dot = 0.0;
+            for (int r = 0; r < csize; ++r) dot += cl_part[r];
+        }
         double part = 0.0;
         for (int d = tid; d < D; d += nt) {
             double s1 = 0.0, s2 = 0.0;
@@ -711,26 +771,8 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
             const double m = mu[d];
             part += -2.0 * (s1 + m * colx[d]) + 2.0 * m * s2 + cnt[d] * (m * m + muvar[d]);
         }
-        // (d, p) advance incrementally and (i, j) come from a table: a 64-bit division and a square root per element made
-        //  this loop 0.5 ms at D = 1024, q = 32)
-        {
-            int d = tid / P, pp = tid - (tid / P) * P;
-            const int dstep = nt / P, pstep = nt - (nt / P) * P;
-            for (long long idx = tid; idx < (long long)D * P; idx += nt) {
-                const int ij = ijtab[pp], i = ij >> 8, j = ij & 255;
-                double g = Wbar[(size_t)d * q + i] * Wbar[(size_t)d * q + j];
-                if (i == j) g += Wvar[(size_t)d * q + i];
-                else g *= 2.0;
-                part = fma(g, T1[idx], part);
-                d += dstep;
-                pp += pstep;
-                if (pp >= P) {
-                    pp -= P;
-                    ++d;
-                }
-            }
-        }
-        resid2 = block_sum(part, sh) + sc[PYVB_SC_SXX] + sc[PYVB_SC_SUMV];
+        part = block_sum(part, sh) + dot;
+        resid2 = part + sc[PYVB_SC_SXX] + sc[PYVB_SC_SUMV];
         if (ops & PYVB_OP_BETA) {
             qb = c.b0 + 0.5 * resid2;
             tau = qa / qb;
@@ -830,8 +872,22 @@ global_kernel(int D, int q, int ops, int col_lo, int col_hi, const double *__res
 cudaError_t launch_global(int D, int q, int ops, int col_lo, int col_hi, const double *stats, const double *Wbar, const double *Wvar,
                           double *mu, double *muvar, double *gl, const double *P0, const double *h0,
                           const pyvb_consts &c, double *elbo_out, cudaStream_t st) {
-    global_kernel<<<1, 1024, 0, st>>>(D, q, ops, col_lo, col_hi, stats, Wbar, Wvar, mu, muvar, gl, P0, h0, c, elbo_out);
-    return cudaGetLastError();
+    // one cluster; its size follows the work of the D x P contraction (small problems: one CTA)
+    const long long work = (long long)D * q * (q + 1) / 2;
+    const int cl = work >= (1LL << 17) ? GK_CLUSTER : work >= (1LL << 15) ? 2 : 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cl, 1, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, global_kernel, D, q, ops, col_lo, col_hi, stats, Wbar, Wvar, mu, muvar, gl, P0, h0, c, elbo_out);
 }
 
 // =============================================================== mode A imputation, warp per row
