@@ -27,7 +27,8 @@ def test_lds_matches_literal_reference(name):
     e.check()
 
 
-@pytest.mark.parametrize("shape", [(300, 40, 8, 5), (1000, 17, 3, 2), (5, 200, 8, 8), (64, 9, 1, 1)])
+@pytest.mark.parametrize("shape", [(300, 40, 8, 5), (1000, 17, 3, 2), (5, 200, 8, 8), (64, 9, 1, 1), (7, 3, 2, 2), (3, 67, 8, 5),
+                                   (2, 131, 4, 3)])
 def test_lds_batch_matches_oracle(shape):
     from pyvb_b200 import LDSEngine
     B, T, q, d = shape
@@ -53,6 +54,24 @@ def test_lds_batch_matches_oracle(shape):
     for k in KEYS:
         assert np.array_equal(st2[k], st[k]), k
     e.check()
+
+
+def test_lds_scan_and_step_by_step_sweeps_agree(monkeypatch):
+    """The chunked-scan sweeps (default) against the step-by-step Gauss-Seidel sweeps of round 1 (PYVB_LDS=serial): the same
+    arithmetic up to the rounding of the chunk starts."""
+    from pyvb_b200 import LDSEngine
+    B, T, q, d = 40, 200, 8, 5
+    Y = synth_lds(B, T, q, d, seed=11)
+    out = {}
+    for mode in ("scan", "serial"):
+        monkeypatch.setenv("PYVB_LDS", mode)
+        e = LDSEngine(Y, q, device="cuda:0")
+        e.init_random(seed=2)
+        e.iterate(3)
+        out[mode] = e.get_state()
+        e.check()
+    for k in KEYS:
+        assert tensor_rel(out["scan"][k], out["serial"][k]) < 1e-12, k
 
 
 def test_lds_empty_batch_is_a_noop():
