@@ -409,12 +409,32 @@ class PlateEngine(object):
         out["al_qb"] = gl[GL_ALQB:GL_ALQB + q].copy()
         return out
 
+    def get_row(self, i):
+        """Host copy of ONE row of the plate (O(q^2 + D), no pass over the other rows): zbar_i, Sigma_i and, in mode A,
+        <x_i> and its variances."""
+        q = self.q
+        ii, jj = tril_pack_index(q)
+        z = self.Zbar[i].contiguous().to(torch.float64).cpu().numpy()
+        if self.Sig is not None:
+            sp = self.Sig[i].cpu().numpy()
+        else:
+            sp = self.M2[i].contiguous().to(torch.float64).cpu().numpy() - z[ii] * z[jj]
+        Sig = np.zeros((q, q))
+        Sig[ii, jj] = sp
+        Sig[jj, ii] = sp
+        out = {"Zbar": z, "Sig": Sig}
+        if self.mode == "A":
+            out["Xhat"] = self.X[i].cpu().numpy()
+            out["V"] = self.V[i].cpu().numpy()
+        return out
+
     def get_state_small(self):
         """Host copy of the replicated (row-independent) state only."""
         gl = self.gl.cpu().numpy()
         return {"Wbar": self.Wbar.cpu().numpy(), "Wvar": self.Wvar.cpu().numpy(), "mu": self.mu.cpu().numpy(),
                 "muvar": self.muvar.cpu().numpy(), "qa": float(gl[GL_QA]), "qb": float(gl[GL_QB]),
-                "tau": float(gl[GL_TAU]), "alpha": gl[GL_ALPHA:GL_ALPHA + self.q].copy()}
+                "tau": float(gl[GL_TAU]), "alpha": gl[GL_ALPHA:GL_ALPHA + self.q].copy(),
+                "al_qb": gl[GL_ALQB:GL_ALQB + self.q].copy()}
 
     def check(self):
         """Raise LinAlgError if any posterior precision was not positive definite (gaussian.py:118)."""

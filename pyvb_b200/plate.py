@@ -200,6 +200,8 @@ class PCAPlate(object):
     # ------------------------------------------------------------------ updates
     def _touch(self):
         self._host = None
+        self._small = None
+        self._rows = {}
         self._elbo_terms = None
 
     def run(self, kind, lo, hi):
@@ -266,9 +268,31 @@ class PCAPlate(object):
             self._host = self.engine.get_state()
         return self._host
 
+    def _view(self, kind, i):
+        """What one node's attributes need: the replicated state (O(D q)) for W / Mu / Beta / Alpha, plus ONE row of the plate
+        for Z_i / X_i -- the manual update order of src/tests.py:312-316 reads an attribute after every single update, and a
+        copy of the whole state each time would cost O(N q^2) per read."""
+        if self._host is not None:
+            return self._host
+        if getattr(self, "_small", None) is None:
+            self.engine.check()
+            self._small = self.engine.get_state_small()
+        if kind not in "ZX":
+            return self._small
+        rows = getattr(self, "_rows", None)
+        if rows is None:
+            rows = self._rows = {}
+        if i not in rows:
+            rows[i] = self.engine.get_row(i)
+        r = rows[i]
+        st = dict(self._small)
+        for k, v in r.items():                                 # (indexable by i like the full state)
+            st[k] = {i: v}
+        return st
+
     def get(self, node, attr):
         kind, i = self.index[id(node)]
-        st = self._state()
+        st = self._view(kind, i)
         if attr == "qb":
             return st["qb"] if kind == "B" else float(st["al_qb"][i])
         if kind == "W":
