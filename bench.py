@@ -291,7 +291,7 @@ def kernel_breakdown(torch, dev, eng, lib, _cabi, rows):
         out["zstep_k1_eta_ms"] = tc(lambda: k1_phase(3), 5)
         out["zstep_k1_ms"] = tc(lambda: k1_phase(1), 5)
         k1_phase(1)
-        out["zsolve_k2_ms"] = tc(k2_only, 1)
+        out["zsolve_k2_ms"] = tc(k2_only, 3)
         eng.update_Z()
     elif lib.pyvb_algo_supported(2, D, q):
         def k1_only():
@@ -300,7 +300,7 @@ def kernel_breakdown(torch, dev, eng, lib, _cabi, rows):
             eng.algo = alg
         out["zstep_k1_ms"] = tc(k1_only, 5)
         k1_only()
-        out["zsolve_k2_ms"] = tc(k2_only, 1)
+        out["zsolve_k2_ms"] = tc(k2_only, 3)
         eng.update_Z()
 
     def stats_call():
