@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(NTHR, 1)
 zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO8, long long N, int D, int q,
                 const double *__restrict__ P0, const double *__restrict__ gscale, const double *__restrict__ gl, int nrb,
-                int nst, int hstage, int adbl, long long *prof) {
+                int nst, int hstage, int adbl, long long *prof, int ks) {
     const I8Geom G(q);
     long long w0 = 0, w1 = 0, w2 = 0;                          // PYVB_I8_PROF: clocks spent waiting, per role
     const long long tstart = clock64();
@@ -300,8 +300,11 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // row block starts with the latency of its 128 x D mask load: a quarter of the kernel at D = 256)
     const int nab = adbl ? 2 : 1;
     unsigned char *a_base = smem;                                              // [nab][nk][128 x 64 B] resident mask block(s)
-    unsigned char *b_base = smem + (size_t)nab * nk * A_B;                     // [nst][224 (PAIR: 112) x 64 B] digit tiles
-    unsigned char *o_base = b_base + (size_t)nst * BSZ;                        // [8 warps][32 rows x 128 B] output staging (swizzled)
+    // ks: K chunks (digit tiles) per ring stage.  One tile per stage makes the producer's and the issuer's per-stage latency
+    // (barrier round trip, TMA / MMA issue, commit: ~300 clocks each) as long as the two MMAs of a tile (257 clocks)
+    const int SB = ks * BSZ;                                                   // bytes of a ring stage in THIS CTA
+    unsigned char *b_base = smem + (size_t)nab * nk * A_B;                     // [nst][ks][224 (PAIR: 112) x 64 B] digit tiles
+    unsigned char *o_base = b_base + (size_t)nst * SB;                         // [8 warps][32 rows x 128 B] output staging (swizzled)
     double *p0v = reinterpret_cast<double *>(o_base + (hstage ? OUT_B / 2 : OUT_B));   // [NC8]: packed P0, zero pad
     double *fcol = p0v + G.NC8;                                                // [NC8]: tau * scale_c * 2^-54
     uint64_t *afull = reinterpret_cast<uint64_t *>(fcol + G.NC8);              // [nab][nk]
@@ -373,40 +376,48 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int rl = 0; rl < niter; ++rl) {
             for (int ci = 0; ci < G.NCT; ++ci) {
                 const int ct = (ci + ct0 < G.NCT) ? ci + ct0 : ci + ct0 - G.NCT;
-                for (int ki = 0; ki < nk; ++ki) {
-                    const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
+                for (int ki = 0; ki < nk; ki += ks) {
                     if (ci == 0) {
-                        // mask chunk kb of row block r into buffer r % nab, once that buffer's previous user (row block r - nab)
-                        // has been consumed by its last column tile.  Two buffers: row block rl + 1 is fetched NOW, a whole
-                        // row block ahead of its use (and row block 0 with it).
-                        for (int r = (nab == 2 && rl > 0) ? rl + 1 : rl; r <= rl + nab - 1 && r < niter; ++r) {
-                            const int ab = (r & (nab - 1)) * nk + kb;
-                            const int rbr = (int)blockIdx.x + r * (int)gridDim.x;
-                            PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[ab], (uint32_t)(((r / nab) & 1) ^ 1)));
-                            if (leader) {
-                                if (PAIR) {    // both CTAs' chunks complete on the LEADER's barrier (armed by the leader for both)
-                                    if (crank == 0) mbar_arrive_expect_tx(&afull[ab], (uint32_t)(2 * A_B));
-                                    tma_load_3d_i8_pair(a_base + (size_t)ab * A_B, &tmA, 0, (rbr * nk + kb) * BM, 0, afull_l + (uint32_t)ab * 8u);
-                                } else {
-                                    mbar_arrive_expect_tx(&afull[ab], (uint32_t)A_B);
-                                    tma_load_3d_i8(a_base + (size_t)ab * A_B, &tmA, 0, (rbr * nk + kb) * BM, 0, &afull[ab]);   // past the end: zero fill
+                        for (int h = 0; h < ks; ++h) {
+                            const int kb = (ki + h + kb0 < nk) ? ki + h + kb0 : ki + h + kb0 - nk;
+                            // mask chunk kb of row block r into buffer r % nab, once that buffer's previous user (row block r - nab)
+                            // has been consumed by its last column tile.  Two buffers: row block rl + 1 is fetched NOW, a whole
+                            // row block ahead of its use (and row block 0 with it).
+                            for (int r = (nab == 2 && rl > 0) ? rl + 1 : rl; r <= rl + nab - 1 && r < niter; ++r) {
+                                const int ab = (r & (nab - 1)) * nk + kb;
+                                const int rbr = (int)blockIdx.x + r * (int)gridDim.x;
+                                PROF_WAIT(w1, umma::mbar_wait_bounded(&aempty[ab], (uint32_t)(((r / nab) & 1) ^ 1)));
+                                if (leader) {
+                                    if (PAIR) {    // both CTAs' chunks complete on the LEADER's barrier (armed by the leader for both)
+                                        if (crank == 0) mbar_arrive_expect_tx(&afull[ab], (uint32_t)(2 * A_B));
+                                        tma_load_3d_i8_pair(a_base + (size_t)ab * A_B, &tmA, 0, (rbr * nk + kb) * BM, 0, afull_l + (uint32_t)ab * 8u);
+                                    } else {
+                                        mbar_arrive_expect_tx(&afull[ab], (uint32_t)A_B);
+                                        tma_load_3d_i8(a_base + (size_t)ab * A_B, &tmA, 0, (rbr * nk + kb) * BM, 0, &afull[ab]);   // past the end: zero fill
+                                    }
                                 }
                             }
                         }
                     }
                     PROF_WAIT(w0, umma::mbar_wait_bounded(&empty[s], ph ^ 1));
                     if (leader) {
-                        if (PAIR) {            // this CTA's half of the tile (rows crank * 112 ...) into its own stage
-                            if (crank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
-                            tma_load_3d_i8_pair(b_base + s * BSZ, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / 2), 0,
-                                                full_l + (uint32_t)s * 8u);
+                        if (PAIR) {
+                            if (crank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(ks * B_B));
                         } else {
-                            mbar_arrive_expect_tx(&full[s], (uint32_t)B_B);
-                            if (CL == 1)
-                                tma_load_3d_i8(b_base + s * B_B, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT), 0, &full[s]);   // 7 planes x 32 columns
-                            else                                                                               // this CTA's slice, to everybody
-                                tma_load_3d_i8_mc(b_base + s * B_B + crank * (B_B / CL), &tmB, 0,
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)(ks * B_B));
+                        }
+                        for (int h = 0; h < ks; ++h) {
+                            const int kb = (ki + h + kb0 < nk) ? ki + h + kb0 : ki + h + kb0 - nk;
+                            unsigned char *dst = b_base + s * SB + h * BSZ;
+                            if (PAIR) {            // this CTA's half of the tile (rows crank * 112 ...) into its own stage
+                                tma_load_3d_i8_pair(dst, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / 2), 0,
+                                                    full_l + (uint32_t)s * 8u);
+                            } else if (CL == 1) {
+                                tma_load_3d_i8(dst, &tmB, 0, (kb * G.NCT + ct) * (NPL * CT), 0, &full[s]);   // 7 planes x 32 columns
+                            } else {                                                                           // this CTA's slice, to everybody
+                                tma_load_3d_i8_mc(dst + crank * (B_B / CL), &tmB, 0,
                                                   (kb * G.NCT + ct) * (NPL * CT) + crank * (NPL * CT / CL), 0, &full[s], CMASK);
+                            }
                         }
                     }
                     __syncwarp();
@@ -432,26 +443,33 @@ zstep_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 PROF_WAIT(w1, umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1)));
                 umma::fence_after_sync();
                 const uint32_t dacc = tmem + (uint32_t)(buf * 256);
-                for (int ki = 0; ki < nk; ++ki) {
-                    const int kb = (ki + kb0 < nk) ? ki + kb0 : ki + kb0 - nk;
-                    const int ab = (rl & (nab - 1)) * nk + kb;               // mask chunk kb of this row block's buffer
-                    if (ci == 0) PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[ab], (uint32_t)((rl / nab) & 1)));
+                for (int ki = 0; ki < nk; ki += ks) {
+                    if (ci == 0)
+                        for (int h = 0; h < ks; ++h) {
+                            const int kb = (ki + h + kb0 < nk) ? ki + h + kb0 : ki + h + kb0 - nk;
+                            const int ab = (rl & (nab - 1)) * nk + kb;       // mask chunk kb of this row block's buffer
+                            PROF_WAIT(w2, umma::mbar_wait_bounded(&afull[ab], (uint32_t)((rl / nab) & 1)));
+                        }
                     PROF_WAIT(w0, umma::mbar_wait_bounded(&full[s], ph));
                     umma::fence_after_sync();
                     if (leader) {
-                        const uint64_t ad = adesc0 + (uint64_t)(ab * (A_B >> 4)), bd = bdesc0 + (uint64_t)(s * (BSZ >> 4));
-                        if (PAIR) {
-                            umma::mma_i8_pair(dacc, ad, bd, idesc, ki ? 1u : 0u);
-                            umma::mma_i8_pair(dacc, ad + 2, bd + 2, idesc, 1u);
-                            umma::mma_commit_pair(&empty[s]);                            // frees the stage in both CTAs
-                            if (ci == G.NCT - 1) umma::mma_commit_pair(&aempty[ab]);
-                        } else {
-                            umma::mma_i8(dacc, ad, bd, idesc, ki ? 1u : 0u);
-                            umma::mma_i8(dacc, ad + 2, bd + 2, idesc, 1u);
-                            if (CL == 1) umma::mma_commit(&empty[s]);
-                            else mma_commit_mc(&empty[s], CMASK);
-                            if (ci == G.NCT - 1) umma::mma_commit(&aempty[ab]);
+                        for (int h = 0; h < ks; ++h) {
+                            const int kb = (ki + h + kb0 < nk) ? ki + h + kb0 : ki + h + kb0 - nk;
+                            const int ab = (rl & (nab - 1)) * nk + kb;
+                            const uint64_t ad = adesc0 + (uint64_t)(ab * (A_B >> 4)), bd = bdesc0 + (uint64_t)((s * SB + h * BSZ) >> 4);
+                            if (PAIR) {
+                                umma::mma_i8_pair(dacc, ad, bd, idesc, (ki + h) ? 1u : 0u);
+                                umma::mma_i8_pair(dacc, ad + 2, bd + 2, idesc, 1u);
+                                if (ci == G.NCT - 1) umma::mma_commit_pair(&aempty[ab]);
+                            } else {
+                                umma::mma_i8(dacc, ad, bd, idesc, (ki + h) ? 1u : 0u);
+                                umma::mma_i8(dacc, ad + 2, bd + 2, idesc, 1u);
+                                if (ci == G.NCT - 1) umma::mma_commit(&aempty[ab]);
+                            }
                         }
+                        if (PAIR) umma::mma_commit_pair(&empty[s]);                      // frees the stage in both CTAs
+                        else if (CL == 1) umma::mma_commit(&empty[s]);
+                        else mma_commit_mc(&empty[s], CMASK);
                     }
                     __syncwarp();
                     if (++s == nst) {
@@ -878,17 +896,19 @@ template <int CL, bool PAIR = false>
 __global__ void __launch_bounds__(NTHR, 1)
 stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, long long N, int D, int q,
                 const double *__restrict__ zscale, double *__restrict__ ws, long long rows_per_chunk, int nchunks, int ndb,
-                int nct) {
+                int nct, int ks) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
-    constexpr int BSZ = PAIR ? B_B / 2 : B_B, STG = A_B + BSZ, NS = PAIR ? SST_PAIR : SST;
+    constexpr int BSZ = PAIR ? B_B / 2 : B_B, STG = A_B + BSZ, NSMAX = PAIR ? SST_PAIR : SST;
+    // ks K steps (64 rows each) per ring stage: half the barrier round trips, TMA arms and commits per MMA (see K1-i8)
+    const int NS = NSMAX / ks, SB = ks * STG;
     const int P = i_tri(q), NCZ = (P + q + 31) & ~31;
     unsigned char *st_base = smem;                                             // [NS][A 8 KB | B 14 KB (PAIR: 7 KB)]
-    double *fcol = reinterpret_cast<double *>(smem + (size_t)NS * STG);         // [NCZ]: zscale_c * 2^-54
+    double *fcol = reinterpret_cast<double *>(smem + (size_t)NSMAX * STG);      // [NCZ]: zscale_c * 2^-54
     uint64_t *full = reinterpret_cast<uint64_t *>(fcol + NCZ);
-    uint64_t *empty = full + NS;
-    uint64_t *tfull = empty + NS;
+    uint64_t *empty = full + NSMAX;
+    uint64_t *tfull = empty + NSMAX;
     uint64_t *tempty = tfull + 2;
     uint32_t *tbase = reinterpret_cast<uint32_t *>(tempty + 2);
 
@@ -902,7 +922,7 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (tid == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < NS; ++s) {
+        for (int s = 0; s < NSMAX; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], PAIR ? 1 : CL);
         }
@@ -945,24 +965,30 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int chunk, db, ct, nsteps;
             long long r0;
             item_geom(item, chunk, db, ct, r0, nsteps);
-            for (int k = 0; k < nsteps; ++k) {
+            for (int k = 0; k < nsteps; k += ks) {
+                const int kc = (nsteps - k < ks) ? nsteps - k : ks;          // K steps in this stage (the chunk's tail: fewer)
                 umma::mbar_wait_bounded(&empty[s], ph ^ 1);
                 if (leader) {
-                    unsigned char *st = st_base + (size_t)s * STG;
-                    const long long kb = r0 / BKB + k;
                     if (PAIR) {                // both CTAs' tiles complete on the LEADER's barrier (armed by the leader for both)
-                        if (crank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * STG));
-                        tma_load_3d_i8_pair(st, &tmA, 0, (int)(kb * D + db * BM), 0, full_l + (uint32_t)s * 8u);
-                        tma_load_3d_i8_pair(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / 2)), 0,
-                                            full_l + (uint32_t)s * 8u);
+                        if (crank == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(2 * kc * STG));
                     } else {
-                        mbar_arrive_expect_tx(&full[s], (uint32_t)(A_B + B_B));
-                        tma_load_3d_i8(st, &tmA, 0, (int)(kb * D + db * BM), 0, &full[s]);               // 128 data dimensions x 64 rows
-                        if (CL == 1)
-                            tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
-                        else
-                            tma_load_3d_i8_mc(st + A_B + crank * (B_B / CL), &tmB, 0,
-                                              (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / CL)), 0, &full[s], CMASK);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(kc * (A_B + B_B)));
+                    }
+                    for (int h = 0; h < kc; ++h) {
+                        unsigned char *st = st_base + (size_t)s * SB + (size_t)h * STG;
+                        const long long kb = r0 / BKB + k + h;
+                        if (PAIR) {
+                            tma_load_3d_i8_pair(st, &tmA, 0, (int)(kb * D + db * BM), 0, full_l + (uint32_t)s * 8u);
+                            tma_load_3d_i8_pair(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / 2)), 0,
+                                                full_l + (uint32_t)s * 8u);
+                        } else {
+                            tma_load_3d_i8(st, &tmA, 0, (int)(kb * D + db * BM), 0, &full[s]);               // 128 data dimensions x 64 rows
+                            if (CL == 1)
+                                tma_load_3d_i8(st + A_B, &tmB, 0, (int)((kb * nct + ct) * (NPL * CT)), 0, &full[s]);   // 7 planes x 32 columns x 64 rows
+                            else
+                                tma_load_3d_i8_mc(st + A_B + crank * (B_B / CL), &tmB, 0,
+                                                  (int)((kb * nct + ct) * (NPL * CT) + crank * (NPL * CT / CL)), 0, &full[s], CMASK);
+                        }
                     }
                 }
                 __syncwarp();
@@ -987,21 +1013,24 @@ stats_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma::mbar_wait_bounded(&tempty[buf], (uint32_t)(((tl >> 1) & 1) ^ 1));
             umma::fence_after_sync();
             const uint32_t dacc = tmem + (uint32_t)(buf * 256);
-            for (int k = 0; k < nsteps; ++k) {
+            for (int k = 0; k < nsteps; k += ks) {
+                const int kc = (nsteps - k < ks) ? nsteps - k : ks;
                 umma::mbar_wait_bounded(&full[s], ph);
                 umma::fence_after_sync();
                 if (leader) {
-                    const uint64_t off = (uint64_t)(s * (STG >> 4));
-                    if (PAIR) {
-                        umma::mma_i8_pair(dacc, adesc0 + off, bdesc0 + off, idesc, k ? 1u : 0u);
-                        umma::mma_i8_pair(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
-                        umma::mma_commit_pair(&empty[s]);
-                    } else {
-                        umma::mma_i8(dacc, adesc0 + off, bdesc0 + off, idesc, k ? 1u : 0u);
-                        umma::mma_i8(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
-                        if (CL == 1) umma::mma_commit(&empty[s]);
-                        else mma_commit_mc(&empty[s], CMASK);
+                    for (int h = 0; h < kc; ++h) {
+                        const uint64_t off = (uint64_t)((s * SB + h * STG) >> 4);
+                        if (PAIR) {
+                            umma::mma_i8_pair(dacc, adesc0 + off, bdesc0 + off, idesc, (k + h) ? 1u : 0u);
+                            umma::mma_i8_pair(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
+                        } else {
+                            umma::mma_i8(dacc, adesc0 + off, bdesc0 + off, idesc, (k + h) ? 1u : 0u);
+                            umma::mma_i8(dacc, adesc0 + off + 2, bdesc0 + off + 2, idesc, 1u);
+                        }
                     }
+                    if (PAIR) umma::mma_commit_pair(&empty[s]);
+                    else if (CL == 1) umma::mma_commit(&empty[s]);
+                    else mma_commit_mc(&empty[s], CMASK);
                 }
                 __syncwarp();
                 if (++s == NS) {
@@ -1214,9 +1243,21 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
         adbl_on = (ev && ev[0] == '0') ? 0 : 1;
     }
     const int adbl = (adbl_on && !pair && i8_stages(D, q, hstage, 0, 1) >= ST / 2) ? 1 : 0;
-    const int nst = i8_stages(D, q, hstage, pair, adbl);
+    int nst = i8_stages(D, q, hstage, pair, adbl);
     if (nst < 2) return cudaErrorNotSupported;
     const size_t smem = i8_smem_bytes(D, q, nst, hstage, pair, adbl);
+    // two K chunks per ring stage: half as many barrier round trips, TMA arms and commits per MMA -- with one tile per stage the
+    // producer's and the issuer's per-stage latency (~300 clocks each) was as long as the tile's two MMAs (257 clocks).  Measured
+    // under ncu on one box: config-3 shard 5.07 -> 4.02 ms, config 2 0.450 -> 0.388 ms, D = 512 / q = 64 unchanged.
+    // PYVB_I8_KS = 1 | 2 overrides.
+    static int ks_env = -1;
+    if (ks_env < 0) {
+        const char *ev = getenv("PYVB_I8_KS");
+        ks_env = ev ? atoi(ev) : 0;
+    }
+    int ks = (ks_env == 1 || ks_env == 2) ? ks_env : 2;
+    if ((nk % 2) != 0 || nst < 4) ks = 1;
+    if (ks == 2) nst /= 2;                                   // same bytes: the ring keeps its depth in K chunks
     CUtensorMap tmO8;
     {   // the same rows as 8-column x 32-row boxes (64-byte rows, SWIZZLE_64B) for the half-staging epilogue
         EncodeTiledFn enc = get_encode_i8();
@@ -1239,7 +1280,7 @@ cudaError_t launch_zstep_i8(long long N, int D, int q, const void *mask, const v
         if (prof_on && cudaMalloc(&prof, 148 * 10 * sizeof(long long)) != cudaSuccess) prof_on = 0;
     }
     e = launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, tmO, tmO8, N, D, q, P0, gscale, gl, (int)nrb, nst, hstage, adbl,
-                       prof_on ? prof : (long long *)nullptr);
+                       prof_on ? prof : (long long *)nullptr, ks);
     if (prof_on && e == cudaSuccess) {      // diagnosis only: synchronises
         long long h[148 * 10];
         cudaStreamSynchronize(st);
@@ -1370,8 +1411,15 @@ cudaError_t launch_stats_i8(long long N, int D, int q, const void *maskT, const 
     if (e != cudaSuccess) return e;
     const long long nitems = (long long)((ndb + cl - 1) / cl) * nct * nchunks;
     const int grid = (int)(nitems < 148 / cl ? nitems : 148 / cl) * cl;
+    // K steps per ring stage (as in K1-i8; ncu on one box: config-3 shard 4.17 -> 3.34 ms, config 2 284 -> 265 us; 3 and 4 are slower)
+    static int ks_env = -1;                                    // PYVB_I8_STATS_KS = 1 .. 4 (default 2)
+    if (ks_env < 0) {
+        const char *ev = getenv("PYVB_I8_STATS_KS");
+        ks_env = ev ? atoi(ev) : 0;
+    }
+    const int ks = (ks_env >= 1 && ks_env <= 4) ? ks_env : 2;
     return launch_cluster(kern, grid, NTHR, smem, cl, st, tmA, tmB, N, D, q, (const double *)zscale, ws,
-                          stats_i8_rows_per_chunk(N, nchunks), nchunks, ndb, nct);
+                          stats_i8_rows_per_chunk(N, nchunks), nchunks, ndb, nct, ks);
 }
 
 }  // namespace pyvb
