@@ -50,7 +50,7 @@ template <int Q, int RPL_, int WARPS_> struct GJ {
     static constexpr int STAGE_D = MPW * PITCH;               // the rows of a group as they lie in HBM
     static constexpr int BC_P = MPW * (Q + 2);                // published columns of the warp's matrices + the next pivot row's diagonal
     static constexpr int BC_D = 2 * BC_P;                     // two parities
-    static constexpr int WARP_D = STAGE_D + BC_D + OROW + 4 + 2 * Q + 2;   // .. | csum | scalars | maxima | mbarrier (+ pad)
+    static constexpr int WARP_D = 2 * STAGE_D + BC_D + OROW + 4 + 2 * Q + 2;   // two stages | .. | csum | scalars | maxima | 2 mbarriers
     static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8;
     static_assert(LPM <= 32 && (32 % LPM) == 0, "a matrix lives in one warp");
     static_assert((STAGE_D % 2) == 0 && (BC_D % 2) == 0 && (OROW % 2) == 0, "16-byte alignment of the per-warp arrays");
@@ -82,14 +82,17 @@ zsolve_gj_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = lane / LPM, l = lane % LPM;
     double *stage = smem_gj + (size_t)warp * T::WARP_D;
-    double *bc = stage + T::STAGE_D;
+    double *bc = stage + 2 * T::STAGE_D;
     double *csum = bc + T::BC_D;                                  // [OROW]
     double *wsc = csum + T::OROW;                                 // [4]
     double *wmx = wsc + 4;                                        // [2 Q]: max_n <z_i z_i>, max_n |<z_i>| of this warp's rows
     uint64_t *bar = reinterpret_cast<uint64_t *>(wmx + 2 * Q);
 
     for (int c = lane; c < T::OROW; c += 32) csum[c] = 0.0;
-    if (lane == 0) mbar_init(bar, 1);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+    }
     // INT8 guard (kernels.h: I8Check): a row whose largest diagonal entry is below `thr` carries too much fixed-point rounding
     if (chk.gscale != nullptr) {                                 // kernel-uniform
         double mx = 0.0;
@@ -120,22 +123,31 @@ zsolve_gj_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig,
     const long long nwarps = (long long)gridDim.x * T::WARPS;
     const long long ngroups = (N + MPW - 1) / MPW;
     long long g = (long long)blockIdx.x * T::WARPS + warp;
-    uint32_t parity = 0;
+    // Two stages: while group g is inverted in stage s, the bulk copy of the warp's next group lands in stage s ^ 1 (whose
+    // store -- the group before g -- has been read by then).  With one stage every group paid the store's read + the next
+    // load's latency with the warp idle, and an issue-bound kernel at two warps per scheduler cannot hide an idle warp.
     if (g < ngroups && lane == 0) {                               // the first group of this warp
         const long long left = N - g * MPW;
         const uint32_t bytes = (uint32_t)((left < MPW ? left : MPW) * PITCH * 8);
         mbar_arrive_expect_tx(bar, bytes);
         bulk_g2s(stage, MZ + g * MPW * PITCH, bytes, bar);
     }
-    double *st = stage + m * PITCH;                               // this lane's matrix
-    for (; g < ngroups; g += nwarps) {
+    for (int it = 0; g < ngroups; g += nwarps, ++it) {
+        const int sidx = it & 1;
+        double *stg = stage + sidx * T::STAGE_D;                  // this group's rows
+        double *st = stg + m * PITCH;                             // this lane's matrix
         const long long n0 = g * MPW;
         const int nval = (N - n0 < MPW) ? (int)(N - n0) : MPW;
         const bool valid = m < nval;
-        const long long gn = g + nwarps;                         // the group after this one: pull it into L2 now
-        if (lane == 0 && gn * MPW + MPW <= N) prefetch_l2(MZ + gn * MPW * PITCH, (uint32_t)(MPW * PITCH * 8));
-        mbar_wait(bar, parity);
-        parity ^= 1u;
+        const long long gn = g + nwarps;                         // the warp's next group: into the other stage now
+        if (lane == 0 && gn < ngroups) {
+            bulk_wait_read_all();                                // (the store of the group before this one has read that stage)
+            const long long left = N - gn * MPW;
+            const uint32_t bytes = (uint32_t)((left < MPW ? left : MPW) * PITCH * 8);
+            mbar_arrive_expect_tx(bar + (sidx ^ 1), bytes);
+            bulk_g2s(stage + (sidx ^ 1) * T::STAGE_D, MZ + gn * MPW * PITCH, bytes, bar + (sidx ^ 1));
+        }
+        mbar_wait(bar + sidx, (uint32_t)((it >> 1) & 1));
 
         // ---- rows of the packed lower triangle -> full rows in registers
         double a[RPL][Q];
@@ -307,7 +319,7 @@ zsolve_gj_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig,
         __syncwarp();
         // ---- rows back to HBM (one bulk store), column sums of the finished rows, next group in
         if (lane == 0) {
-            bulk_s2g(MZ + n0 * PITCH, stage, (uint32_t)(nval * PITCH * 8));
+            bulk_s2g(MZ + n0 * PITCH, stg, (uint32_t)(nval * PITCH * 8));
             bulk_commit();
         }
         if (zsums != nullptr) {                                  // kernel-uniform
@@ -315,20 +327,11 @@ zsolve_gj_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig,
                 double v = 0.0;
 #pragma unroll
                 for (int mm = 0; mm < MPW; ++mm)
-                    if (mm < nval) v += stage[mm * PITCH + c];
+                    if (mm < nval) v += stg[mm * PITCH + c];
                 csum[c] += v;
             }
         }
         __syncwarp();
-        if (lane == 0) {
-            bulk_wait_read_all();                                // the store has read the stage
-            if (gn < ngroups) {
-                const long long left = N - gn * MPW;
-                const uint32_t bytes = (uint32_t)((left < MPW ? left : MPW) * PITCH * 8);
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s(stage, MZ + gn * MPW * PITCH, bytes, bar);
-            }
-        }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
@@ -357,7 +360,7 @@ zsolve_gj_kernel(long long N, double *__restrict__ MZ, double *__restrict__ Sig,
     }
     __syncthreads();
     double *out = zsums + (size_t)blockIdx.x * T::KW;
-    const double *w0 = smem_gj + T::STAGE_D + T::BC_D;            // csum of warp 0
+    const double *w0 = smem_gj + 2 * T::STAGE_D + T::BC_D;            // csum of warp 0
     for (int c = tid; c < T::OROW + 4; c += 32 * T::WARPS) {
         double v = 0.0;
         for (int w = 0; w < T::WARPS; ++w) v += w0[(size_t)w * T::WARP_D + c];   // [csum OROW | scalars 4] is contiguous
