@@ -119,7 +119,7 @@ int pyvb_zsums_kw(int q) { return 2 * (gw_woff(q) + q) + PYVB_ZS_EXTRA; }
 
 size_t pyvb_zsums_len(long long N, int q) {
     size_t len = 0;                                     // the largest over the K2 implementations (PYVB_K2 is read per call)
-    for (int impl = 0; impl <= 4; ++impl) {
+    for (int impl = 0; impl <= 5; ++impl) {
         int nblk, kw;
         zsolve_partials_of(impl, N, q, nblk, kw);
         if ((size_t)nblk * kw > len) len = (size_t)nblk * kw;

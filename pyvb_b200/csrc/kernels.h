@@ -74,7 +74,7 @@ int zsolve_blocked_kw(int q);
 cudaError_t launch_zsolve_blocked(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl,
                                   double *zsums, cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
 // 0 register-resident, 1 blocked tensor-core, 2 thread per matrix, 3 blocked with lane-parallel diagonal blocks,
-// 4 Gauss-Jordan in registers (PYVB_K2 overrides)
+// 4 Gauss-Jordan in registers, 5 blocked symmetric sweep (scalar panel + DMMA update) (PYVB_K2 overrides)
 int k2_impl(int q);
 int k2_impl_f32(int q);   // the FP32-row variant only exists for the blocked / thread-per-matrix kernels
 // blocked tensor-core K2 with lane-parallel 8 x 8 diagonal blocks, several matrices per warp (kernels_k2m.cu): q in {16, 32, 64}
@@ -87,6 +87,12 @@ int zsolve_gj_blocks(long long N, int q);
 int zsolve_gj_kw(int q);
 cudaError_t launch_zsolve_gj(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
                              cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
+// blocked symmetric sweep, scalar panel + DMMA trailing update, in place in the packed rows (kernels_k2s.cu): q in {16, 32, 64};
+// same partial layout as the blocked kernel
+int zsolve_sweep_blocks(long long N, int q);
+int zsolve_sweep_kw(int q);
+cudaError_t launch_zsolve_sweep(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
+                                cudaStream_t st, const double *cond = nullptr, I8Check chk = I8Check());
 // thread-per-matrix K2 (kernels_k2t.cu): q in {8, 16}
 int zsolve_tpm_blocks(long long N, int q);
 int zsolve_tpm_kw(int q);

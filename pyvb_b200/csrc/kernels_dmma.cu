@@ -652,23 +652,28 @@ static cudaError_t launch_zsolve_q(long long N, double *MZ, double *Sig, double 
 }
 
 // Which batched solve runs for this q: 0 = register-resident (lane per matrix row, above), 1 = blocked tensor-core
-// kernel (kernels_k2.cu), 2 = thread per matrix (kernels_k2t.cu).  q = 64 only exists blocked.  PYVB_K2 = reg /
-// blocked / tpm overrides the default (measured per 1M rows, FP64: q = 16: 1.62 / 2.0 / see DESIGN ms; q = 32: 9.0 / 5.8).
+// kernel (kernels_k2.cu), 2 = thread per matrix (kernels_k2t.cu), 3 = lane-parallel diagonal blocks (kernels_k2m.cu), 4 = Gauss-Jordan
+// (kernels_k2g.cu), 5 = blocked symmetric sweep (kernels_k2s.cu).  q = 64 exists blocked / lanediag / sweep.  PYVB_K2 = reg /
+// blocked / tpm / lanediag / gj / sweep overrides the default (measured per 1M rows, FP64: q = 16: 1.62 / 2.0 / see DESIGN ms; q = 32: 9.0 / 5.8).
 int k2_impl(int q) {
     const char *e = getenv("PYVB_K2");               // read per call (tests flip it); callers size zsums with pyvb_zsums_len
     int mode = (e && e[0] == 'b') ? 1 : (e && e[0] == 'r') ? 0 : (e && e[0] == 't') ? 2 : (e && e[0] == 'l') ? 3
-               : (e && e[0] == 'g') ? 4 : -1;
+               : (e && e[0] == 'g') ? 4 : (e && e[0] == 's') ? 5 : -1;
     if (q == 64 && (mode == 0 || mode == 2)) mode = -1;  // q = 64 only exists blocked
     if (mode == 2 && q > 16) mode = -1;
     if (mode == 3 && q < 16) mode = -1;
     if (mode == 4 && q != 16 && q != 32) mode = -1;
+    if (mode == 5 && q != 16 && q != 32 && q != 64) mode = -1;
     if (mode >= 0) return mode;
     if (q == 16 || q == 32) return 4;
+    // (5, the blocked sweep of kernels_k2s.cu, is as fast as the blocked Cholesky kernel at q = 64 and leaves the column sums, which
+    //  saves the mzpart pass: 24.1 -> 22.1 ms per sweep at the config-4 shape -- but its explicit 8 x 8 pivot-tile inverses cost accuracy
+    //  on ill-conditioned rows: 1.0e-8 on Zbar in test_ard_modeB_vs_oracle[(600, 64, 64)], where D < q.  Opt-in only: PYVB_K2=sweep.)
     return q >= 32 ? 1 : 2;      // (the lane-parallel-diagonal kernel, 3, is not faster: 7.7 vs 7.4 ms at q = 32)
 }
 int k2_impl_f32(int q) {
     const int impl = k2_impl(q);
-    return impl == 4 ? (q >= 32 ? 1 : 2) : impl;
+    return (impl == 4 || impl == 5) ? (q >= 32 ? 1 : 2) : impl;
 }
 
 void zsolve_partials(long long N, int q, int &nblk, int &kw) { zsolve_partials_of(k2_impl(q), N, q, nblk, kw); }
@@ -697,6 +702,11 @@ void zsolve_partials_of(int impl, long long N, int q, int &nblk, int &kw) {
     if (impl == 4) {
         kw = zsolve_gj_kw(q);
         nblk = kw > 0 ? zsolve_gj_blocks(N, q) : 0;
+        return;
+    }
+    if (impl == 5) {
+        kw = zsolve_sweep_kw(q);
+        nblk = kw > 0 ? zsolve_sweep_blocks(N, q) : 0;
         return;
     }
     switch (q) {
@@ -788,11 +798,12 @@ cudaError_t launch_zsolve(long long N, int q, double *MZ, double *Sig, double *l
     if (N <= 0) return cudaSuccess;
     const int impl = k2_impl(q);
     // the Gauss-Jordan kernel moves the rows with bulk copies: 16-byte aligned rows (the pitch is a multiple of 32 bytes)
-    if (impl == 4 && (reinterpret_cast<uintptr_t>(MZ) & 15) != 0) return cudaErrorMisalignedAddress;
+    if ((impl == 4 || impl == 5) && (reinterpret_cast<uintptr_t>(MZ) & 15) != 0) return cudaErrorMisalignedAddress;
     if (impl == 1) return launch_zsolve_blocked(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 2) return launch_zsolve_tpm(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 3) return launch_zsolve_lanediag(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (impl == 4) return launch_zsolve_gj(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
+    if (impl == 5) return launch_zsolve_sweep(N, q, MZ, Sig, logdet, gl, zsums, st, cond, chk);
     if (cond != nullptr || chk.gscale != nullptr) return cudaErrorNotSupported;   // the cross-check kernel has no guard
     switch (q) {
         case 8: return launch_zsolve_q<8>(N, MZ, Sig, logdet, gl, zsums, st);

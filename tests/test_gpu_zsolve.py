@@ -60,7 +60,7 @@ def _run(impl, q, A, eta, want_sig=True):
             zs.cpu().numpy()[:nblk * kw] if nblk else None, zoff)
 
 
-@pytest.mark.parametrize("impl", ["reg", "blocked", "tpm", "lanediag", "gj"])
+@pytest.mark.parametrize("impl", ["reg", "blocked", "tpm", "lanediag", "gj", "sweep"])
 @pytest.mark.parametrize("q,N", [(8, 1000), (16, 1), (16, 4099), (32, 2500), (32, 3), (64, 700), (64, 1)])
 def test_zsolve_matches_lapack(impl, q, N):
     if impl == "reg" and q == 64:
@@ -71,6 +71,8 @@ def test_zsolve_matches_lapack(impl, q, N):
         pytest.skip("the lane-parallel-diagonal kernel covers q >= 16")
     if impl == "gj" and q not in (16, 32):
         pytest.skip("the Gauss-Jordan kernel covers q = 16, 32")
+    if impl == "sweep" and q not in (16, 32, 64):
+        pytest.skip("the blocked-sweep kernel covers q = 16, 32, 64")
     A, eta = _case(N, q, seed=q + N, cond=1e4)
     out, sig, logdet, gl, zs, zoff = _run(impl, q, A, eta)
     ii, jj = np.tril_indices(q)
@@ -103,7 +105,7 @@ def test_zsolve_matches_lapack(impl, q, N):
         assert abs(tot[zoff + q + 1] - logdet.sum()) <= 1e-12 * abs(logdet.sum())
 
 
-@pytest.mark.parametrize("impl", ["reg", "blocked", "tpm", "lanediag", "gj"])
+@pytest.mark.parametrize("impl", ["reg", "blocked", "tpm", "lanediag", "gj", "sweep"])
 def test_zsolve_flags_non_pd(impl):
     q, N = 16, 64
     A, eta = _case(N, q, seed=5, cond=10.0)

@@ -10,7 +10,7 @@ dev = torch.device("cuda", 0)
 cases = [(16, 1000000), (32, 1000000), (64, 400000), (8, 1000000)]
 if len(sys.argv) > 2:
     cases = [(int(sys.argv[1]), int(sys.argv[2]))]
-impls = ["reg", "blocked", "tpm", "lanediag", "gj"] if len(sys.argv) <= 3 else [sys.argv[3]]
+impls = ["reg", "blocked", "tpm", "lanediag", "gj", "sweep"] if len(sys.argv) <= 3 else sys.argv[3:]   # "sweep:2,12,2" = PYVB_SWEEP
 for q, N in cases:
     P = q * (q + 1) // 2
     ld, zoff = int(lib.pyvb_mz_pitch(q)), int(lib.pyvb_gw_woff(q))
@@ -22,9 +22,13 @@ for q, N in cases:
     base[:, zoff:zoff + q] = torch.randn(N, q, generator=g, device=dev, dtype=torch.float64)
     logdet = torch.zeros(N, dtype=torch.float64, device=dev)
     gl = torch.zeros(144, dtype=torch.float64, device=dev)
-    for impl in impls:
+    for impl_cfg in impls:
+        impl, _, cfg = impl_cfg.partition(":")
+        os.environ.pop("PYVB_SWEEP", None)
+        if cfg:
+            os.environ["PYVB_SWEEP"] = cfg
         if (impl == "reg" and q == 64) or (impl == "tpm" and q > 16) or (impl == "lanediag" and q < 16) or \
-                (impl == "gj" and q not in (16, 32)):
+                (impl == "gj" and q not in (16, 32)) or (impl == "sweep" and q not in (16, 32, 64)):
             continue
         os.environ["PYVB_K2"] = impl
         nz = int(lib.pyvb_zsums_len(N, q))
@@ -43,5 +47,5 @@ for q, N in cases:
         ms = min(ts[1:])
         fl = N * (q ** 3 + 2.0 * q * q)
         by = N * 2.0 * (zoff + q) * 8
-        print("q=%d N=%d %-8s %.3f ms  %.2f TF/s  %.0f GB/s  nonpd=%g" % (q, N, impl, ms, fl / ms * 1e-9, by / ms * 1e-6,
+        print("q=%d N=%d %-14s %.3f ms  %.2f TF/s  %.0f GB/s  nonpd=%g" % (q, N, impl_cfg, ms, fl / ms * 1e-9, by / ms * 1e-6,
                                                                      float(gl[11])), flush=True)
