@@ -5,12 +5,14 @@ Gaussian.update (/root/reference/src/pyvb/nodes/gaussian.py:117-123).
 It follows the kernel step by step ON THE PACKED ROW as it lies in HBM / shared memory (lower triangle, element (i, j) at
 i (i + 1) / 2 + j; eta behind it): the 32 lanes of a warp are numpy vectors, a DMMA.8x8x4 is emulated from its fragment layout
 (lane l: a = A[l/4][l%4], b = B[l%4][l/4], c0/c1 = C[l/4][2 (l%4) + {0,1}]).  Per tile column K: the 8 x 8 pivot tiles of the
-warp's matrices inverted together by the scalar sweep (lane (m, r) = row r of matrix m's tile, published entries, deferred scaling),
--inv(M_KK) kept in place; the old panel tiles as A fragments, T_J = old_J inv(M_KK) on the emulated tensor core, written back in
-the symmetric sweep convention (+M_IK inv(M_KK); above the pivot tile into the slots of the transposed elements), the trailing
-update M_IJ += (-T_I) old_J^T of the lower tiles; then zbar = Sigma eta (lane = row) and
-<zz^T> = Sigma + zbar zbar^T tile by tile, from the state -Sigma.  A wrong fragment index, a missing mirror read or a read
-after an in-place write shows up here, on the CPU.  (One rounding per fused multiply-add is not modelled.)"""
+warp's matrices factored together, M_KK = L D L^T and X = L^-1 by elimination on [M_KK | I] (lane (m, r) = row r of matrix m's
+tile, one published column entry per lane and pivot plus the pivot lane's row of X), kept in the tile's own slots (X below the
+diagonal, 1 / d on it); the old panel tiles as A fragments, W_J = old_J X^T on the emulated tensor core, through the panel slots
+into A fragments, the new panel (W_J D^-1) X in the symmetric sweep convention (above the pivot tile into the slots of the
+transposed elements), the pivot tile -X^T D^-1 X, the trailing update M_IJ -= (W_I D^-1) W_J^T of the lower tiles; then
+zbar = Sigma eta (lane = row) and <zz^T> = Sigma + zbar zbar^T tile by tile, from the state -Sigma.  A wrong fragment index, a
+missing mirror read or a read after an in-place write shows up here, on the CPU.  (One rounding per fused multiply-add is not
+modelled.)"""
 import numpy as np
 
 LANE = np.arange(32)
@@ -37,8 +39,9 @@ def dmma(c0, c1, a, b):
 
 
 def pivot_tile(stg, q, K, mpw, pr, pos):
-    """8 x 8 pivot tiles K of the mpw matrices: M_KK <- -inv(M_KK) in place, lane (m, r) = row r of matrix m's tile (with
-    mpw < 4 the other lanes shadow a lane of the same row)"""
+    """8 x 8 pivot tiles K of the mpw matrices: M_KK = L D L^T by elimination without pivoting, X = L^-1 by the same eliminations
+    on the identity; lane (m, r) = row r of matrix m's tile (with mpw < 4 the other lanes shadow a lane of the same row).
+    Out, in the slots of the tile's lower triangle: X below the diagonal (its diagonal is 1), 1 / d on the diagonal."""
     pitch = mz_pitch(q)
     c0 = 8 * K
     m, r = (LANE >> 3) % mpw, LANE & 7
@@ -47,25 +50,36 @@ def pivot_tile(stg, q, K, mpw, pr, pos):
     a = np.empty((32, 8))
     for j in range(8):
         a[:, j] = np.where(j <= r, stg[base + tri(i) + c0 + np.minimum(j, r)], stg[base + tri(c0 + j) + i])
-    sinv = np.ones(32)
+    x = np.zeros((32, 8))
+    dinv = np.ones(32)
     for k in range(8):
         bc = np.full((mpw, 8), np.nan)
-        bc[m, r] = a[:, k] * sinv                                 # published (shadow lanes publish the same value)
-        B = bc[m]
+        bc[m, r] = a[:, k]                                        # column k of the reduced tile (rows >= k are current) = its row k
+        xk = np.zeros((mpw, 8))
+        w = r == k
+        xk[m[w]] = x[w]                                           # the pivot lane publishes its row of X (entries < k)
+        B, XK = bc[m], xk[m]
         rc = 1.0 / B[:, k]
-        piv = r == k
-        t = np.where(piv, 0.0, -a[:, k] * rc)
-        sinv = np.where(piv, -rc, sinv)
-        for j in range(8):
-            if j != k:
-                a[:, j] = a[:, j] + t * B[:, j]
-        a[:, k] = np.where(piv, 1.0, t)
+        dinv = np.where(r == k, rc, dinv)
+        l = np.where(r > k, a[:, k] * rc, 0.0)
+        for j in range(k + 1, 8):
+            a[:, j] = a[:, j] - l * B[:, j]
+        for j in range(k):
+            x[:, j] = x[:, j] - l * XK[:, j]
+        x[:, k] = -l
     act = (LANE >> 3) < mpw
-    pr *= np.where(act, -sinv, 1.0)
-    pos &= np.where(act, -sinv > 0.0, True)
+    pr *= np.where(act, dinv, 1.0)
+    pos &= np.where(act, dinv > 0.0, True)
     for j in range(8):
-        w = j <= r
-        stg[(base + tri(i) + c0 + j)[w]] = (a[:, j] * sinv)[w]
+        w = j < r
+        stg[(base + tri(i) + c0 + j)[w]] = x[:, j][w]
+    stg[base + tri(i) + c0 + r] = dinv
+
+
+def xfrag(st, c0, rr, cc):
+    """element (rr, cc) of the unit lower triangular X kept below the diagonal of pivot tile c0 (rr, cc local lane vectors)"""
+    v = st[tri(c0 + np.maximum(rr, cc)) + c0 + np.minimum(rr, cc)]
+    return np.where(rr > cc, v, np.where(rr == cc, 1.0, 0.0))
 
 
 def sweep_tile(stg, q, K, mpw, pr, pos):
@@ -80,38 +94,60 @@ def sweep_tile(stg, q, K, mpw, pr, pos):
             for h in range(2):
                 if J != K:
                     of[J, h] = (st[tri(8 * J + GID) + c0 + 4 * h + QD] if J > K else st[tri(c0 + 4 * h + QD) + 8 * J + GID]).copy()
-        pb = []
-        for h in range(2):
-            rr, cc = c0 + 4 * h + QD, c0 + GID
-            pb.append(st[tri(np.maximum(rr, cc)) + np.minimum(rr, cc)].copy())
-        nt = {}
+        xa = [xfrag(st, c0, GID, 4 * h + QD) for h in range(2)]           # X[gid][4h + qd]: A fragment of X = B fragment of X^T
+        xb = [xfrag(st, c0, 4 * h + QD, GID) for h in range(2)]           # X[4h + qd][gid]: B fragment of X = A fragment of X^T
+        dk = [st[tri(c0 + 4 * h + QD) + c0 + 4 * h + QD].copy() for h in range(2)]   # 1 / d_k, k = 4h + qd
+        # W_J = old_J X^T
+        wt = {}
         for J in range(nbt):
             if J != K:
-                c = dmma(np.zeros(32), np.zeros(32), of[J, 0], pb[0])
-                nt[J] = dmma(c[0], c[1], of[J, 1], pb[1])
+                c = dmma(np.zeros(32), np.zeros(32), of[J, 0], xa[0])
+                wt[J] = dmma(c[0], c[1], of[J, 1], xa[1])
+        # the pivot tile: -inv(M_KK) = -X^T D^-1 X
+        c = dmma(np.zeros(32), np.zeros(32), xb[0], xb[0] * dk[0])
+        pv = dmma(c[0], c[1], xb[1], xb[1] * dk[1])
+        for e in range(2):
+            w = 2 * QD + e <= GID
+            st[(tri(c0 + GID) + c0 + 2 * QD + e)[w]] = -pv[e][w]
+        # W into the panel slots (for the change of layout), back as A fragments
         for J in range(nbt):
             if J == K:
                 continue
             if J > K:
                 o = tri(8 * J + GID) + c0 + 2 * QD
-                st[o] = -nt[J][0]
-                st[o + 1] = -nt[J][1]
+                st[o] = wt[J][0]
+                st[o + 1] = wt[J][1]
             else:
-                st[tri(c0 + 2 * QD) + 8 * J + GID] = -nt[J][0]
-                st[tri(c0 + 2 * QD + 1) + 8 * J + GID] = -nt[J][1]
-        ta = {}
+                st[tri(c0 + 2 * QD) + 8 * J + GID] = wt[J][0]
+                st[tri(c0 + 2 * QD + 1) + 8 * J + GID] = wt[J][1]
+        wa, wd = {}, {}
         for I in range(nbt):
             for h in range(2):
                 if I != K:
-                    ta[I, h] = -(st[tri(8 * I + GID) + c0 + 4 * h + QD] if I > K else st[tri(c0 + 4 * h + QD) + 8 * I + GID])
+                    wa[I, h] = (st[tri(8 * I + GID) + c0 + 4 * h + QD] if I > K else st[tri(c0 + 4 * h + QD) + 8 * I + GID]).copy()
+                    wd[I, h] = wa[I, h] * dk[h]
+        # T_J = (W_J D^-1) X into the panel slots (sweep convention: +M_JK inv(M_KK))
+        for J in range(nbt):
+            if J == K:
+                continue
+            c = dmma(np.zeros(32), np.zeros(32), wd[J, 0], xb[0])
+            tt = dmma(c[0], c[1], wd[J, 1], xb[1])
+            if J > K:
+                o = tri(8 * J + GID) + c0 + 2 * QD
+                st[o] = tt[0]
+                st[o + 1] = tt[1]
+            else:
+                st[tri(c0 + 2 * QD) + 8 * J + GID] = tt[0]
+                st[tri(c0 + 2 * QD + 1) + 8 * J + GID] = tt[1]
+        # trailing update: M_IJ -= (W_I D^-1) W_J^T, lower tiles outside row / column K
         for I in range(nbt):
             for J in range(I + 1):
                 if I == K or J == K:
                     continue
                 o = tri(8 * I + GID) + 8 * J + 2 * QD
                 c0v, c1v = st[o].copy(), st[o + 1].copy()         # (upper half of a diagonal tile: junk, never stored)
-                c0v, c1v = dmma(c0v, c1v, ta[I, 0], of[J, 0])
-                c0v, c1v = dmma(c0v, c1v, ta[I, 1], of[J, 1])
+                c0v, c1v = dmma(c0v, c1v, -wd[I, 0], wa[J, 0])
+                c0v, c1v = dmma(c0v, c1v, -wd[I, 1], wa[J, 1])
                 w0 = np.ones(32, bool) if I > J else (2 * QD <= GID)
                 w1 = np.ones(32, bool) if I > J else (2 * QD + 1 <= GID)
                 st[o[w0]] = c0v[w0]

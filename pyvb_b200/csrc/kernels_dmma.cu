@@ -666,9 +666,10 @@ int k2_impl(int q) {
     if (mode == 5 && q != 16 && q != 32 && q != 64) mode = -1;
     if (mode >= 0) return mode;
     if (q == 16 || q == 32) return 4;
-    // (5, the blocked sweep of kernels_k2s.cu, is as fast as the blocked Cholesky kernel at q = 64 and leaves the column sums, which
-    //  saves the mzpart pass: 24.1 -> 22.1 ms per sweep at the config-4 shape -- but its explicit 8 x 8 pivot-tile inverses cost accuracy
-    //  on ill-conditioned rows: 1.0e-8 on Zbar in test_ard_modeB_vs_oracle[(600, 64, 64)], where D < q.  Opt-in only: PYVB_K2=sweep.)
+    // q = 64: the blocked sweep (kernels_k2s.cu).  As K2 alone it is 7 % slower than the blocked Cholesky kernel (13.2 vs 12.4 ms per 400k
+    // rows), but it leaves the column sums / maxima, which saves the statistics' extra pass over the MZ rows: 24.1 -> 23.5 ms per sweep
+    // at the config-4 shape.  (q = 32: 7.0 vs 5.7 ms for the Gauss-Jordan kernel: not there.)
+    if (q == 64) return 5;
     return q >= 32 ? 1 : 2;      // (the lane-parallel-diagonal kernel, 3, is not faster: 7.7 vs 7.4 ms at q = 32)
 }
 int k2_impl_f32(int q) {

@@ -1,5 +1,5 @@
-// K2 as a BLOCKED symmetric sweep: scalar panel elimination + FP64 tensor-core trailing update, IN PLACE in the packed rows as
-// they lie in HBM.
+// K2 as a BLOCKED symmetric sweep: 8 x 8 pivot tiles factored by scalar elimination, everything else on the FP64 tensor cores,
+// IN PLACE in the packed rows as they lie in HBM.
 //
 // Replaces cho_factor / cho_solve(., I) / dot(qcov, .) / q_ln_det of Gaussian.update (nodes/gaussian.py:117-123).
 //
@@ -11,21 +11,25 @@
 //
 // which keeps the state symmetric, so that only the lower triangle exists, every intermediate overwrites the slots of the block
 // it replaces (element (i, j), i >= j, at i (i + 1) / 2 + j: the HBM layout; a reader of the upper half swaps the indices) and
-// after q / 8 sweeps the row holds -Sigma:
+// after q / 8 sweeps the row holds -Sigma.  inv(M_KK) is only ever applied in FACTORED form, M_KK = L D L^T, X = L^-1:
 //
-//   panel   q x 8 column block K in ROW layout (lane = row): the scalar sweep of kernels_k2g.cu over its 8 pivots -- the tile
-//           rows publish one entry each per pivot, every row adds t_i b_j over the 8 columns: 8 q^2 FMA per matrix instead of q^3.
-//           The multipliers come from 1 x 1 pivots exactly as in the unblocked elimination: NO explicit inverse of a block is
-//           ever applied (a recursive Schur-complement version with explicit 8 x 8 / 16 x 16 inverses was 10 - 400 x less
-//           accurate than the Cholesky route at cond 1e4 - 1e6 in the lane-level restatement and was dropped);
-//   update  M_IJ += (-T_I) old_J^T for the lower tiles outside row / column K: DMMA.8x8x4, 256 FMA per issue slot.  The A
-//           fragment of T_I and the B fragment of old_J^T (= the A fragment of the old panel tile, read before the panel is
-//           overwritten) are plain LDS.64 from the packed rows, the accumulators go back with STS.64.
+//   pivot   the 8 x 8 pivot tiles of the warp's MPW matrices together, lane (m, r) = row r of matrix m's tile: elimination without
+//           pivoting on [M_KK | I] gives D and X (one published column entry per lane and pivot, the pivot lane's row of X);
+//   panel   W_J = old_J X^T  and the new panel  M_JK <- (W_J D^-1) X;   pivot tile  M_KK <- -X^T D^-1 X;
+//   update  M_IJ -= (W_I D^-1) W_J^T  for the lower tiles outside row / column K
+//
+// -- all DMMA.8x8x4 (256 FMA per issue slot).  This is block Cholesky (||W D^-1/2||^2 <= ||M||): as stable as the unblocked
+// elimination.  (The first version applied the explicit inverse of the pivot tile, T_J = old_J inv(M_KK), M_IJ -= T_I old_J^T:
+// block LU, 4 - 22 x the error of the Cholesky route at q = 32 and cond 1e4 - 1e6, 1e-8 on a rank-deficient q = 64 case; a
+// recursive Schur-complement version with explicit 16 x 16 / 32 x 32 inverses was 400 x worse.  Both were found and measured in
+// the lane-level restatement, oracle/sweep_oracle.py, before / beside the GPU runs.)
+// Operand fragments are plain LDS.64 from the packed rows -- an A fragment of a tile is the B fragment of its transpose, so W^T
+// and the tiles above the pivot tile need no transposition pass -- accumulators go back with STS.64; W crosses shared memory
+// once (accumulator layout -> A fragments) through the panel slots it is about to vacate.
 //
 // ln prod diag chol = 1/2 sum ln(pivots): the pivots are those of the unblocked elimination.  zbar = Sigma eta: lane = row,
 // symmetric reads.  <zz^T> = Sigma + zbar zbar^T: tile by tile in the accumulator layout.  Column sums / maxima bounds /
-// log-det scalars per CTA as in the other K2 kernels (partial layout of the blocked kernel).  oracle/sweep_oracle.py restates
-// the kernel lane by lane on the packed row.
+// log-det scalars per CTA as in the other K2 kernels (partial layout of the blocked kernel).
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -51,7 +55,7 @@ template <int Q, int MPW_, int WARPS_, int STAGES_, int UM_> struct SB {
     static constexpr int P = s_tri(Q), PP = (P + 7) & ~7, OROW = PP + Q, PITCH = s_pitch(Q);
     static constexpr int KW = 2 * OROW + PYVB_ZS_EXTRA;       // [column sums OROW | 4 scalars | bounds on the column maxima OROW]
     static constexpr int STAGE_D = MPW * PITCH;               // the rows of a group as they lie in HBM
-    static constexpr int BC_D = 2 * MPW * 8;                  // published pivot columns of the diagonal sweep, two parities
+    static constexpr int BC_D = 2 * MPW * 16;                 // published column + X row per pivot of the diagonal tiles, two parities
     static constexpr int NTR = (Q > 32) ? Q / 32 : 1;         // rows of the maxima a lane tracks
     static constexpr int WARP_D = STAGES * STAGE_D + BC_D + OROW + 4 + 2 * Q + 2;   // stages | .. | csum | scalars | maxima | mbarriers
     static constexpr size_t SMEM = (size_t)WARPS * WARP_D * 8;
@@ -70,54 +74,77 @@ __device__ __forceinline__ double s_rcp(double d) {
     return fma(r, e, r);
 }
 
-// ---- 8 x 8 pivot tiles K of the warp's MPW matrices: M_KK <- -inv(M_KK) in place, lane (m, r) = row r of matrix m's tile (with
-// MPW < 4 the other lanes shadow a lane of the same row: same arithmetic, same stores).  The sweep of kernels_k2g.cu at q = 8:
-// every lane publishes  b_i = a[i][k] s_i  (s_i = 1 before row i's pivot, -1 / d_i after it), a[i][j] += t_i b_j  with
-// t_i = -a[i][k] / d_k;  the pivot row keeps t = 0 and gets a 1 in column k, its scaling by 1 / d_k is deferred to the end.
+// ---- 8 x 8 pivot tiles K of the warp's MPW matrices: M_KK = L D L^T by elimination without pivoting and X = L^-1 by the same
+// eliminations on the identity, lane (m, r) = row r of matrix m's tile (with MPW < 4 the other lanes shadow a lane of the same
+// row: same arithmetic, same stores).  Per pivot k every lane publishes its entry of column k (= row k of the reduced tile, by
+// symmetry) and the pivot lane its row of X; rows r > k subtract l_rk times both.  Out, in the slots of the tile's lower
+// triangle: X below the diagonal (its diagonal is 1), 1 / d on the diagonal.
 template <int K, typename T>
 __device__ __forceinline__ void s_pivot_tile(double *stg, double *bc, int lane, double &pr, bool &pos) {
     constexpr int C0 = 8 * K;
     const int m = (lane >> 3) % T::MPW, r = lane & 7;
     double *st = stg + m * T::PITCH;
     const int i = C0 + r;
-    double a[8];
+    double a[8], x[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = (j <= r) ? st[s_tri(i) + C0 + j] : st[s_tri(C0 + j) + i];
-    double sinv = 1.0;
+    for (int j = 0; j < 8; ++j) {
+        a[j] = (j <= r) ? st[s_tri(i) + C0 + j] : st[s_tri(C0 + j) + i];
+        x[j] = 0.0;
+    }
+    double dinv = 1.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        double *b = bc + (k & 1) * (T::MPW * 8) + m * 8;
-        b[r] = a[k] * sinv;
-        __syncwarp();
-        double B[8];
+        double *b = bc + (k & 1) * (T::MPW * 16) + m * 16;      // [column k of the reduced tile (8) | row k of X (8)]
+        b[r] = a[k];
+        if (r == k) {
 #pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) {
+            for (int j = 0; j < k; ++j) b[8 + j] = x[j];
+        }
+        __syncwarp();
+        double B[8], XK[8];
+#pragma unroll
+        for (int j2 = k / 2; j2 < 4; ++j2) {
             const double2 v = *reinterpret_cast<const double2 *>(b + 2 * j2);
             B[2 * j2] = v.x;
             B[2 * j2 + 1] = v.y;
         }
-        const double rc = s_rcp(B[k]);
-        const bool piv = (r == k);
-        double t = -a[k] * rc;
-        t = piv ? 0.0 : t;
-        sinv = piv ? -rc : sinv;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j != k) a[j] = fma(t, B[j], a[j]);
-        a[k] = piv ? 1.0 : t;
+        for (int j2 = 0; j2 < (k + 1) / 2; ++j2) {
+            const double2 v = *reinterpret_cast<const double2 *>(b + 8 + 2 * j2);
+            XK[2 * j2] = v.x;
+            XK[2 * j2 + 1] = v.y;
+        }
+        const double rc = s_rcp(B[k]);
+        dinv = (r == k) ? rc : dinv;
+        const double l = (r > k) ? a[k] * rc : 0.0;
+#pragma unroll
+        for (int j = k + 1; j < 8; ++j) a[j] = fma(-l, B[j], a[j]);
+#pragma unroll
+        for (int j = 0; j < k; ++j) x[j] = fma(-l, XK[j], x[j]);
+        x[k] = -l;
     }
     if ((lane >> 3) < T::MPW) {
-        pr *= -sinv;                                            // 1 / d_r
-        pos = pos && (-sinv > 0.0);
+        pr *= dinv;                                             // 1 / d_r
+        pos = pos && (dinv > 0.0);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        if (j <= r) st[s_tri(i) + C0 + j] = a[j] * sinv;        // row r of inv(M_KK) is a[] (-sinv): the state keeps MINUS the inverse
+        if (j < r) st[s_tri(i) + C0 + j] = x[j];
+    st[s_tri(i) + i] = dinv;
     __syncwarp();
 }
 
+// element (rr, cc) of the unit lower triangular X kept below the diagonal of pivot tile C0
+__device__ __forceinline__ double s_xfrag(const double *st, int C0, int rr, int cc) {
+    const int hi = rr > cc ? rr : cc, lo = rr > cc ? cc : rr;
+    const double v = st[s_tri(C0 + hi) + C0 + lo];
+    return rr > cc ? v : (rr == cc ? 1.0 : 0.0);
+}
+
 // ---- sweep of tile column K of the warp's MPW matrices, everything in place.  In: the symmetric sweep state M (lower triangle).
-// Out:   M_KK <- -inv(M_KK),   M_IK <- M_IK inv(M_KK),   M_IJ <- M_IJ - M_IK inv(M_KK) M_KJ      (I, J != K).
+// Out:   M_KK <- -inv(M_KK),   M_IK <- M_IK inv(M_KK),   M_IJ <- M_IJ - M_IK inv(M_KK) M_KJ      (I, J != K),
+// with inv(M_KK) only ever applied in its FACTORED form X^T D^-1 X (block Cholesky: as stable as the unblocked elimination):
+//   W_J = old_J X^T,    M_IJ -= (W_I D^-1) W_J^T,    M_JK <- (W_J D^-1) X,    M_KK <- -X^T D^-1 X.
 template <int K, typename T>
 __device__ __forceinline__ void s_sweep_tile(double *stg, double *bc, int lane, double &pr, bool &pos) {
     constexpr int NBT = T::NBT, C0 = 8 * K;
@@ -126,7 +153,7 @@ __device__ __forceinline__ void s_sweep_tile(double *stg, double *bc, int lane, 
 #pragma unroll(T::UM)
     for (int m = 0; m < T::MPW; ++m) {
         double *st = stg + m * T::PITCH;
-        // A fragments of the OLD panel tiles (J, K), J != K (== B fragments of their transposes)
+        // A fragments of the OLD panel tiles (J, K), J != K
         double of[NBT][2];
 #pragma unroll
         for (int J = 0; J < NBT; ++J)
@@ -135,55 +162,82 @@ __device__ __forceinline__ void s_sweep_tile(double *stg, double *bc, int lane, 
                 if (J == K) continue;
                 of[J][h] = (J > K) ? st[s_tri(8 * J + gid) + C0 + 4 * h + qd] : st[s_tri(C0 + 4 * h + qd) + 8 * J + gid];
             }
-        // B fragments of -inv(M_KK) (symmetric: the stored lower half serves both)
-        double pb[2];
+        // X[gid][4h + qd] (A fragment of X = B fragment of X^T), X[4h + qd][gid] (B fragment of X = A fragment of X^T), 1 / d_(4h + qd)
+        double xa[2], xb[2], dk[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const int rr = C0 + 4 * h + qd, cc = C0 + gid;
-            pb[h] = (rr >= cc) ? st[s_tri(rr) + cc] : st[s_tri(cc) + rr];
+            xa[h] = s_xfrag(st, C0, gid, 4 * h + qd);
+            xb[h] = s_xfrag(st, C0, 4 * h + qd, gid);
+            dk[h] = st[s_tri(C0 + 4 * h + qd) + C0 + 4 * h + qd];
         }
-        // -T_J = old_J (-inv(M_KK))
-        double nt[NBT][2];
+        // W_J = old_J X^T
+        double wt[NBT][2];
 #pragma unroll
         for (int J = 0; J < NBT; ++J) {
             if (J == K) continue;
-            nt[J][0] = nt[J][1] = 0.0;
-            dmma884(nt[J][0], nt[J][1], of[J][0], pb[0]);
-            dmma884(nt[J][0], nt[J][1], of[J][1], pb[1]);
+            wt[J][0] = wt[J][1] = 0.0;
+            dmma884(wt[J][0], wt[J][1], of[J][0], xa[0]);
+            dmma884(wt[J][0], wt[J][1], of[J][1], xa[1]);
         }
-        __syncwarp();                                           // every lane has read the old panel
+        // the pivot tile: X^T D^-1 X
+        double pv0 = 0.0, pv1 = 0.0;
+        dmma884(pv0, pv1, xb[0], xb[0] * dk[0]);
+        dmma884(pv0, pv1, xb[1], xb[1] * dk[1]);
+        __syncwarp();                                           // every lane has read the old panel and X
+        if (2 * qd <= gid) st[s_tri(C0 + gid) + C0 + 2 * qd] = -pv0;
+        if (2 * qd + 1 <= gid) st[s_tri(C0 + gid) + C0 + 2 * qd + 1] = -pv1;
+        // W through the panel slots (the change of layout), back as A fragments (== B fragments of W^T)
 #pragma unroll
         for (int J = 0; J < NBT; ++J) {
             if (J == K) continue;
             if (J > K) {
                 double *o = st + s_tri(8 * J + gid) + C0 + 2 * qd;
-                o[0] = -nt[J][0];
-                o[1] = -nt[J][1];
+                o[0] = wt[J][0];
+                o[1] = wt[J][1];
             } else {                                            // above the pivot tile: the slot of the transposed element
-                st[s_tri(C0 + 2 * qd) + 8 * J + gid] = -nt[J][0];
-                st[s_tri(C0 + 2 * qd + 1) + 8 * J + gid] = -nt[J][1];
+                st[s_tri(C0 + 2 * qd) + 8 * J + gid] = wt[J][0];
+                st[s_tri(C0 + 2 * qd + 1) + 8 * J + gid] = wt[J][1];
             }
         }
         __syncwarp();
-        // trailing update on the tensor cores: M_IJ += (-T_I) old_J^T for the lower tiles I >= J, I, J != K
-        double ta[NBT][2];
+        double wa[NBT][2], wd[NBT][2];
 #pragma unroll
         for (int I = 0; I < NBT; ++I)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (I == K) continue;
-                ta[I][h] = -((I > K) ? st[s_tri(8 * I + gid) + C0 + 4 * h + qd] : st[s_tri(C0 + 4 * h + qd) + 8 * I + gid]);
+                wa[I][h] = (I > K) ? st[s_tri(8 * I + gid) + C0 + 4 * h + qd] : st[s_tri(C0 + 4 * h + qd) + 8 * I + gid];
+                wd[I][h] = wa[I][h] * dk[h];
             }
+        __syncwarp();                                           // every lane has read W
+        // the new panel (sweep convention): M_JK <- (W_J D^-1) X
+#pragma unroll
+        for (int J = 0; J < NBT; ++J) {
+            if (J == K) continue;
+            double t0 = 0.0, t1 = 0.0;
+            dmma884(t0, t1, wd[J][0], xb[0]);
+            dmma884(t0, t1, wd[J][1], xb[1]);
+            if (J > K) {
+                double *o = st + s_tri(8 * J + gid) + C0 + 2 * qd;
+                o[0] = t0;
+                o[1] = t1;
+            } else {
+                st[s_tri(C0 + 2 * qd) + 8 * J + gid] = t0;
+                st[s_tri(C0 + 2 * qd + 1) + 8 * J + gid] = t1;
+            }
+        }
+        // trailing update on the tensor cores: M_IJ -= (W_I D^-1) W_J^T for the lower tiles I >= J, I, J != K
 #pragma unroll
         for (int I = 0; I < NBT; ++I) {
             if (I == K) continue;
+            const double na0 = -wd[I][0], na1 = -wd[I][1];
 #pragma unroll
             for (int J = 0; J <= I; ++J) {
                 if (J == K) continue;
                 double *o = st + s_tri(8 * I + gid) + 8 * J + 2 * qd;
                 double c0 = o[0], c1 = o[1];                    // (a diagonal tile: the upper half is junk that is never stored)
-                dmma884(c0, c1, ta[I][0], of[J][0]);
-                dmma884(c0, c1, ta[I][1], of[J][1]);
+                dmma884(c0, c1, na0, wa[J][0]);
+                dmma884(c0, c1, na1, wa[J][1]);
                 if (I > J || 2 * qd <= gid) o[0] = c0;
                 if (I > J || 2 * qd + 1 <= gid) o[1] = c1;
             }
@@ -460,7 +514,7 @@ cudaError_t launch_sweep_cfg(long long N, double *MZ, double *Sig, double *logde
 void sweep_config(int q, int &mpw, int &warps, int &stages, int &um) {
     if (q == 16) mpw = 4, warps = 16, stages = 2, um = 4;
     else if (q == 32) mpw = 4, warps = 8, stages = 1, um = 4;
-    else mpw = 1, warps = 6, stages = 1, um = 1;
+    else mpw = 2, warps = 4, stages = 1, um = 1;
     const char *e = getenv("PYVB_SWEEP");
     int a = 0, b = 0, c = 0, d = 0;
     if (e && sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4) {
@@ -483,7 +537,7 @@ int zsolve_sweep_blocks(long long N, int q) {
 }
 
 int zsolve_sweep_kw(int q) {
-    return q == 16 ? SB<16, 4, 16, 2, 4>::KW : q == 32 ? SB<32, 4, 8, 1, 4>::KW : q == 64 ? SB<64, 1, 6, 1, 1>::KW : 0;
+    return q == 16 ? SB<16, 4, 16, 2, 4>::KW : q == 32 ? SB<32, 4, 8, 1, 4>::KW : q == 64 ? SB<64, 2, 4, 1, 1>::KW : 0;
 }
 
 cudaError_t launch_zsolve_sweep(long long N, int q, double *MZ, double *Sig, double *logdet, double *gl, double *zsums,
