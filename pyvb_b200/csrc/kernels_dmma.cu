@@ -666,9 +666,9 @@ int k2_impl(int q) {
     if (mode == 5 && q != 16 && q != 32 && q != 64) mode = -1;
     if (mode >= 0) return mode;
     if (q == 16 || q == 32) return 4;
-    // q = 64: the blocked sweep (kernels_k2s.cu).  As K2 alone it is 7 % slower than the blocked Cholesky kernel (13.2 vs 12.4 ms per 400k
-    // rows), but it leaves the column sums / maxima, which saves the statistics' extra pass over the MZ rows: 24.1 -> 23.5 ms per sweep
-    // at the config-4 shape.  (q = 32: 7.0 vs 5.7 ms for the Gauss-Jordan kernel: not there.)
+    // q = 64: the blocked sweep on swizzled tiles (kernels_k2s.cu): 11.4 ms per 400k rows against 12.3 for the blocked Cholesky kernel,
+    // and it leaves the column sums / maxima, which saves the statistics' extra pass over the MZ rows: 24.1 -> 21.4 ms per sweep at the
+    // config-4 shape.  (q = 32: 6.0 vs 5.5 ms for the Gauss-Jordan kernel, q = 16: 1.4 vs 0.6: not there.)
     if (q == 64) return 5;
     return q >= 32 ? 1 : 2;      // (the lane-parallel-diagonal kernel, 3, is not faster: 7.7 vs 7.4 ms at q = 32)
 }

@@ -13,6 +13,7 @@ from scipy.linalg import cho_factor, cho_solve
 
 from helpers import tensor_rel
 from oracle.sweep_oracle import sweep_solve
+from oracle.tsweep_oracle import tsweep_solve
 
 
 def _case(N, q, seed, cond):
@@ -24,16 +25,17 @@ def _case(N, q, seed, cond):
     return 0.02 * A + (Qm * s) @ Qm.T, rng.randn(N, q) * 3.0
 
 
+@pytest.mark.parametrize("layout", ["packed", "tiles"])
 @pytest.mark.parametrize("q", [8, 16, 32, 64])
 @pytest.mark.parametrize("cond", [1e2, 1e4, 1e6])
-def test_blocked_sweep_is_as_accurate_as_the_cholesky_route(q, cond):
+def test_blocked_sweep_is_as_accurate_as_the_cholesky_route(q, cond, layout):
     A, eta = _case(9, q, seed=q, cond=cond)                      # (9: the last group is ragged)
     Al = A.astype(np.longdouble)
     X = np.linalg.inv(A).astype(np.longdouble)
     for _ in range(3):                                           # Newton refinement in extended precision
         X = X + X @ (np.eye(q, dtype=np.longdouble) - Al @ X)
     ref = np.stack([cho_solve(cho_factor(a), np.eye(q)) for a in A])
-    Sg, z, ld, M2 = sweep_solve(A, eta, mpw=1 if q == 64 else 4)
+    Sg, z, ld, M2 = (sweep_solve if layout == "packed" else tsweep_solve)(A, eta, mpw=(1 if layout == "packed" else 2) if q == 64 else 4)
     e_ref, e_s = tensor_rel(ref, X), tensor_rel(Sg, X)
     assert e_s < 4 * e_ref + 1e-15, (e_s, e_ref)
     assert tensor_rel(Sg, ref) < 50 * cond * 1.2e-16
