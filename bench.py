@@ -13,7 +13,8 @@ sweep (W columns, Z rows, Mu, Beta, ELBO) over the shard.
 Besides the headline the line carries: `parity` (N = 1: the benchmarked kernels against the CPU oracle, ELBO and state
 relative errors = BASELINE.json's "ELBO rel err vs ref"), `multi_gpu_check` (N > 1: a fixed global problem sharded over the
 ranks against the oracle, both exchanges, bit-identity of the replicas), `c3_shard` (BASELINE.json configs[2] at one GPU's
-share of its rows, 1.25M x 1024, q = 32: with --gpus 8 this is config 3 itself), `dmma_variant` / `f32_variant` /
+share of its rows, 1.25M x 1024, q = 32: with --gpus 8 this is config 3 itself), `c4_shape` (N = 1: the shape of configs[3],
+ARD, D = 512, q = 64, at 400k rows: the q = 64 kernels), `dmma_variant` / `f32_variant` /
 `variant_elbo` (the all-FP64-tensor-core and the FP32 tcgen05 sweeps on the same shard, same sweep counts), `cpu_baseline`.
 """
 import argparse
@@ -328,7 +329,9 @@ def rooflines(eng, kt, rows, ms_sweep, hbm, peak_tf, traffic_json):
                   (rows * (8.0 * (P + q) + 7.0 * ncz + 1.0 * D + 7.0 * ncz + 8.0 * D + 8.0 * q), kt["stats_ms"])}
         table = {k: {"ms": v[1], "algorithmic_GB": v[0] * 1e-9, "GBps": v[0] / (v[1] * 1e-3) * 1e-9,
                      "frac_of_hbm_peak": v[0] / (v[1] * 1e-3) * 1e-9 / hbm} for k, v in by.items()}
-        kname = "zsolve (K2: batched q x q SPD inverse / solve, in place on the MZ rows; Gauss-Jordan in registers at q = 16, 32)"
+        kname = ("zsolve (K2: batched q x q SPD inverse / solve, in place on the MZ rows; Gauss-Jordan in registers at q = 16, 32)"
+                 if q != 64 else
+                 "zsolve (K2: batched q x q SPD inverse / solve, in place on the MZ rows; blocked symmetric sweep on DMMA at q = 64)")
         by_dom, ms_dom = rows * (16.0 * (P + q) + 8.0), kt["zsolve_k2_ms"]
         traffic = None
         t = traffic_json.get("zsolve%d_dram_bytes_per_row" % q)
@@ -729,6 +732,20 @@ def run_ours(a):
         except Exception as ex:  # pragma: no cover
             extra["c3_shard"] = {"error": repr(ex)}
 
+    # ---- the shape of BASELINE.json configs[3] (ARD, D = 512, q = 64, 30 % missing) at 400k rows: the q = 64 kernels under the same clock
+    if world == 1 and not a.quick and not a.no_c4 and a.mode == "B":
+        try:
+            c4 = {"N": 400000, "D": 512, "q": 64, "missing": 0.3, "algo": a.algo, "ard": True}
+            e4, r4, _ = measure_config(torch, dist, dev, rank, world, local, lib, _cabi, c4, max(3, min(a.steps, 10)), 3,
+                                       None, hbm, peak_tf, traffic_json)
+            r4["workload"] = "VB-PCA missing data with ARD N=400000 D=512 q=64 30% missing FP64 mode=B"
+            e4.close()
+            del e4
+            torch.cuda.empty_cache()
+            extra["c4_shape"] = r4
+        except Exception as ex:  # pragma: no cover
+            extra["c4_shape"] = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -765,6 +782,7 @@ def main():
     ap.add_argument("--no-f32", action="store_true", help="skip the FP32-variant leg")
     ap.add_argument("--no-c3", action="store_true", help="skip the config-3 shard leg")
     ap.add_argument("--quick", action="store_true", help="headline + e2e only (profiling runs)")
+    ap.add_argument("--no-c4", dest="no_c4", action="store_true", help="skip the config-4-shape object (q = 64, ARD)")
     ap.add_argument("--ard", action="store_true", help="ARD Gamma precisions per latent column (config 4)")
     a = ap.parse_args()
     if a.impl == "reference":
