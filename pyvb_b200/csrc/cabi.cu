@@ -123,6 +123,12 @@ size_t pyvb_zsums_len(long long N, int q) {
         int nblk, kw;
         zsolve_partials_of(impl, N, q, nblk, kw);
         if ((size_t)nblk * kw > len) len = (size_t)nblk * kw;
+        // the Gauss-Jordan and blocked-sweep kernels run one CTA per SM at most, but how many rows a CTA takes depends on the
+        // configuration picked by PYVB_GJ / PYVB_SWEEP, which is also read per call: size for the worst case
+        if ((impl == 4 || impl == 5) && kw > 0) {
+            const size_t worst = (size_t)(N < 148 ? (N < 1 ? 1 : N) : 148) * kw;
+            if (worst > len) len = worst;
+        }
     }
     return len;
 }

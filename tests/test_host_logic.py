@@ -137,6 +137,29 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_cabi.Consts) == 14 * 8 + 8
 
 
+def test_zsums_buffer_covers_every_k2_kernel_and_configuration(monkeypatch):
+    """The engine sizes the K2 partial buffer once (pyvb_zsums_len) while PYVB_K2 / PYVB_GJ / PYVB_SWEEP are read per call: whatever
+    kernel and configuration a later call picks must fit (no compute: size queries only)."""
+    from pyvb_b200 import _cabi
+    L = _cabi.lib()
+    envs = [{}] + [{"PYVB_K2": k} for k in ("reg", "blocked", "tpm", "lanediag", "gj", "sweep")] + \
+           [{"PYVB_K2": "sweep", "PYVB_SWEEP": c} for c in ("1,6,1,1", "2,4,1,1", "4,8,1,4", "2,12,1,1", "4,12,2,4")] + \
+           [{"PYVB_K2": "sweep", "PYVB_SWEEP_TILED": "0", "PYVB_SWEEP": c} for c in ("2,15,1,1", "4,16,2,4", "1,6,1,1")] + \
+           [{"PYVB_K2": "gj", "PYVB_GJ": c} for c in ("2,16", "1,12")]
+    for q in (8, 16, 32, 64):
+        for N in (1, 7, 100, 1000, 40000, 1000000):
+            for k in ("PYVB_K2", "PYVB_GJ", "PYVB_SWEEP", "PYVB_SWEEP_TILED"):
+                monkeypatch.delenv(k, raising=False)
+            size = L.pyvb_zsums_len(N, q)
+            for env in envs:
+                for k in ("PYVB_K2", "PYVB_GJ", "PYVB_SWEEP", "PYVB_SWEEP_TILED"):
+                    monkeypatch.delenv(k, raising=False)
+                for k, v in env.items():
+                    monkeypatch.setenv(k, v)
+                need = L.pyvb_zsums_blocks(N, q) * L.pyvb_zsums_kw(q)
+                assert need <= size, (q, N, env, need, size)
+
+
 def test_engine_refuses_to_run_without_gpu():
     import torch
     if torch.cuda.is_available():
